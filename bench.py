@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the WCSPH per-timestep hot path (neighbour build -> forces -> integration).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one full predictor-corrector time step (2 force evaluations + 2 integrations, plus a
+neighbour-list rebuild every 10th step like the reference, src/Integrator.cc:85-91).
+Metric (BASELINE.json): million particle-interactions per second,
+    MIPS = numInteractions x 2 x steps / seconds / 1e6          
+where numInteractions is the neighbour-list entry count the neighbour engine itself reports; the
+particle-updates/s figure (the reference's own MIPPS x 1e6) is printed alongside.
+
+Prints ONE JSON line (rank 0). See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, args) — BASELINE.json configs; see SURVEY.md section 6.2 for what they resolve to
+    "dambreak2m": ("dambreak", dict(dp=0.0043)),     # configs[1]: DamBreak3D ~2M particles, Ferrari
+    "dambreak8m": ("dambreak", dict(dp=0.0026)),     # headline target size
+    "dambreak84k": ("dambreak", dict(dp=0.015)),     # configs[0]: the reference's default
+    "lattice8m": ("lattice", dict(n=200)),           # configs[2]
+    "lattice2m": ("lattice", dict(n=126)),
+    "lattice85k": ("lattice", dict(n=44)),
+}
+FORCES_BYTES_PER_PARTICLE = 60      # R pos16+vel16+info8+hash4, W forces16
+L2_BYTES = 126 * 1024 * 1024
+
+
+def make_problem(name):
+    from gpusph_b200 import capi
+    from gpusph_b200.problems import dambreak_problem, lattice_problem
+    kind, kw = WORKLOADS[name]
+    if kind == "dambreak":
+        return dambreak_problem(kw["dp"], densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
+    return lattice_problem(kw["n"], densitydiffusion=capi.RHODIFF_NONE)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline_port(seconds=12.0):
+    """The CPU oracle (scalar C + OpenMP) timed on a bounded sample of the same kind of workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from gpusph_b200 import capi
+    from gpusph_b200.problems import dambreak_problem
+    params, parts = dambreak_problem(0.012, densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
+    w = ob.OracleWorker(params, parts)
+    w.step()                                    # includes the first neighbour build
+    inter = 0
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < seconds:
+        w.step()
+        inter += 2 * w.neibs_info.num_interactions
+        steps += 1
+    el = time.perf_counter() - t0
+    return {"value": inter / el / 1e6, "unit": "M interactions/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"DamBreak3D-like dp=0.012 ({parts.n} particles), {steps} steps in {el:.1f}s, oracle/sph_oracle.c with OpenMP",
+            "particle_updates_per_s": steps * parts.n / el}
+
+
+def run_reference(args):
+    """--impl reference: the UNMODIFIED GPUSPH reference (shim-built binary oracle/_ref/DamBreak3D, its own
+    CUDA engines — the reference has no CPU compute path) on the same box."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    binp = os.path.join(ROOT, "oracle", "_ref", "DamBreak3D")
+    kind, kw = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "particle_interactions_per_second", "unit": "M interactions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload}}
+    if kind != "dambreak" or not os.path.exists(binp):
+        cb = cpu_baseline_port(20.0)
+        line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "note": "reference binary not available for this workload: CPU oracle port timed instead"})
+        print(json.dumps(line))
+        return 0
+    import tempfile
+
+    def run(maxiter):
+        d = tempfile.mkdtemp(prefix="gpusph_ref_")
+        dev = ",".join(str(i) for i in range(args.gpus))
+        cmd = [binp, "--deltap", str(kw["dp"]), "--maxiter", str(maxiter), "--nosave", "--dir", d,
+               "--device", dev, "--density-diffusion", "1", "--num_obstacles", "0"]
+        t0 = time.perf_counter()
+        p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
+        el = time.perf_counter() - t0
+        return el, p.stdout + p.stderr, p.returncode
+
+    t_w, out_w, rc_w = run(max(args.warmup, 1))
+    t_k, out_k, rc_k = run(max(args.warmup, 1) + args.steps)
+    m = re.search(r"([\d,]+) parts", out_k)
+    nparts = int(m.group(1).replace(",", "")) if m else None
+    if rc_k != 0 or nparts is None:
+        line.update({"unavailable": f"reference binary failed (rc={rc_k}): {out_k[-300:]!r}"})
+        print(json.dumps(line))
+        return 0
+    sec = max(t_k - t_w, 1e-9)
+    ups = nparts * args.steps / sec
+    # interactions per particle: measured by our neighbour engine on the same geometry/dp (the reference
+    # does not print its numInteractions counter); see DESIGN.md "Measurement"
+    npp = float(os.environ.get("B200SPH_NEIBS_PER_PARTICLE", "0")) or None
+    if npp is None:
+        try:
+            import torch
+            from gpusph_b200.simulation import Worker
+            params, parts = make_problem(args.workload)
+            w = Worker(params, parts, 0)
+            w.build_neibs()
+            npp = w.last_neibs_info.num_interactions / parts.n
+            del w
+            torch.cuda.empty_cache()
+        except Exception:
+            npp = 0.0
+    val = ups * npp * 2 / 1e6
+    line.update({"value": val, "ms_per_step": sec / args.steps * 1e3, "particle_updates_per_s": ups,
+                 "particles": nparts, "neibs_per_particle": npp,
+                 "cpu_baseline": {"value": val, "unit": "M interactions/s", "cores": 1 + args.gpus, "kind": "reference",
+                                  "sample": f"oracle/_ref/DamBreak3D --deltap {kw['dp']} --density-diffusion 1 --num_obstacles 0: "
+                                            f"wall({args.warmup}+{args.steps} iters) - wall({args.warmup} iters); the reference's own CUDA engines "
+                                            "on the same GPU (it has no CPU compute path), 1 orchestrator + 1 worker host thread per GPU"},
+                 "e2e": {"value": val, "unit": "M interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.workload is None:
+        args.workload = "dambreak2m"
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the engines have no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gpusph_b200.simulation import Worker
+
+    params, parts = make_problem(args.workload)
+    if world > 1:
+        from gpusph_b200.multigpu import SlabWorker
+        w = SlabWorker(params, parts, local, rank=rank, world=world)
+    else:
+        w = Worker(params, parts, local)
+    n_global = parts.n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        w.step()
+    # working set: pos/vel x2 states + forces + list > L2 for every benchmark workload; say which
+    working_set = n_global * (4 * 16 + 16 + 12) + w.last_neibs_info.num_interactions * 2
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    inter0 = w.total_interactions
+    launches0 = w.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        w.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    inter = torch.tensor([float(w.total_interactions - inter0)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(inter, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    interactions = float(inter.item())
+    clocks = sampler.stop() if sampler else None
+    launches = w.launches - launches0
+    value = interactions / (ms / 1e3) / 1e6
+    updates = n_global * args.steps / (ms / 1e3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if world == 1:
+        n = w.numParticles
+        hp = [torch.empty((n, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hi = torch.empty((n, 4), dtype=torch.int16).pin_memory()
+        hh = torch.empty(n, dtype=torch.int32).pin_memory()
+        hp[0].copy_(w.pos[w.cur][:n]); hp[1].copy_(w.vel[w.cur][:n]); hi.copy_(w.info[:n]); hh.copy_(w.hash[:n])
+        torch.cuda.synchronize()
+        esteps = max(args.steps // 2, 5)
+        i0 = w.total_interactions
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(esteps):
+            # host -> device: the step's inputs (state n)
+            w.pos[w.cur][:n].copy_(hp[0], non_blocking=True)
+            w.vel[w.cur][:n].copy_(hp[1], non_blocking=True)
+            w.info[:n].copy_(hi, non_blocking=True)
+            w.hash[:n].copy_(hh, non_blocking=True)
+            w.step()
+            n = w.numParticles
+            # device -> host: the step's result (state n+1; info/hash too because a rebuild re-sorts them)
+            hp[0][:n].copy_(w.pos[w.cur][:n], non_blocking=True)
+            hp[1][:n].copy_(w.vel[w.cur][:n], non_blocking=True)
+            hi[:n].copy_(w.info[:n], non_blocking=True)
+            hh[:n].copy_(w.hash[:n], non_blocking=True)
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ems = e0.elapsed_time(e1)
+        e2e = {"value": (w.total_interactions - i0) / (ems / 1e3) / 1e6, "unit": "M interactions/s",
+               "h2d_bytes_per_step": n * 44, "d2h_bytes_per_step": n * 44, "ms_per_step": ems / esteps,
+               "particle_updates_per_s": n * esteps / (ems / 1e3)}
+
+    # ---- roofline of the dominant kernel (forces), timed live with CUDA events on the launching stream ----
+    roofline = None
+    if rank == 0:
+        s = w.state(w.cur)
+        n = w.numParticles
+        reps = 10
+        eos_tmp = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+        flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device="cuda")
+
+        def timed(fn):
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(1)                      # flush L2 between timed launches
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / reps
+        t_step = timed(lambda: w.forces.basicstep(s, s, n, 0, w.particleRangeEnd, 0))
+        t_eos = timed(lambda: w.forces.eos_probe(s, eos_tmp, n))
+        t_kernel = max(t_step - t_eos, 1e-6)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = FORCES_BYTES_PER_PARTICLE * n / (t_kernel / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "forces_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_particle": FORCES_BYTES_PER_PARTICLE, "kernel_ms": t_kernel,
+                    "eos_prepass_ms": t_eos,
+                    "pair_rate_G_per_s": w.last_neibs_info.num_interactions / (t_kernel / 1e3) / 1e9,
+                    "note": "pair kernel is FP32-issue/LSU bound, not HBM bound (SURVEY.md 8d); the HBM fraction is reported as required"}
+        tr = os.path.join(ROOT, "profiles", "forces_traffic.json")
+        if os.path.exists(tr):
+            try:
+                roofline["traffic"] = json.load(open(tr)).get(args.workload)
+            except Exception:
+                pass
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_port()
+        line = {
+            "metric": "particle_interactions_per_second", "value": value, "unit": "M interactions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "particles": n_global,
+                       "neibs_per_particle": w.last_neibs_info.num_interactions / max(w.numParticles, 1),
+                       "buildneibsfreq": 10, "density_diffusion": "ferrari" if "dambreak" in args.workload else "none",
+                       "l2": f"inputs larger than L2 (working set {working_set / 1e6:.0f} MB vs 126 MB)" if working_set > L2_BYTES
+                             else "working set fits L2 (small reference config)",
+                       "parallelism": f"slab{world}" if world > 1 else "single"},
+            "particle_updates_per_s": updates,
+            "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

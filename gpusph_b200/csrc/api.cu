@@ -1,0 +1,153 @@
+// api.cu — context management and error plumbing of the C ABI (include/b200sph.h).
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <math.h>
+
+static thread_local char g_err[512] = "";
+
+void b200_set_error(const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *b200sph_last_error(void) { return g_err; }
+extern "C" int b200sph_abi_version(void) { return B200SPH_ABI_VERSION; }
+
+extern "C" int b200sph_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+// Which option combinations are implemented. Everything else fails loudly
+// (never silently fall back).
+extern "C" int b200sph_validate(const b200sph_params *p)
+{
+	if (!p) { b200_set_error("null params"); return B200SPH_EINVAL; }
+	if (p->abi_version != B200SPH_ABI_VERSION) {
+		b200_set_error("ABI version mismatch: caller %u, library %d", p->abi_version, B200SPH_ABI_VERSION);
+		return B200SPH_EINVAL;
+	}
+	for (int a = 0; a < 3; ++a) {
+		if (p->grid_size[a] == 0 || !(p->cell_size[a] > 0)) { b200_set_error("empty grid / non-positive cell size"); return B200SPH_EINVAL; }
+		if (p->coord[a] > 2) { b200_set_error("bad linearisation"); return B200SPH_EINVAL; }
+	}
+	if (p->coord[0] == p->coord[1] || p->coord[0] == p->coord[2] || p->coord[1] == p->coord[2]) {
+		b200_set_error("linearisation must be a permutation of xyz"); return B200SPH_EINVAL;
+	}
+	const uint64_t ncells = (uint64_t)p->grid_size[0] * p->grid_size[1] * p->grid_size[2];
+	if (ncells > (0xFFFFFFFFu >> 2)) { b200_set_error("too many cells (MAX_CELLS, src/multi_gpu_defines.h:56)"); return B200SPH_EINVAL; }
+	if (p->neiblistsize < 4 || p->neibboundpos >= p->neiblistsize) { b200_set_error("bad neiblistsize/neibboundpos"); return B200SPH_EINVAL; }
+	if (p->num_fluids < 1 || p->num_fluids > B200SPH_MAX_FLUIDS) { b200_set_error("num_fluids out of range"); return B200SPH_EINVAL; }
+	if (p->kerneltype != B200SPH_KERNEL_WENDLAND) { b200_set_error("unsupported SPH kernel %u: only WENDLAND is implemented", p->kerneltype); return B200SPH_EUNSUP; }
+	if (p->sph_formulation != B200SPH_SPH_F1) { b200_set_error("unsupported SPH formulation %u: only SPH_F1 is implemented", p->sph_formulation); return B200SPH_EUNSUP; }
+	if (p->boundarytype != B200SPH_DYN_BOUNDARY) { b200_set_error("unsupported boundary type %u: only DYN_BOUNDARY is implemented", p->boundarytype); return B200SPH_EUNSUP; }
+	if (p->densitydiffusiontype > B200SPH_RHODIFF_COLAGROSSI) { b200_set_error("unsupported density diffusion %u (BREZZI not implemented)", p->densitydiffusiontype); return B200SPH_EUNSUP; }
+	if (p->rheologytype > B200SPH_RHEOLOGY_NEWTONIAN) { b200_set_error("unsupported rheology %u", p->rheologytype); return B200SPH_EUNSUP; }
+	if (p->turbmodel > B200SPH_TURB_ARTIFICIAL) { b200_set_error("unsupported turbulence model %u", p->turbmodel); return B200SPH_EUNSUP; }
+	if (p->rheologytype == B200SPH_RHEOLOGY_NEWTONIAN && p->viscmodel != B200SPH_VISCMODEL_MORRIS) { b200_set_error("unsupported viscous model %u: only MORRIS", p->viscmodel); return B200SPH_EUNSUP; }
+	if (p->viscavgop > B200SPH_AVG_GEOMETRIC || p->compvisc > B200SPH_COMPVISC_DYNAMIC) { b200_set_error("bad viscous averaging / computational viscosity"); return B200SPH_EINVAL; }
+	if (!(p->slength > 0) || !(p->influenceradius > 0)) { b200_set_error("non-positive smoothing length"); return B200SPH_EINVAL; }
+	return B200SPH_OK;
+}
+
+static void fill_devparams(const b200sph_params *p, DevParams *d)
+{
+	memset(d, 0, sizeof(*d));
+	for (int a = 0; a < 3; ++a) {
+		d->cellSize[a] = p->cell_size[a];
+		d->gridSize[a] = (int)p->grid_size[a];
+		d->coord[a] = (int)p->coord[a];
+		d->gravity[a] = p->gravity[a];
+	}
+	d->periodic = p->periodic;
+	d->neiblistsize = p->neiblistsize; d->neibboundpos = p->neibboundpos; d->stride = p->neiblist_stride;
+	d->nlSqInflRad = p->nl_sq_influence_radius;
+	d->kerneltype = p->kerneltype; d->densitydiffusiontype = p->densitydiffusiontype; d->boundarytype = p->boundarytype;
+	d->inviscid = (p->rheologytype == B200SPH_RHEOLOGY_INVISCID);
+	d->turbmodel = p->turbmodel; d->compvisc = p->compvisc; d->viscavgop = p->viscavgop; d->is_const_visc = p->is_const_visc;
+	d->slength = p->slength; d->influenceradius = p->influenceradius; d->deltap = p->deltap;
+	// same expression and evaluation types as the reference (float h powers, double M_PI): src/cuda/forces.cu:274-291
+	const float h = p->slength; const float h2 = h * h; const float h4 = h2 * h2; const float h5 = h4 * h;
+	d->fcoeff_wendland = (float)(105.0f / (128.0f * M_PI * h5));
+	d->densityDiffCoeff = p->density_diff_coeff; d->artvisccoeff = p->artvisccoeff; d->epsartvisc = p->epsartvisc;
+	d->numFluids = p->num_fluids;
+	for (uint f = 0; f < B200SPH_MAX_FLUIDS; ++f) {
+		d->rho0[f] = p->rho0[f]; d->bcoeff[f] = p->bcoeff[f]; d->gammacoeff[f] = p->gammacoeff[f];
+		d->sscoeff[f] = p->sscoeff[f]; d->sspowercoeff[f] = p->sspowercoeff[f]; d->visccoeff[f] = p->visccoeff[f];
+		d->sqC0[f] = p->sscoeff[f] * p->sscoeff[f];   // src/cuda/forces.cu:318-323
+	}
+}
+
+extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
+{
+	if (!out) { b200_set_error("null out pointer"); return B200SPH_EINVAL; }
+	*out = NULL;
+	int rc = b200sph_validate(p);
+	if (rc) return rc;
+	if (b200sph_device_count() <= 0) {
+		b200_set_error("no CUDA device: this library has no CPU fallback");
+		return B200SPH_ENODEV;
+	}
+	b200sph_ctx *ctx = (b200sph_ctx *)calloc(1, sizeof(b200sph_ctx));
+	if (!ctx) { b200_set_error("out of host memory"); return B200SPH_ENOMEM; }
+	ctx->hp = *p;
+	fill_devparams(p, &ctx->dp);
+	CUDA_TRY(cudaGetDevice(&ctx->device));
+	ctx->stream = 0;
+	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
+	CUDA_TRY(cudaMalloc(&ctx->d_scalar, 4 * sizeof(float)));
+	CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));
+	CUDA_TRY(cudaMallocHost(&ctx->h_scalar, 4 * sizeof(float)));
+	CUDA_TRY(cudaMallocHost(&ctx->h_flag, sizeof(int)));
+	CUDA_TRY(cudaMemset(ctx->d_counters, 0, sizeof(NeibsCounters)));
+	*out = ctx;
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_destroy(b200sph_ctx *ctx)
+{
+	if (!ctx) return B200SPH_OK;
+	cudaSetDevice(ctx->device);
+	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->eos); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
+	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);
+	free(ctx);
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_set_stream(b200sph_ctx *ctx, void *s)
+{
+	if (!ctx) { b200_set_error("null context"); return B200SPH_EINVAL; }
+	ctx->stream = (cudaStream_t)s;
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_set_gravity(b200sph_ctx *ctx, const float g[3])
+{
+	if (!ctx || !g) { b200_set_error("null argument"); return B200SPH_EINVAL; }
+	for (int a = 0; a < 3; ++a) { ctx->hp.gravity[a] = g[a]; ctx->dp.gravity[a] = g[a]; }
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_get_neibboundpos(const b200sph_ctx *ctx, uint32_t *v)
+{
+	if (!ctx || !v) { b200_set_error("null argument"); return B200SPH_EINVAL; }
+	*v = ctx->hp.neibboundpos;
+	return B200SPH_OK;
+}
+
+// reference: src/cuda/forces.cu:540-554, 961-965
+extern "C" uint32_t b200sph_fmax_elements(uint32_t n) { return (div_up(n, BLOCK_FORCES) + 3) / 4 * 4; }
+// reducefmax(NULL, NULL, n): src/cuda/forces.cu:106-141 (n = number of CFL elements, a multiple of 4)
+extern "C" uint32_t b200sph_fmax_temp_elements(uint32_t n)
+{
+	uint32_t nb = div_up(div_up(n, 4u), 256u);
+	if (nb > 1) { nb = (nb + 3) / 4 * 4; if (nb > 1024u) nb = 1024u; }
+	return nb;
+}
+extern "C" uint32_t b200sph_round_particles(uint32_t n) { return (n / BLOCK_FORCES) * BLOCK_FORCES; }

@@ -1,0 +1,126 @@
+// common.cuh — shared declarations of the B200 WCSPH engine (internal; the public
+// boundary is include/b200sph.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/b200sph.h"
+
+typedef unsigned int uint;
+typedef unsigned short ushort;
+
+// ---- data contract constants (reference: src/multi_gpu_defines.h:58-84,
+// src/hashkey.h:44, src/common_types.h:57-74) ----
+#define CELLTYPE_BITMASK (~(3U << 30))
+#define CELL_HASH_MAX 0xFFFFFFFFu
+#define CELL_EMPTY 0xFFFFFFFFu
+#define NEIBS_END 0xFFFFu
+#define CELLNUM_SHIFT 11
+#define CELLNUM_ENCODED (1U << CELLNUM_SHIFT)
+#define NEIBINDEX_MASK (CELLNUM_ENCODED - 1)
+
+#define PT_FLUID 0
+#define PT_BOUNDARY 1
+#define PT_VERTEX 2
+#define PT_TESTPOINT 3
+
+// block sizes; forces uses 128 so that the CFL array has exactly the layout the
+// reference's getFmaxElements() sizes it for (src/cuda/forces.cu:56-68,540-544)
+#define BLOCK_STREAM 256
+#define BLOCK_FORCES 128
+
+// Device-side copy of everything the kernels need. Passed BY VALUE as a
+// __grid_constant__ kernel parameter (constant bank, no symbol upload, no sync,
+// one context per device/thread without global state).
+struct DevParams {
+	float cellSize[3];
+	int gridSize[3];
+	int coord[3];           // axis of COORD1,2,3
+	uint periodic;
+	uint neiblistsize, neibboundpos, stride;
+	float nlSqInflRad;
+	uint kerneltype, densitydiffusiontype, boundarytype;
+	uint inviscid, turbmodel, compvisc, viscavgop, is_const_visc;
+	float slength, influenceradius, deltap;
+	float fcoeff_wendland;  // 105/(128 pi h^5), src/cuda/forces.cu:289
+	float densityDiffCoeff, artvisccoeff, epsartvisc;
+	uint numFluids;
+	float rho0[B200SPH_MAX_FLUIDS], bcoeff[B200SPH_MAX_FLUIDS], gammacoeff[B200SPH_MAX_FLUIDS];
+	float sscoeff[B200SPH_MAX_FLUIDS], sspowercoeff[B200SPH_MAX_FLUIDS], visccoeff[B200SPH_MAX_FLUIDS];
+	float sqC0[B200SPH_MAX_FLUIDS];
+	float gravity[3];
+};
+
+struct NeibsCounters {     // mirrors the reference's device counters, src/cuda/buildneibs_kernel.cu:108-112
+	int numInteractions;
+	int maxFluidBoundaryNeibs;
+	int maxVertexNeibs;
+	int hasTooManyNeibs;
+	int hasMaxNeibs[3];
+	int pad;
+};
+
+struct b200sph_ctx {
+	b200sph_params hp;      // host copy
+	DevParams dp;
+	int device;
+	cudaStream_t stream;
+	// scratch (grown on demand)
+	void *sort_tmp; size_t sort_tmp_bytes;
+	uint64_t *keys_in, *keys_out; uint32_t *vals_out; void *info_tmp; size_t sort_cap;
+	float2 *eos; size_t eos_cap;           // per-particle {P/rho^2, sound speed}
+	NeibsCounters *d_counters;
+	float *d_scalar;                        // device scalar for reductions
+	float *h_scalar;                        // pinned host scalar
+	int *d_flag; int *h_flag;
+};
+
+// ---- error plumbing ----
+void b200_set_error(const char *fmt, ...);
+#define CUDA_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+	b200_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+	return B200SPH_ECUDA; } } while (0)
+#define KERNEL_TRY() CUDA_TRY(cudaGetLastError())
+#define CHECK_CTX(ctx) do { if (!(ctx)) { b200_set_error("null context"); return B200SPH_EINVAL; } \
+	CUDA_TRY(cudaSetDevice((ctx)->device)); } while (0)
+
+static inline uint div_up(uint a, uint b) { return (a + b - 1) / b; }
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+__device__ __forceinline__ int ptype_of(ushort4 info) { return info.x & 7; }
+__device__ __forceinline__ uint id_of(ushort4 info) { return (uint)info.z | ((uint)info.w << 16); }
+__device__ __forceinline__ int fluid_num_of(ushort4 info) { return info.y >> 12; }
+__device__ __forceinline__ bool inactive_w(float w) { return !isfinite(w); }
+
+// linear cell index from grid position, reference calcGridHash (src/cuda/cellgrid.cuh:101-106)
+__device__ __forceinline__ uint grid_hash(const DevParams &P, int gx, int gy, int gz)
+{
+	const int g[3] = { gx, gy, gz };
+	// select by coord without dynamic register indexing
+	auto sel = [&](int c) { return c == 0 ? g[0] : (c == 1 ? g[1] : g[2]); };
+	auto selG = [&](int c) { return c == 0 ? P.gridSize[0] : (c == 1 ? P.gridSize[1] : P.gridSize[2]); };
+	return (uint)(sel(P.coord[2]) * selG(P.coord[1]) * selG(P.coord[0]) + sel(P.coord[1]) * selG(P.coord[0]) + sel(P.coord[0]));
+}
+// reference calcGridPosFromCellHash (src/cuda/cellgrid.cuh:117-128)
+__device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
+{
+	auto selG = [&](int c) { return c == 0 ? P.gridSize[0] : (c == 1 ? P.gridSize[1] : P.gridSize[2]); };
+	const int G1 = selG(P.coord[0]), G2 = selG(P.coord[1]);
+	int temp = G2 * G1;
+	const int g3 = (int)cellHash / temp;
+	temp = (int)cellHash - g3 * temp;
+	const int g2 = temp / G1;
+	const int g1 = temp - g2 * G1;
+	int3 r;
+	// scatter back to x,y,z
+	r.x = P.coord[0] == 0 ? g1 : (P.coord[1] == 0 ? g2 : g3);
+	r.y = P.coord[0] == 1 ? g1 : (P.coord[1] == 1 ? g2 : g3);
+	r.z = P.coord[0] == 2 ? g1 : (P.coord[1] == 2 ? g2 : g3);
+	return r;
+}
+#endif
+
+// ---- internal launchers implemented in the .cu files ----
+int b200_eos_precompute(b200sph_ctx *ctx, const float4 *vel, const ushort4 *info, uint n);

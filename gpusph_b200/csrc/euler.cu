@@ -1,0 +1,59 @@
+// euler.cu — integration engine: predictor/corrector update.
+// Behavioural specification: GPUSPH eulerDevice, src/cuda/euler_kernel.def:396-540
+// (corrected velocity :117-134, continuity :200-206). Streaming kernel: 60 B in, 32 B out per particle.
+#include "common.cuh"
+
+template<int STEP>
+__global__ void __launch_bounds__(BLOCK_STREAM)
+euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ oldPos, const float4 *__restrict__ oldVel,
+	const ushort4 *__restrict__ infoArray, const float4 *__restrict__ forces,
+	float4 *__restrict__ newPos, float4 *__restrict__ newVel, const uint numParticles, const float dt)
+{
+	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
+	if (index >= numParticles) return;
+	float4 pos = oldPos[index];
+	float4 vel = oldVel[index];
+	const float4 force = forces[index];
+	const ushort4 info = infoArray[index];
+	const int type = ptype_of(info);
+	const bool integrateBoundary = (P.boundarytype == B200SPH_DYN_BOUNDARY || P.boundarytype == B200SPH_SA_BOUNDARY);   // :424-425
+	if (!inactive_w(pos.w) && !(type == PT_BOUNDARY && !integrateBoundary && !(info.x & B200SPH_FG_MOVING_BOUNDARY))) {
+		// velc = vel (+ force*dt/2 on the corrector), :117-134
+		float vcx = vel.x, vcy = vel.y, vcz = vel.z;
+		if (STEP == 2) {
+			const float hdt = dt / 2;
+			vcx += force.x * hdt; vcy += force.y * hdt; vcz += force.z * hdt;
+		}
+		if (type == PT_FLUID) {                                   // :441-462
+			pos.x += vcx * dt; pos.y += vcy * dt; pos.z += vcz * dt;
+			vel.w += dt * force.w;
+			vel.x += dt * force.x; vel.y += dt * force.y; vel.z += dt * force.z;
+		} else if (type == PT_BOUNDARY || type == PT_VERTEX) {     // :468-512 (moving bodies: SURVEY section 8 row f1)
+			if (P.boundarytype == B200SPH_DYN_BOUNDARY) vel.w += dt * force.w;
+		}
+	}
+	newPos[index] = pos;
+	newVel[index] = vel;
+}
+
+extern "C" int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
+	const uint32_t *hash, const void *forces, void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step)
+{
+	CHECK_CTX(ctx);
+	(void)hash;
+	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }   // euler.cu:361-362
+	if (particle_range_end == 0) return B200SPH_OK;
+	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
+	const uint nb = div_up(particle_range_end, BLOCK_STREAM);
+	// NOTE the reference passes numParticles (not the range end) as the kernel bound, euler.cu:352
+	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
+	if (step == 1)
+		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
+			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt);
+	else
+		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
+			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}

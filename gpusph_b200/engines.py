@@ -1,0 +1,224 @@
+"""Host-side mirror of GPUSPH's three hot engines on top of the C ABI.
+
+The class and method names, the argument meaning and the error behaviour follow the
+reference's abstract interfaces so that tests read like the reference's call sites:
+
+* ``NeibsEngine``       <-> AbstractNeibsEngine        (src/engine_neibs.h:45-107)
+* ``ForcesEngine``      <-> AbstractForcesEngine       (src/engine_forces.h:42-179)
+* ``IntegrationEngine`` <-> AbstractIntegrationEngine  (src/engine_integration.h:40-143)
+
+Buffers are passed like the reference's ``BufferList`` (src/buffer.h:595-775): a mapping from
+the reference's buffer keys (``BUFFER_POS`` ...; src/define_buffers.h:78-200) to device arrays —
+here torch CUDA tensors, whose only role is to own device memory. ``bufread`` holds inputs,
+``bufwrite`` outputs; a missing mandatory buffer raises like the reference does.
+
+All compute happens in ``libb200sph.so`` (hand-written sm_100a CUDA); this file contains no
+arithmetic on particle data and no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import capi
+
+# buffer keys (src/define_buffers.h)
+BUFFER_POS = "BUFFER_POS"
+BUFFER_VEL = "BUFFER_VEL"
+BUFFER_INFO = "BUFFER_INFO"
+BUFFER_HASH = "BUFFER_HASH"
+BUFFER_PARTINDEX = "BUFFER_PARTINDEX"
+BUFFER_CELLSTART = "BUFFER_CELLSTART"
+BUFFER_CELLEND = "BUFFER_CELLEND"
+BUFFER_NEIBSLIST = "BUFFER_NEIBSLIST"
+BUFFER_FORCES = "BUFFER_FORCES"
+BUFFER_CFL = "BUFFER_CFL"
+BUFFER_CFL_TEMP = "BUFFER_CFL_TEMP"
+BUFFER_COMPACT_DEV_MAP = "BUFFER_COMPACT_DEV_MAP"
+
+
+class BufferList(dict):
+    """Keyed device arrays; ``get_ptr`` returns 0 for a missing optional buffer (reference: NULL)."""
+
+    def ptr(self, key: str, mandatory: bool = True) -> int:
+        t = self.get(key)
+        if t is None:
+            if mandatory:
+                raise ValueError(f"missing mandatory buffer {key}")   # reference: std::invalid_argument
+            return 0
+        if not t.is_cuda:
+            raise ValueError(f"buffer {key} is not a device array")
+        if not t.is_contiguous():
+            raise ValueError(f"buffer {key} is not contiguous")
+        return t.data_ptr()
+
+
+class DeviceContext:
+    """Per-device engine state = the result of the engines' ``setconstants`` calls."""
+
+    def __init__(self, params: capi.Params, device: torch.device | int | None = None):
+        self.lib = capi.load()
+        if not torch.cuda.is_available() or self.lib.b200sph_device_count() <= 0:
+            raise capi.B200Error("no CUDA device: the B200 engines have no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else device.index or 0))
+        torch.cuda.set_device(self.device)
+        self.params = params.copy()
+        h = C.c_void_p()
+        capi.check(self.lib.b200sph_create(C.byref(self.params), C.byref(h)))
+        self.handle = h
+        self.use_stream(torch.cuda.current_stream(self.device))
+
+    def use_stream(self, stream: torch.cuda.Stream) -> None:
+        self.stream = stream
+        capi.check(self.lib.b200sph_set_stream(self.handle, C.c_void_p(stream.cuda_stream)))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.b200sph_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NeibsEngine:
+    """AbstractNeibsEngine (src/engine_neibs.h:45-107)."""
+
+    def __init__(self, ctx: DeviceContext):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+    def getconstants(self) -> int:
+        v = C.c_uint32()
+        capi.check(self.lib.b200sph_get_neibboundpos(self.ctx.handle, C.byref(v)))
+        return v.value
+
+    def resetinfo(self) -> None:
+        capi.check(self.lib.b200sph_neibs_resetinfo(self.ctx.handle))
+
+    def getinfo(self) -> capi.NeibsInfo:
+        out = capi.NeibsInfo()
+        capi.check(self.lib.b200sph_neibs_getinfo(self.ctx.handle, C.byref(out)))
+        return out
+
+    def calcHash(self, bufread: BufferList, bufwrite: BufferList, numParticles: int) -> None:
+        capi.check(self.lib.b200sph_calc_hash(
+            self.ctx.handle, bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_HASH), bufwrite.ptr(BUFFER_PARTINDEX),
+            bufread.ptr(BUFFER_INFO), bufread.ptr(BUFFER_COMPACT_DEV_MAP, False), numParticles))
+
+    def fixHash(self, bufread: BufferList, bufwrite: BufferList, numParticles: int) -> None:
+        capi.check(self.lib.b200sph_fix_hash(
+            self.ctx.handle, bufwrite.ptr(BUFFER_HASH, False), bufwrite.ptr(BUFFER_PARTINDEX),
+            bufread.ptr(BUFFER_INFO), bufread.ptr(BUFFER_COMPACT_DEV_MAP, False), numParticles))
+
+    def sort(self, bufread: BufferList, bufwrite: BufferList, numParticles: int) -> None:
+        capi.check(self.lib.b200sph_sort(
+            self.ctx.handle, bufwrite.ptr(BUFFER_HASH), bufwrite.ptr(BUFFER_INFO), bufwrite.ptr(BUFFER_PARTINDEX),
+            numParticles))
+
+    def reorderDataAndFindCellStart(self, segmentStart, sorted_buffers: BufferList, unsorted_buffers: BufferList,
+                                    numParticles: int, newNumParticles: torch.Tensor,
+                                    extra_keys=()) -> None:
+        extras = (capi.ReorderExtra * max(len(extra_keys), 1))()
+        for i, k in enumerate(extra_keys):
+            extras[i].unsorted = unsorted_buffers.ptr(k)
+            extras[i].sorted = sorted_buffers.ptr(k)
+            extras[i].elem_size = sorted_buffers[k].element_size() * (sorted_buffers[k].shape[1] if sorted_buffers[k].dim() > 1 else 1)
+        capi.check(self.lib.b200sph_reorder(
+            self.ctx.handle, sorted_buffers.ptr(BUFFER_CELLSTART), sorted_buffers.ptr(BUFFER_CELLEND),
+            0 if segmentStart is None else segmentStart.data_ptr(),
+            sorted_buffers.ptr(BUFFER_POS), sorted_buffers.ptr(BUFFER_VEL),
+            unsorted_buffers.ptr(BUFFER_POS), unsorted_buffers.ptr(BUFFER_VEL),
+            extras, len(extra_keys),
+            sorted_buffers.ptr(BUFFER_INFO), sorted_buffers.ptr(BUFFER_HASH), sorted_buffers.ptr(BUFFER_PARTINDEX),
+            numParticles, newNumParticles.data_ptr()))
+
+    def buildNeibsList(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
+                       gridCells: int = 0, sqinfluenceradius: float = 0.0, boundNlSqInflRad: float = 0.0) -> None:
+        capi.check(self.lib.b200sph_build_neibs(
+            self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_INFO), bufread.ptr(BUFFER_HASH),
+            bufread.ptr(BUFFER_CELLSTART), bufread.ptr(BUFFER_CELLEND), bufwrite.ptr(BUFFER_NEIBSLIST),
+            numParticles, particleRangeEnd))
+
+
+class ForcesEngine:
+    """AbstractForcesEngine (src/engine_forces.h:42-179) — the subset on the hot path."""
+
+    def __init__(self, ctx: DeviceContext):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+    def setgravity(self, gravity) -> None:
+        g = (C.c_float * 3)(*gravity)
+        capi.check(self.lib.b200sph_set_gravity(self.ctx.handle, g))
+
+    # texture binding does not exist on this architecture; kept so call sequences match GPUWorker::pre_forces
+    def bind_textures(self, bufread: BufferList, numParticles: int, run_mode=None) -> None:
+        return None
+
+    def unbind_textures(self, run_mode=None) -> None:
+        return None
+
+    def getFmaxElements(self, n: int) -> int:
+        return int(self.lib.b200sph_fmax_elements(n))
+
+    def getFmaxTempElements(self, n: int) -> int:
+        return int(self.lib.b200sph_fmax_temp_elements(n))
+
+    def round_particles(self, n: int) -> int:
+        return int(self.lib.b200sph_round_particles(n))
+
+    def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, fromParticle: int,
+                  toParticle: int, cflOffset: int = 0) -> int:
+        nblocks = C.c_uint32()
+        capi.check(self.lib.b200sph_forces(
+            self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
+            bufread.ptr(BUFFER_HASH), bufread.ptr(BUFFER_CELLSTART), bufread.ptr(BUFFER_NEIBSLIST),
+            bufwrite.ptr(BUFFER_FORCES), bufwrite.ptr(BUFFER_CFL, False),
+            numParticles, fromParticle, toParticle, cflOffset, C.byref(nblocks)))
+        return nblocks.value
+
+    def eos_probe(self, bufread: BufferList, out: torch.Tensor, numParticles: int) -> None:
+        """Diagnostic: per-particle {P/rho^2, sound speed} as the forces kernel evaluates them."""
+        capi.check(self.lib.b200sph_eos_probe(self.ctx.handle, bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
+                                              out.data_ptr(), numParticles))
+
+    def dtreduce(self, bufread: BufferList, bufwrite: BufferList, numBlocks: int) -> float:
+        dt = C.c_float()
+        capi.check(self.lib.b200sph_dtreduce(
+            self.ctx.handle, bufread.ptr(BUFFER_CFL), bufwrite.ptr(BUFFER_CFL_TEMP, False), numBlocks, C.byref(dt)))
+        return dt.value
+
+
+class IntegrationEngine:
+    """AbstractIntegrationEngine (src/engine_integration.h:40-143) — basicstep."""
+
+    def __init__(self, ctx: DeviceContext):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+    def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
+                  dt: float, step: int) -> None:
+        capi.check(self.lib.b200sph_euler(
+            self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
+            bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES),
+            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, dt, step))
+
+
+class SimFramework:
+    """The bag of engines a problem gets from SETUP_FRAMEWORK (src/simframework.h:65-134)."""
+
+    def __init__(self, params: capi.Params, device=None):
+        self.ctx = DeviceContext(params, device)
+        self.neibsEngine = NeibsEngine(self.ctx)
+        self.forcesEngine = ForcesEngine(self.ctx)
+        self.integrationEngine = IntegrationEngine(self.ctx)
+
+    @property
+    def params(self) -> capi.Params:
+        return self.ctx.params

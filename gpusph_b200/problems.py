@@ -1,0 +1,228 @@
+"""Host-side problem setup: parameters and initial particle arrays.
+
+Mirrors what GPUSPH's ProblemCore does on the host before the first step
+(src/ProblemCore.cc:121-173 initialize, :1433-1496 set_grid_params, :1554-1583
+calc_localpos_and_hash; defaults from src/simparams.h:280-300, src/physparams.h:385-400).
+Pure numpy — nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+
+from . import capi
+
+COORD_YZX = (1, 2, 0)   # reference default linearisation "yzx" (Makefile:517-523, src/linearization.h)
+
+
+@dataclasses.dataclass
+class ParticleArrays:
+    """Host copies of the per-particle buffers in the reference's layouts."""
+    pos: np.ndarray      # float32 [N,4] cell-local xyz + mass
+    vel: np.ndarray      # float32 [N,4] velocity + relative density
+    info: np.ndarray     # uint16  [N,4]
+    hash: np.ndarray     # uint32  [N]
+
+    @property
+    def n(self) -> int:
+        return int(self.pos.shape[0])
+
+
+def make_info(ptype: int, flags: int = 0, fluid: int = 0, obj: int = 0, ids=None, n: int | None = None) -> np.ndarray:
+    """particleinfo bit layout, src/particleinfo.h:295-330."""
+    ids = np.arange(n, dtype=np.uint32) if ids is None else np.asarray(ids, dtype=np.uint32)
+    info = np.zeros((ids.shape[0], 4), dtype=np.uint16)
+    info[:, 0] = ptype | flags
+    info[:, 1] = (fluid << 12) | obj
+    info[:, 2] = ids & 0xFFFF
+    info[:, 3] = ids >> 16
+    return info
+
+
+def make_params(*, origin, size, deltap, allocated_particles: int,
+                sfactor: float = 1.3, kernelradius: float = 2.0, nlexpansionfactor: float = 1.0,
+                neiblistsize: int = 128, periodic: int = 0, coord=COORD_YZX,
+                rho0: float = 1000.0, gamma: float = 7.0, c0: float = 20.0,
+                gravity=(0.0, 0.0, -9.81), densitydiffusion: int = capi.RHODIFF_NONE,
+                density_diff_coeff: float | None = None,
+                rheology: int = capi.RHEOLOGY_INVISCID, turbmodel: int = capi.TURB_ARTIFICIAL,
+                kinvisc: float = 0.0, viscavgop: int = capi.AVG_ARITHMETIC,
+                artvisccoeff: float = 0.3, dtadaptfactor: float = 0.3) -> capi.Params:
+    """Build b200sph_params the way ProblemCore + the engines' setconstants derive them."""
+    p = capi.Params()
+    p.abi_version = capi.ABI_VERSION
+    slength = np.float32(sfactor * deltap)                      # set_deltap / set_smoothing, simparams.h:340-375
+    influence = np.float32(slength * np.float32(kernelradius))
+    nl_influence = float(nlexpansionfactor) * float(influence)
+    cell_side = nl_influence                                     # ProblemCore.cc:1471
+    for a in range(3):
+        g = int(math.floor(size[a] / cell_side))                 # :1475-1477
+        if g <= 0:
+            raise ValueError("resolution too low: grid size would be 0 (ProblemCore.cc:1484-1489)")
+        p.grid_size[a] = g
+        p.cell_size[a] = np.float32(size[a] / g)                 # :1491-1493
+        p.world_origin[a] = np.float32(origin[a])
+        p.coord[a] = coord[a]
+        p.gravity[a] = gravity[a]
+    p.periodic = periodic
+    p.neiblistsize = neiblistsize
+    p.neibboundpos = neiblistsize - 1                            # non-SA: ProblemCore.h:346-353
+    p.neiblist_stride = allocated_particles
+    p.nl_sq_influence_radius = np.float32(nl_influence * nl_influence)
+    p.kerneltype = capi.KERNEL_WENDLAND
+    p.sph_formulation = capi.SPH_F1
+    p.densitydiffusiontype = densitydiffusion
+    p.boundarytype = capi.DYN_BOUNDARY
+    p.rheologytype = rheology
+    p.turbmodel = turbmodel
+    p.compvisc = capi.COMPVISC_KINEMATIC
+    p.viscmodel = capi.VISCMODEL_MORRIS
+    p.viscavgop = viscavgop
+    p.is_const_visc = 1 if rheology == capi.RHEOLOGY_NEWTONIAN else 0   # single fluid, Newtonian, no k-eps (visc_spec.h:262)
+    p.slength = slength
+    p.influenceradius = influence
+    p.deltap = np.float32(deltap)
+    if density_diff_coeff is None:
+        density_diff_coeff = 0.1 if densitydiffusion == capi.RHODIFF_COLAGROSSI else 0.0
+    if densitydiffusion == capi.RHODIFF_COLAGROSSI:             # pre-multiplied by 2h, ProblemCore.cc:1411-1418
+        density_diff_coeff = np.float32(np.float32(density_diff_coeff) * np.float32(2.0) * slength)
+    p.density_diff_coeff = np.float32(density_diff_coeff)
+    p.dtadaptfactor = dtadaptfactor
+    p.num_fluids = 1
+    p.rho0[0] = rho0
+    p.bcoeff[0] = np.float32(rho0 * c0 * c0 / gamma)             # physparams.h:506-517
+    p.gammacoeff[0] = gamma
+    p.sscoeff[0] = c0
+    p.sspowercoeff[0] = np.float32((gamma - 1.0) / 2.0)
+    p.visccoeff[0] = kinvisc
+    p.artvisccoeff = artvisccoeff
+    p.epsartvisc = np.float32(0.01 * float(slength) * float(slength))   # ProblemCore.cc:160-161
+    p.max_sound_speed_cfl = np.float32(np.float32(c0) * 1.1)     # GPUWorker.cc:3010-3011
+    p.max_kinvisc = kinvisc if rheology != capi.RHEOLOGY_INVISCID else 0.0
+    p.dtadapt = 1
+    return p
+
+
+def initial_dt(p: capi.Params) -> float:
+    """First-iteration dt: ProblemCore::check_dt, src/ProblemCore.cc:748-803 (float arithmetic)."""
+    f32 = np.float32
+    dt_ss = min(f32(p.slength) / f32(p.sscoeff[f]) for f in range(p.num_fluids)) * f32(p.dtadaptfactor)
+    g = math.sqrt(sum(float(p.gravity[a]) ** 2 for a in range(3)))
+    dt_g = f32(math.sqrt(float(p.slength) / g)) * f32(p.dtadaptfactor) if g > 0 else f32(np.inf)
+    dt = min(f32(dt_ss), f32(dt_g))
+    if p.rheologytype != capi.RHEOLOGY_INVISCID and p.max_kinvisc > 0:
+        dt = min(dt, f32(f32(p.slength) * f32(p.slength) / f32(p.max_kinvisc)) * f32(0.125))
+    return float(f32(dt))
+
+
+def localpos_and_hash(p: capi.Params, gpos: np.ndarray, mass: np.ndarray):
+    """Global double positions -> (cell-local float4 + mass, cell hash); ProblemCore.cc:1554-1583."""
+    origin = np.array([p.world_origin[a] for a in range(3)], dtype=np.float64)
+    cs = np.array([p.cell_size[a] for a in range(3)], dtype=np.float64)
+    G = np.array([p.grid_size[a] for a in range(3)], dtype=np.int64)
+    g = np.floor((gpos - origin) / cs).astype(np.int64)
+    g = np.minimum(np.maximum(g, 0), G - 1)
+    c = [p.coord[a] for a in range(3)]
+    hashv = (g[:, c[2]] * G[c[1]] * G[c[0]] + g[:, c[1]] * G[c[0]] + g[:, c[0]]).astype(np.uint32)
+    pos = np.empty((gpos.shape[0], 4), dtype=np.float32)
+    pos[:, :3] = (gpos - origin - (g + 0.5) * cs).astype(np.float32)
+    pos[:, 3] = mass
+    return pos, hashv
+
+
+def global_positions(p: capi.Params, pos: np.ndarray, hashv: np.ndarray) -> np.ndarray:
+    """Inverse of localpos_and_hash (double): worldOrigin + (gridPos + 0.5)*cellSize + pos."""
+    G = [int(p.grid_size[a]) for a in range(3)]
+    c = [p.coord[a] for a in range(3)]
+    cell = (hashv & 0x3FFFFFFF).astype(np.int64)
+    g = np.empty((pos.shape[0], 3), dtype=np.int64)
+    t = G[c[1]] * G[c[0]]
+    g[:, c[2]] = cell // t
+    r = cell - g[:, c[2]] * t
+    g[:, c[1]] = r // G[c[0]]
+    g[:, c[0]] = r - g[:, c[1]] * G[c[0]]
+    origin = np.array([p.world_origin[a] for a in range(3)], dtype=np.float64)
+    cs = np.array([p.cell_size[a] for a in range(3)], dtype=np.float64)
+    return origin + (g + 0.5) * cs + pos[:, :3].astype(np.float64)
+
+
+def lattice_problem(n: int, *, dp: float = 0.01, jitter: float = 0.05, seed: int = 12345,
+                    densitydiffusion: int = capi.RHODIFF_NONE, rho0: float = 1000.0, c0: float = 20.0,
+                    nz: int | None = None, ny: int | None = None, alloc_extra: float = 0.0, **kw):
+    """Synthetic cubic fluid lattice of SURVEY.md section 8(d): n^3 (or n*ny*nz) fluid particles with
+    spacing dp at (i+1/2)dp, domain padded by one cell, h = 1.3 dp, velocity
+    0.1 c0 (sin, cos, sin)(2 pi x/L), optional uniform jitter of +-jitter*dp."""
+    nx = n
+    ny = n if ny is None else ny
+    nz = n if nz is None else nz
+    N = nx * ny * nz
+    pad = 2.6 * dp
+    L = np.array([nx, ny, nz], dtype=np.float64) * dp
+    origin = -np.array([pad, pad, pad])
+    size = L + 2 * pad
+    params = make_params(origin=origin, size=size, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
+                         rho0=rho0, c0=c0, densitydiffusion=densitydiffusion, **kw)
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    g = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1).astype(np.float64)
+    gpos = (g + 0.5) * dp
+    if jitter:
+        rng = np.random.default_rng(seed)
+        gpos = gpos + rng.uniform(-jitter * dp, jitter * dp, size=gpos.shape)
+    mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
+    pos, hashv = localpos_and_hash(params, gpos, mass)
+    vel = np.zeros((N, 4), dtype=np.float32)
+    ph = 2 * np.pi * gpos / L
+    vel[:, 0] = 0.1 * c0 * np.sin(ph[:, 0])
+    vel[:, 1] = 0.1 * c0 * np.cos(ph[:, 1])
+    vel[:, 2] = 0.1 * c0 * np.sin(ph[:, 2])
+    info = make_info(capi.PT_FLUID, n=N)
+    return params, ParticleArrays(pos, vel, info, hashv)
+
+
+def _box_shell(lo, hi, dp, layers):
+    """Points of `layers` layers of spacing dp lining the inside of the box [lo,hi] (all six faces)."""
+    n = np.maximum(np.round((np.asarray(hi) - np.asarray(lo)) / dp).astype(int), 1)
+    xs = [np.asarray(lo)[a] + (np.arange(n[a] + 1)) * ((np.asarray(hi)[a] - np.asarray(lo)[a]) / n[a]) for a in range(3)]
+    I, J, K = np.meshgrid(np.arange(n[0] + 1), np.arange(n[1] + 1), np.arange(n[2] + 1), indexing="ij")
+    shell = (I < layers) | (I > n[0] - layers) | (J < layers) | (J > n[1] - layers) | (K < layers) | (K > n[2] - layers)
+    return np.stack([xs[0][I[shell]], xs[1][J[shell]], xs[2][K[shell]]], axis=1)
+
+
+def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_COLAGROSSI, layers: int = 3,
+                     alloc_extra: float = 0.0, **kw):
+    """DamBreak3D-like setup (src/problems/DamBreak3D.cu:36-205 with --num_obstacles 0): a 1.6 x 0.67 x 0.6 m
+    tank lined with `layers` layers of DYN boundary particles, a 0.4 m long, 0.4 m high water column,
+    Wendland kernel, artificial viscosity, c0 = 20, gamma = 7. Fill order/ids are ours, not the reference's
+    (bit-level parity with the reference is tested from the reference's own initial state instead)."""
+    dim = np.array([1.6, 0.67, 0.6])
+    H = 0.4
+    bd = dp * layers
+    wall = _box_shell(np.zeros(3), dim, dp, layers)
+    lo = np.array([bd, bd, bd])
+    ext = np.array([0.4 - bd, dim[1] - 2 * bd, H - bd])
+    nf = np.maximum(np.floor(ext / dp + 1e-9).astype(int), 1)
+    I, J, K = np.meshgrid(np.arange(nf[0] + 1), np.arange(nf[1] + 1), np.arange(nf[2] + 1), indexing="ij")
+    fluid = lo + np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * (ext / nf)
+    nfl, nb = fluid.shape[0], wall.shape[0]
+    N = nfl + nb
+    rho0 = 1000.0
+    c0 = 20.0
+    params = make_params(origin=np.zeros(3), size=dim, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
+                         rho0=rho0, c0=c0, densitydiffusion=densitydiffusion, **kw)
+    gpos = np.concatenate([fluid, wall], axis=0)
+    mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
+    pos, hashv = localpos_and_hash(params, gpos, mass)
+    vel = np.zeros((N, 4), dtype=np.float32)
+    # hydrostatic initial density for the fluid column (ProblemAPI_1.cc hydrostatic filling):
+    # rho = rho0 (1 + g (H - z)/B)^(1/gamma), stored as rho/rho0 - 1
+    gam = 7.0
+    B = rho0 * c0 * c0 / gam
+    depth = np.clip(H - gpos[:, 2], 0, None)
+    in_column = gpos[:, 0] <= 0.4 + bd
+    dens = np.where(in_column, np.power(1.0 + rho0 * 9.81 * depth / B, 1.0 / gam) - 1.0, 0.0)
+    vel[:, 3] = dens.astype(np.float32)
+    info = np.concatenate([make_info(capi.PT_FLUID, ids=np.arange(nfl)),
+                           make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, N))], axis=0)
+    return params, ParticleArrays(pos, vel, info, hashv)

@@ -1,0 +1,166 @@
+"""Per-device worker: owns the particle buffers and drives the engines through one time step.
+
+Host-side mirror of the part of GPUWorker / PredictorCorrector that fixes the call order and the
+arguments of the hot-path engines (src/GPUWorker.cc:1779-2269 runCommand<CALCHASH|SORT|REORDER|
+BUILDNEIBS|FORCES_SYNC|EULER>, src/integrators/PredictorCorrectorIntegrator.cc:387-680,
+src/Integrator.cc:93-249, src/GPUSPH.cc:636-699). torch is used for device memory only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import capi
+from .engines import (BUFFER_CELLEND, BUFFER_CELLSTART, BUFFER_CFL, BUFFER_CFL_TEMP, BUFFER_COMPACT_DEV_MAP,
+                      BUFFER_FORCES, BUFFER_HASH, BUFFER_INFO, BUFFER_NEIBSLIST, BUFFER_PARTINDEX, BUFFER_POS,
+                      BUFFER_VEL, BufferList, SimFramework)
+from .problems import ParticleArrays, initial_dt
+
+
+def _dev(a: np.ndarray, device, dtype=None) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.view(dtype)
+    return t.to(device)
+
+
+class Worker:
+    """One GPU's particle system (states "step n" / "step n*", src/ParticleSystem.h) + engines."""
+
+    def __init__(self, params: capi.Params, particles: ParticleArrays, device=None, *,
+                 buildneibsfreq: int = 10, clobber: bool = False, fixed_dt: float | None = None,
+                 compact_dev_map: np.ndarray | None = None):
+        self.framework = SimFramework(params, device)
+        self.params = self.framework.params
+        self.device = self.framework.ctx.device
+        self.neibs = self.framework.neibsEngine
+        self.forces = self.framework.forcesEngine
+        self.integration = self.framework.integrationEngine
+        self.buildneibsfreq = buildneibsfreq
+        self.clobber = clobber
+        self.fixed_dt = fixed_dt
+        self.allocated = int(self.params.neiblist_stride)
+        n = particles.n
+        if n > self.allocated:
+            raise ValueError("more particles than allocated")
+        self.numParticles = n
+        self.particleRangeEnd = n
+        A, dev = self.allocated, self.device
+        f4 = lambda: torch.zeros((A, 4), dtype=torch.float32, device=dev)
+        # double-buffered properties (src/predcorr_alloc_policy.cc:41-53)
+        self.pos = [f4(), f4()]
+        self.vel = [f4(), f4()]
+        self.cur = 0                      # index of state "step n"
+        self.info = torch.zeros((A, 4), dtype=torch.int16, device=dev)       # ushort4 bits
+        self.hash = torch.zeros(A, dtype=torch.int32, device=dev)            # uint32 bits
+        self.partindex = torch.zeros(A, dtype=torch.int32, device=dev)
+        self.forces_buf = f4()
+        ncells = self.params.num_cells
+        self.cellstart = torch.empty(ncells, dtype=torch.int32, device=dev)
+        self.cellend = torch.empty(ncells, dtype=torch.int32, device=dev)
+        self.neibslist = torch.empty((int(self.params.neiblistsize), A), dtype=torch.int16, device=dev)
+        self.neibslist.fill_(-1)
+        ncfl = self.forces.getFmaxElements(A)
+        self.cfl = torch.zeros(ncfl, dtype=torch.float32, device=dev)
+        self.cfl_temp = torch.zeros(max(self.forces.getFmaxTempElements(ncfl), 4), dtype=torch.float32, device=dev)
+        self.new_num = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.compact_dev_map = None if compact_dev_map is None else _dev(compact_dev_map.astype(np.uint32), dev, torch.int32)
+        # upload (GPUWorker::uploadSubdomain, src/GPUWorker.cc:1162-1225)
+        self.pos[0][:n].copy_(_dev(particles.pos, dev))
+        self.vel[0][:n].copy_(_dev(particles.vel, dev))
+        self.info[:n].copy_(_dev(particles.info.view(np.int16), dev))
+        self.hash[:n].copy_(_dev(particles.hash.view(np.int32), dev))
+        self.iterations = 0
+        self.t = 0.0
+        self.dt = float(fixed_dt) if fixed_dt is not None else initial_dt(self.params)
+        self.last_neibs_info = None
+        self.total_interactions = 0       # sum over steps of list entries x 2 force evaluations
+        self.launches = 0                 # hand-written kernels launched (CUB's sort passes not counted)
+
+    # ---- buffer lists ----
+    def _common(self) -> dict:
+        d = {BUFFER_INFO: self.info, BUFFER_HASH: self.hash, BUFFER_PARTINDEX: self.partindex,
+             BUFFER_CELLSTART: self.cellstart, BUFFER_CELLEND: self.cellend, BUFFER_NEIBSLIST: self.neibslist,
+             BUFFER_FORCES: self.forces_buf, BUFFER_CFL: self.cfl, BUFFER_CFL_TEMP: self.cfl_temp}
+        if self.compact_dev_map is not None:
+            d[BUFFER_COMPACT_DEV_MAP] = self.compact_dev_map
+        return d
+
+    def state(self, which: int) -> BufferList:
+        b = BufferList(self._common())
+        b[BUFFER_POS] = self.pos[which]
+        b[BUFFER_VEL] = self.vel[which]
+        return b
+
+    # ---- NEIBS_LIST phase (src/Integrator.cc:93-249) ----
+    def build_neibs(self) -> None:
+        n = self.numParticles
+        cur, oth = self.cur, 1 - self.cur
+        s = self.state(cur)
+        if self.iterations == 0:
+            self.neibs.fixHash(s, s, n)            # src/GPUWorker.cc:1800-1807
+        else:
+            self.neibs.calcHash(s, s, n)           # :1779-1799
+        self.neibs.sort(s, s, n)                   # :1811-1827
+        self.cellstart.fill_(-1)                   # clobber CELLSTART, :1846
+        if self.clobber:
+            self.cellend.fill_(-1)
+        srt = self.state(oth)
+        self.neibs.reorderDataAndFindCellStart(None, srt, s, n, self.new_num)   # :1830-1863
+        self.cur = oth
+        new_n = int(self.new_num.item())           # DOWNLOAD_NEWNUMPARTS
+        if new_n != n:
+            self.numParticles = new_n
+            self.particleRangeEnd = new_n
+        self.neibs.resetinfo()                     # BUILDNEIBS :1866-1905
+        if self.clobber:
+            self.neibslist.fill_(-1)
+        s = self.state(self.cur)
+        self.neibs.buildNeibsList(s, s, self.numParticles, self.particleRangeEnd)
+        self.last_neibs_info = self.neibs.getinfo()
+        self.launches += 6                # calc/fixHash, make_keys, apply_sort, reorder, reset_counters, build_neibs
+
+    # ---- one force evaluation + integration sub-step ----
+    def _forces(self, which: int) -> float:
+        s = self.state(which)
+        if self.clobber:
+            self.forces_buf.zero_()                # pre_forces: clobber FORCES, src/GPUWorker.cc:1949
+        nblocks = self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0)
+        self.launches += 2                # eos pre-pass + fused forces kernel
+        if self.fixed_dt is not None:
+            return self.fixed_dt
+        self.launches += 1                # CFL max-reduce
+        return self.forces.dtreduce(s, s, nblocks)   # post_forces :1994-2037
+
+    def step(self) -> None:
+        """One predictor-corrector time step (src/integrators/PredictorCorrectorIntegrator.cc:917-1068)."""
+        if self.iterations % self.buildneibsfreq == 0:
+            self.build_neibs()
+        n, end = self.numParticles, self.particleRangeEnd
+        cur, oth = self.cur, 1 - self.cur
+        dt = self.dt
+        # predictor: forces(n) -> euler step 1 with dt/2 writes n*
+        dt1 = self._forces(cur)
+        rd = self.state(cur)
+        wr = self.state(oth)
+        self.integration.basicstep(rd, wr, n, end, dt / 2, 1)
+        # corrector: forces(n*) -> euler step 2 with dt, reading pos/vel of n, updating n* in place -> n+1
+        dt2 = self._forces(oth)
+        self.integration.basicstep(rd, wr, n, end, dt, 2)
+        self.launches += 2                # two euler launches
+        self.cur = oth
+        self.iterations += 1
+        self.t += dt
+        if self.last_neibs_info is not None:
+            self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
+        if self.fixed_dt is None:
+            self.dt = min(dt1, dt2)                # src/GPUWorker.cc:2224-2229, src/GPUSPH.cc:650-657
+
+    # ---- host copies ----
+    def download(self) -> ParticleArrays:
+        n = self.numParticles
+        return ParticleArrays(
+            pos=self.pos[self.cur][:n].cpu().numpy(),
+            vel=self.vel[self.cur][:n].cpu().numpy(),
+            info=self.info[:n].cpu().numpy().view(np.uint16),
+            hash=self.hash[:n].cpu().numpy().view(np.uint32))

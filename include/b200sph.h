@@ -1,0 +1,249 @@
+/*
+ * b200sph.h — C ABI of the B200-native WCSPH per-timestep engine.
+ *
+ * This is the drop-in boundary for the hot path of GPUSPH (neighbour build ->
+ * forces -> integration). Every entry point replaces one virtual of the
+ * reference's three abstract engines; the reference file:line it replaces is
+ * cited on each declaration (paths relative to the GPUSPH source tree).
+ * The C++ adapter classes that a GPUSPH maintainer would add on the reference
+ * side (thin subclasses of AbstractNeibsEngine / AbstractForcesEngine /
+ * AbstractIntegrationEngine forwarding raw device pointers here) are in
+ * gpusph_b200/host/b200_engines.h and described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; all particle arrays are DEVICE pointers in the
+ *    reference's own layouts:
+ *      pos    float4[N]  xyz = position relative to the cell centre, w = mass
+ *                         (non-finite w  => particle inactive)
+ *      vel    float4[N]  xyz = velocity, w = relative density rho/rho0 - 1
+ *      info   ushort4[N] x = type(3 bits) | flags<<3, y = fluid<<12 | object,
+ *                         z,w = id lo,hi              (src/particleinfo.h:66)
+ *      hash   uint32[N]  bits 0-29 linear cell index, bits 30-31 cell type,
+ *                         0xFFFFFFFF inactive          (src/hashkey.h:40-61)
+ *      forces float4[N]  xyz = Dv/Dt, w = D(rho~)/Dt
+ *      cellStart/cellEnd uint32[C], 0xFFFFFFFF = empty cell
+ *      neibsList ushort[neiblistsize][stride]  (src/cuda/buildneibs_kernel.cu:1029)
+ *  - every function returns 0 on success, a negative B200SPH_E* code on
+ *    failure; b200sph_last_error() gives the message. The reference throws
+ *    C++ exceptions (std::runtime_error / std::invalid_argument); the adapter
+ *    turns the codes back into those exceptions.
+ *  - work is enqueued on the context's CUDA stream (default: the legacy
+ *    default stream, like the reference). Calls that return host values
+ *    (b200sph_neibs_getinfo, b200sph_dtreduce, ...) synchronise that stream.
+ *  - There is NO CPU fallback: without a CUDA device every compute call
+ *    fails with B200SPH_ENODEV.
+ */
+#ifndef B200SPH_H
+#define B200SPH_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPH_ABI_VERSION 1
+
+/* error codes */
+#define B200SPH_OK        0
+#define B200SPH_EINVAL   -1  /* invalid argument (reference: std::invalid_argument) */
+#define B200SPH_EUNSUP   -2  /* option combination not implemented: fails loudly, never falls back */
+#define B200SPH_ECUDA    -3  /* CUDA runtime error (reference: CUDA_SAFE_CALL exception) */
+#define B200SPH_ENODEV   -4  /* no CUDA device */
+#define B200SPH_ENOMEM   -5
+
+/* enumerations: numeric values are the reference's (src/particledefine.h:79-224,
+ * src/visc_spec.h) so that SimParams fields can be passed through unchanged */
+enum { B200SPH_KERNEL_CUBICSPLINE = 1, B200SPH_KERNEL_QUADRATIC, B200SPH_KERNEL_WENDLAND, B200SPH_KERNEL_GAUSSIAN };
+enum { B200SPH_SPH_F1 = 1, B200SPH_SPH_F2, B200SPH_SPH_GRENIER, B200SPH_SPH_HA };
+enum { B200SPH_RHODIFF_NONE = 0, B200SPH_RHODIFF_FERRARI, B200SPH_RHODIFF_COLAGROSSI, B200SPH_RHODIFF_BREZZI };
+enum { B200SPH_LJ_BOUNDARY = 0, B200SPH_MK_BOUNDARY, B200SPH_SA_BOUNDARY, B200SPH_DYN_BOUNDARY };
+enum { B200SPH_PERIODIC_X = 1, B200SPH_PERIODIC_Y = 2, B200SPH_PERIODIC_Z = 4 };
+/* viscous specification (src/visc_spec.h) */
+enum { B200SPH_RHEOLOGY_INVISCID = 0, B200SPH_RHEOLOGY_NEWTONIAN = 1 };
+enum { B200SPH_TURB_LAMINAR = 0, B200SPH_TURB_ARTIFICIAL = 1 };
+enum { B200SPH_COMPVISC_KINEMATIC = 0, B200SPH_COMPVISC_DYNAMIC = 1 };
+enum { B200SPH_VISCMODEL_MORRIS = 0, B200SPH_VISCMODEL_MONAGHAN = 1 };
+enum { B200SPH_AVG_ARITHMETIC = 0, B200SPH_AVG_HARMONIC = 1, B200SPH_AVG_GEOMETRIC = 2 };
+
+#define B200SPH_MAX_FLUIDS 4
+
+/* particle type / flag bits (src/particleinfo.h:135-165) */
+#define B200SPH_PT_FLUID     0
+#define B200SPH_PT_BOUNDARY  1
+#define B200SPH_PT_VERTEX    2
+#define B200SPH_PT_TESTPOINT 3
+#define B200SPH_FG_COMPUTE_FORCE   (1u << 3)
+#define B200SPH_FG_MOVING_BOUNDARY (1u << 4)
+#define B200SPH_FG_SURFACE         (1u << 9)
+
+/*
+ * Everything the three reference engines receive through setconstants()
+ * (src/cuda/buildneibs.cu:64-98, src/cuda/forces.cu:269-420, src/cuda/euler.cu:52-95),
+ * i.e. the relevant subset of SimParams (src/simparams.h) and PhysParams
+ * (src/physparams.h), flattened into one POD.
+ */
+typedef struct b200sph_params {
+	uint32_t abi_version;          /* must be B200SPH_ABI_VERSION */
+	/* cell grid (src/cuda/cellgrid.cuh:66-69) */
+	float    world_origin[3];
+	float    cell_size[3];
+	uint32_t grid_size[3];
+	uint32_t coord[3];             /* linearisation: axis index (0=x,1=y,2=z) of COORD1,2,3; reference default yzx = {1,2,0} (src/linearization.h) */
+	uint32_t periodic;             /* Periodicity bitmask */
+	/* neighbour list (src/simparams.h neiblistsize/neibboundpos; src/cuda/buildneibs.cu:64-98) */
+	uint32_t neiblistsize;         /* rows of the list, DamBreak3D: 128 */
+	uint32_t neibboundpos;         /* row of the first boundary neighbour (grows downwards), = neiblistsize-1 unless SA */
+	uint32_t neiblist_stride;      /* allocated particles = row stride of neibsList */
+	float    nl_sq_influence_radius; /* squared neighbour-search radius (simparams nlSqInfluenceRadius) */
+	/* SPH */
+	uint32_t kerneltype, sph_formulation, densitydiffusiontype, boundarytype;
+	uint32_t rheologytype, turbmodel, compvisc, viscmodel, viscavgop;
+	uint32_t is_const_visc;        /* FullViscSpec::is_const_visc (src/visc_spec.h:262) */
+	float    slength;              /* smoothing length h */
+	float    influenceradius;      /* kernel radius * h */
+	float    deltap;
+	float    density_diff_coeff;   /* d_densityDiffCoeff, already scaled as the reference does (src/cuda/forces.cu:395-410) */
+	float    dtadaptfactor;
+	/* physics (src/physparams.h) */
+	uint32_t num_fluids;
+	float    rho0[B200SPH_MAX_FLUIDS];
+	float    bcoeff[B200SPH_MAX_FLUIDS];      /* rho0 c0^2 / gamma */
+	float    gammacoeff[B200SPH_MAX_FLUIDS];
+	float    sscoeff[B200SPH_MAX_FLUIDS];     /* c0 */
+	float    sspowercoeff[B200SPH_MAX_FLUIDS];/* (gamma-1)/2 */
+	float    visccoeff[B200SPH_MAX_FLUIDS];   /* kinematic (or dynamic) viscosity as uploaded to d_visccoeff */
+	float    gravity[3];
+	float    artvisccoeff;
+	float    epsartvisc;
+	/* adaptive dt (src/GPUWorker.cc:3006-3011) */
+	float    max_sound_speed_cfl;  /* 1.1 * max c0 */
+	float    max_kinvisc;          /* max kinematic viscosity (0 if inviscid) */
+	uint32_t dtadapt;              /* ENABLE_DTADAPT */
+} b200sph_params;
+
+/* mirror of TimingInfo's neighbour counters (src/timing.h:42-97) */
+typedef struct b200sph_neibs_info {
+	int32_t num_interactions;
+	int32_t max_fluid_boundary_neibs;
+	int32_t max_vertex_neibs;
+	int32_t has_too_many_neibs;     /* id of one offending particle, or -1 */
+	int32_t has_max_neibs[3];       /* its per-type neighbour counts */
+} b200sph_neibs_info;
+
+typedef struct b200sph_ctx b200sph_ctx;
+
+const char *b200sph_last_error(void);
+int b200sph_abi_version(void);
+/* number of CUDA devices visible (0 on a CPU box; never fails) */
+int b200sph_device_count(void);
+
+/* ---- context = the engines' per-device constants and scratch ------------- */
+
+/* replaces {CUDANeibsEngine,CUDAForcesEngine,CUDAPredCorrEngine}::setconstants
+ * (src/engine_neibs.h:52, src/engine_forces.h:49, src/engine_integration.h:47).
+ * Fails with B200SPH_EUNSUP for option combinations that are not implemented. */
+int b200sph_create(const b200sph_params *params, b200sph_ctx **out);
+int b200sph_destroy(b200sph_ctx *ctx);
+/* check only: would b200sph_create accept these params? (no device needed) */
+int b200sph_validate(const b200sph_params *params);
+/* cudaStream_t as an opaque pointer; NULL = legacy default stream */
+int b200sph_set_stream(b200sph_ctx *ctx, void *cuda_stream);
+/* AbstractForcesEngine::setgravity (src/engine_forces.h:58) */
+int b200sph_set_gravity(b200sph_ctx *ctx, const float gravity[3]);
+/* AbstractNeibsEngine::getconstants (src/engine_neibs.h:57): returns neibboundpos */
+int b200sph_get_neibboundpos(const b200sph_ctx *ctx, uint32_t *neibboundpos);
+
+/* ---- neighbour engine ---------------------------------------------------- */
+
+/* AbstractNeibsEngine::calcHash (src/engine_neibs.h:66; kernel src/cuda/buildneibs_kernel.cu:664-776).
+ * pos, hash updated in place; part_index written. compact_dev_map may be NULL. Bit-exact. */
+int b200sph_calc_hash(b200sph_ctx *ctx, void *pos, uint32_t *hash, uint32_t *part_index,
+	const void *info, const uint32_t *compact_dev_map, uint32_t num_particles);
+
+/* AbstractNeibsEngine::fixHash (src/engine_neibs.h:71; kernel src/cuda/buildneibs_kernel.cu:790-814). */
+int b200sph_fix_hash(b200sph_ctx *ctx, uint32_t *hash, uint32_t *part_index,
+	const void *info, const uint32_t *compact_dev_map, uint32_t num_particles);
+
+/* AbstractNeibsEngine::sort (src/engine_neibs.h:84; src/cuda/buildneibs.cu:358-415).
+ * Sorts (hash, info) in place by the reference's total order
+ * (hash incl. high bits, particle type, id) and permutes part_index alike. Bit-exact. */
+int b200sph_sort(b200sph_ctx *ctx, uint32_t *hash, void *info, uint32_t *part_index,
+	uint32_t num_particles);
+
+/* one extra per-particle array to be permuted by reorder (the reference gathers up to
+ * 11 optional buffers, src/cuda/buildneibs_kernel.cu:840-992) */
+typedef struct b200sph_reorder_extra {
+	const void *unsorted;
+	void       *sorted;
+	uint32_t    elem_size;   /* 4, 8 or 16 bytes */
+} b200sph_reorder_extra;
+
+/* AbstractNeibsEngine::reorderDataAndFindCellStart (src/engine_neibs.h:76; kernel
+ * src/cuda/buildneibs_kernel.cu:840-992). cell_start/cell_end must have been pre-filled
+ * with 0xFF by the caller (as GPUWorker does, src/GPUWorker.cc:1846).
+ * segment_start (4 uints, device) may be NULL. new_num_particles is a device pointer. */
+int b200sph_reorder(b200sph_ctx *ctx, uint32_t *cell_start, uint32_t *cell_end,
+	uint32_t *segment_start,
+	void *sorted_pos, void *sorted_vel,
+	const void *unsorted_pos, const void *unsorted_vel,
+	const b200sph_reorder_extra *extras, uint32_t num_extras,
+	const void *sorted_info, const uint32_t *sorted_hash, const uint32_t *part_index,
+	uint32_t num_particles, uint32_t *new_num_particles);
+
+/* AbstractNeibsEngine::resetinfo / getinfo (src/engine_neibs.h:60-63; src/cuda/buildneibs.cu:118-146) */
+int b200sph_neibs_resetinfo(b200sph_ctx *ctx);
+int b200sph_neibs_getinfo(b200sph_ctx *ctx, b200sph_neibs_info *out);
+
+/* AbstractNeibsEngine::buildNeibsList (src/engine_neibs.h:89; kernel
+ * src/cuda/buildneibs_kernel.cu:1029-1185). neibs_list must have been pre-filled with 0xFF
+ * by the caller (src/GPUWorker.cc:1883). List contents are bit-exact with the reference. */
+int b200sph_build_neibs(b200sph_ctx *ctx, const void *pos, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint32_t *cell_end,
+	uint16_t *neibs_list, uint32_t num_particles, uint32_t particle_range_end);
+
+/* ---- forces engine ------------------------------------------------------- */
+
+/* AbstractForcesEngine::getFmaxElements / getFmaxTempElements / round_particles
+ * (src/engine_forces.h:157-161,108; src/cuda/forces.cu:540-554,961-965) */
+uint32_t b200sph_fmax_elements(uint32_t n);
+uint32_t b200sph_fmax_temp_elements(uint32_t n);
+uint32_t b200sph_round_particles(uint32_t n);
+
+/* AbstractForcesEngine::basicstep (src/engine_forces.h:133; src/cuda/forces.cu:901-932,718-799):
+ * the reference's forcesDevice<F,F> + <F,B> + <B,F> + finalizeforcesDevice in ONE fused
+ * launch. forces must have been zeroed by the caller (src/GPUWorker.cc:1949) - the result
+ * overwrites it. cfl receives one max per 128-particle block at cfl[cfl_offset + block];
+ * the number of blocks written is returned through num_cfl_blocks (the reference returns it). */
+int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	void *forces, float *cfl,
+	uint32_t num_particles, uint32_t from_particle, uint32_t to_particle,
+	uint32_t cfl_offset, uint32_t *num_cfl_blocks);
+
+/* Diagnostic (no reference counterpart): the per-particle {P/rho^2, sound speed} pairs the forces
+ * kernel uses, evaluated with the same device __powf expressions as the reference's P() and
+ * soundSpeed() (src/cuda/phys_core.cu:99-136). out = float2[num_particles] (device). Lets a
+ * CPU checker separate the GPU's approximate-pow rounding from the summation logic. */
+int b200sph_eos_probe(b200sph_ctx *ctx, const void *vel, const void *info, void *out, uint32_t num_particles);
+
+/* AbstractForcesEngine::dtreduce (src/engine_forces.h:163; src/cuda/forces.cu:557-607).
+ * Synchronises the stream and returns dt on the host, like the reference. */
+int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl,
+	uint32_t num_blocks, float *dt_out);
+
+/* ---- integration engine -------------------------------------------------- */
+
+/* AbstractIntegrationEngine::basicstep (src/engine_integration.h:117; src/cuda/euler.cu:330-372;
+ * kernel src/cuda/euler_kernel.def:396-540). step = 1 (predictor, dt = dt/2 passed by the
+ * caller as in the reference) or 2 (corrector). old_* = state n, forces = current state. */
+int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
+	const void *info, const uint32_t *hash, const void *forces,
+	void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPH_H */

@@ -1,0 +1,106 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, validates options like the reference's framework factory (unsupported combinations
+fail loudly, src/cuda/cudasimframework.cu:147-155) and refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from gpusph_b200 import capi
+from gpusph_b200.problems import lattice_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200sph.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200sph_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"libb200sph.so does not export {s}"
+    # and the ctypes prototypes cover the header exactly
+    assert sorted(capi.PROTOTYPES) == syms
+
+
+def test_abi_version_and_struct_size():
+    lib = capi.load()
+    assert lib.b200sph_abi_version() == capi.ABI_VERSION
+    # layout check: the C compiler and ctypes must agree on sizeof(b200sph_params)
+    src = '#include "b200sph.h"\n#include <stdio.h>\nint main(){printf("%zu %zu", sizeof(b200sph_params), sizeof(b200sph_neibs_info));return 0;}'
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == C.sizeof(capi.Params)
+    assert int(out[1]) == C.sizeof(capi.NeibsInfo)
+
+
+def test_validate_accepts_supported_and_rejects_unsupported():
+    lib = capi.load()
+    params, _ = lattice_problem(4)
+    assert lib.b200sph_validate(C.byref(params)) == 0
+    for field, bad in [("kerneltype", 1), ("sph_formulation", 3), ("boundarytype", capi.SA_BOUNDARY),
+                       ("boundarytype", capi.LJ_BOUNDARY), ("densitydiffusiontype", capi.RHODIFF_BREZZI),
+                       ("turbmodel", 2), ("rheologytype", 3)]:
+        p = params.copy()
+        setattr(p, field, bad)
+        assert lib.b200sph_validate(C.byref(p)) == capi.E_UNSUP, field
+        with pytest.raises(capi.B200Unsupported):
+            capi.check(lib.b200sph_validate(C.byref(p)))
+        assert b"unsupported" in lib.b200sph_last_error()
+    p = params.copy()
+    p.abi_version = 99
+    assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL
+    p = params.copy()
+    p.grid_size[1] = 0
+    with pytest.raises(ValueError):
+        capi.check(lib.b200sph_validate(C.byref(p)))
+    p = params.copy()
+    p.coord[0] = p.coord[1]
+    assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL
+
+
+def test_size_helpers_match_reference_formulas():
+    lib = capi.load()
+    # getFmaxElements = round_up(div_up(n,128),4); round_particles (src/cuda/forces.cu:540-554,961-965)
+    for n in [0, 1, 127, 128, 129, 511, 512, 513, 84444, 8_000_000]:
+        assert lib.b200sph_fmax_elements(n) == ((n + 127) // 128 + 3) // 4 * 4
+        assert lib.b200sph_round_particles(n) == (n // 128) * 128
+    assert lib.b200sph_fmax_temp_elements(4) == 1
+    assert lib.b200sph_fmax_temp_elements(1024) == 1
+    assert lib.b200sph_fmax_temp_elements(1028) == 4
+    assert lib.b200sph_fmax_temp_elements(62500) == 64
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (never route through a CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load()
+    assert lib.b200sph_device_count() == 0
+    params, parts = lattice_problem(4)
+    h = C.c_void_p()
+    assert lib.b200sph_create(C.byref(params), C.byref(h)) == capi.E_NODEV
+    assert b"no CPU fallback" in lib.b200sph_last_error()
+    from gpusph_b200.simulation import Worker
+    with pytest.raises(capi.B200Error):
+        Worker(params, parts)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under gpusph_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "gpusph_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and False, f"{f} mentions the oracle"

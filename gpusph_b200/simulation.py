@@ -29,7 +29,7 @@ class Worker:
 
     def __init__(self, params: capi.Params, particles: ParticleArrays, device=None, *,
                  buildneibsfreq: int = 10, clobber: bool = False, fixed_dt: float | None = None,
-                 compact_dev_map: np.ndarray | None = None):
+                 compact_dev_map: np.ndarray | None = None, start_iteration: int = 0, dt: float | None = None):
         self.framework = SimFramework(params, device)
         self.params = self.framework.params
         self.device = self.framework.ctx.device
@@ -70,9 +70,9 @@ class Worker:
         self.vel[0][:n].copy_(_dev(particles.vel, dev))
         self.info[:n].copy_(_dev(particles.info.view(np.int16), dev))
         self.hash[:n].copy_(_dev(particles.hash.view(np.int32), dev))
-        self.iterations = 0
+        self.iterations = start_iteration  # > 0 when resuming from a checkpoint: the first rebuild then uses calcHash
         self.t = 0.0
-        self.dt = float(fixed_dt) if fixed_dt is not None else initial_dt(self.params)
+        self.dt = float(fixed_dt) if fixed_dt is not None else (float(dt) if dt is not None else initial_dt(self.params))
         self.last_neibs_info = None
         self.total_interactions = 0       # sum over steps of list entries x 2 force evaluations
         self.launches = 0                 # hand-written kernels launched (CUB's sort passes not counted)
@@ -134,7 +134,7 @@ class Worker:
 
     def step(self) -> None:
         """One predictor-corrector time step (src/integrators/PredictorCorrectorIntegrator.cc:917-1068)."""
-        if self.iterations % self.buildneibsfreq == 0:
+        if self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None:
             self.build_neibs()
         n, end = self.numParticles, self.particleRangeEnd
         cur, oth = self.cur, 1 - self.cur

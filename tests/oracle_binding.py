@@ -122,7 +122,7 @@ def euler(params, old_pos, old_vel, info, hashv, f, dt, step, range_end=None):
 class OracleWorker:
     """CPU twin of gpusph_b200.simulation.Worker built from the oracle functions (same call order)."""
 
-    def __init__(self, params, particles: ParticleArrays, buildneibsfreq: int = 10, fixed_dt=None):
+    def __init__(self, params, particles: ParticleArrays, buildneibsfreq: int = 10, fixed_dt=None, start_iteration: int = 0, dt=None):
         self.params = params
         self.pos = particles.pos.copy()
         self.vel = particles.vel.copy()
@@ -130,10 +130,10 @@ class OracleWorker:
         self.hash = particles.hash.copy()
         self.n = particles.n
         self.buildneibsfreq = buildneibsfreq
-        self.iterations = 0
+        self.iterations = start_iteration
         self.t = 0.0
         self.fixed_dt = fixed_dt
-        self.dt = fixed_dt if fixed_dt is not None else initial_dt(params)
+        self.dt = fixed_dt if fixed_dt is not None else (dt if dt is not None else initial_dt(params))
         self.neibslist = None
         self.neibs_info = None
 
@@ -150,7 +150,7 @@ class OracleWorker:
         self.neibslist, self.neibs_info = build_neibs(self.params, self.pos, self.info, self.hash, self.cs, self.ce)
 
     def step(self, dt=None):
-        if self.iterations % self.buildneibsfreq == 0:
+        if self.iterations % self.buildneibsfreq == 0 or self.neibslist is None:
             self.build_neibs()
         dt = self.dt if dt is None else dt
         P = self.params

@@ -1,0 +1,135 @@
+"""Parity against the REAL reference: fixtures under tests/golden/ are HotFile checkpoints written by
+the shim-built, otherwise unmodified GPUSPH binary (oracle/_ref/DamBreak3D, see oracle/build_ref.sh)
+on a B200, packed by oracle/gen_golden.py. Each fixture holds the reference's particle state at
+iterations 0, 10, 20 and 21 of a small DamBreak3D run.
+
+* CPU (not gpu): the oracle restatement reproduces the reference — pins the oracle.
+* GPU: the CUDA engines, through the C ABI, reproduce the reference.
+
+Bar: hash and sorted particle order (ids) bit-exact after a neighbour rebuild + one step from the
+reference's own state (iteration 20 -> 21); positions within 2e-6 dp and velocities within 2e-5 of the
+velocity scale (2e-7 on rho/rho0 - 1) after that step; after 10 steps (0 -> 10, 10 -> 20) within 1e-4 dp /
+1e-3 / 5e-5 (the CPU cannot reproduce the GPU's approximate __powf bit for bit; the GPU engines use it
+like the reference).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from gpusph_b200 import capi
+from gpusph_b200.problems import ParticleArrays, global_positions, initial_dt, make_params
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+def load(path):
+    d = np.load(path)
+    dp = float(d["deltap"])
+    states = {}
+    for it in d["iterations"]:
+        it = int(it)
+        states[it] = (ParticleArrays(d[f"pos_{it}"], d[f"vel_{it}"], d[f"info_{it}"], d[f"hash_{it}"]),
+                      float(d[f"t_{it}"]), float(d[f"dt_{it}"]))
+    n = states[0][0].n
+    # DamBreak3D: origin 0, size 1.6 x 0.67 x 0.6 (src/problems/DamBreak3D.cu:107-122), neiblist 128,
+    # artificial viscosity, c0 = 20, gamma = 7, Colagrossi xi = 0.1 / Ferrari coefficient 0.1 (:46,:95)
+    params = make_params(origin=(0, 0, 0), size=(1.6, 0.67, 0.6), deltap=dp, allocated_particles=n,
+                         densitydiffusion=int(d["rhodiff"]), density_diff_coeff=0.1 if int(d["rhodiff"]) else None)
+    return params, states
+
+
+def ids_of(info):
+    return (info[:, 3].astype(np.int64) << 16) | info[:, 2]
+
+
+def compare(params, got: ParticleArrays, exp: ParticleArrays, pos_tol_dp, vel_tol, exact_order, rho_tol=None):
+    assert got.n == exp.n
+    if exact_order:
+        assert np.array_equal(got.hash, exp.hash), "cell hash differs from the reference"
+        assert np.array_equal(got.info, exp.info), "sorted particle order differs from the reference"
+    og, oe = np.argsort(ids_of(got.info)), np.argsort(ids_of(exp.info))
+    assert np.array_equal(ids_of(got.info)[og], ids_of(exp.info)[oe])
+    live = (exp.info[oe, 0] & 7) != capi.PT_TESTPOINT      # the reference's TESTPOINTS post-process rewrites their vel
+    gp = global_positions(params, got.pos, got.hash)[og]
+    ep = global_positions(params, exp.pos, exp.hash)[oe]
+    perr = np.abs(gp - ep).max() / float(params.deltap)
+    vs = max(np.abs(exp.vel[:, :3]).max(), 1e-3)
+    verr = np.abs(got.vel[og][live, :3] - exp.vel[oe][live, :3]).max() / vs
+    rerr = np.abs(got.vel[og][live, 3] - exp.vel[oe][live, 3]).max()
+    assert perr < pos_tol_dp, f"position error {perr:.2e} dp"
+    assert verr < vel_tol, f"velocity error {verr:.2e}"
+    assert rerr < (rho_tol if rho_tol is not None else vel_tol * 1e-2), f"density error {rerr:.2e}"
+    assert np.array_equal(got.pos[og, 3], exp.pos[oe, 3])   # masses untouched
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_fixture_matches_host_setup(path):
+    """The parameters we derive (grid, cell size, initial dt) are the reference's: its initial state hashes
+    consistently with our grid and its first dt equals ProblemCore::check_dt restated in problems.py."""
+    params, states = load(path)
+    p0, t0, dt0 = states[0]
+    assert dt0 == pytest.approx(initial_dt(params), rel=1e-7)
+    assert int(p0.hash.max()) < params.num_cells
+    cs = np.array([params.cell_size[a] for a in range(3)])
+    assert (np.abs(p0.pos[:, :3]) <= 0.5 * cs * (1 + 1e-5)).all()
+    gp = global_positions(params, p0.pos, p0.hash)
+    assert gp.min() >= -1e-6 and (gp.max(axis=0) <= np.array([1.6, 0.67, 0.6]) + 1e-6).all()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_reference_single_step(path):
+    params, states = load(path)
+    s20, _, dt20 = states[20]
+    s21, _, dt21 = states[21]
+    w = ob.OracleWorker(params, s20, start_iteration=20, dt=dt20)
+    w.step()
+    compare(params, w.download(), s21, pos_tol_dp=2e-6, vel_tol=2e-5, exact_order=True)
+    assert w.dt == pytest.approx(dt21, rel=1e-5)
+    assert w.neibs_info.has_too_many_neibs == -1
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("start", [0, 10])
+def test_oracle_reproduces_reference_ten_steps(path, start):
+    params, states = load(path)
+    s0, t0, dt0 = states[start]
+    s1, t1, dt1 = states[start + 10]
+    w = ob.OracleWorker(params, s0, start_iteration=start, dt=dt0)
+    for _ in range(10):
+        w.step()
+    assert w.t == pytest.approx(t1 - t0, rel=1e-5)
+    assert w.dt == pytest.approx(dt1, rel=1e-4)
+    compare(params, w.download(), s1, pos_tol_dp=1e-4, vel_tol=1e-3, exact_order=False, rho_tol=5e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_gpu_reproduces_reference_single_step(path):
+    from gpusph_b200.simulation import Worker
+    params, states = load(path)
+    s20, _, dt20 = states[20]
+    s21, _, dt21 = states[21]
+    w = Worker(params, s20, 0, start_iteration=20, dt=dt20, clobber=True)
+    w.step()
+    compare(params, w.download(), s21, pos_tol_dp=2e-6, vel_tol=2e-5, exact_order=True)
+    assert w.dt == pytest.approx(dt21, rel=1e-5)
+    assert w.last_neibs_info.has_too_many_neibs == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("start", [0, 10])
+def test_gpu_reproduces_reference_ten_steps(path, start):
+    from gpusph_b200.simulation import Worker
+    params, states = load(path)
+    s0, t0, dt0 = states[start]
+    s1, t1, dt1 = states[start + 10]
+    w = Worker(params, s0, 0, start_iteration=start, dt=dt0, clobber=True)
+    for _ in range(10):
+        w.step()
+    assert w.t == pytest.approx(t1 - t0, rel=1e-5)
+    assert w.dt == pytest.approx(dt1, rel=1e-4)
+    compare(params, w.download(), s1, pos_tol_dp=1e-4, vel_tol=1e-3, exact_order=False, rho_tol=5e-5)

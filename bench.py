@@ -130,7 +130,8 @@ def run_reference(args):
         d = tempfile.mkdtemp(prefix="gpusph_ref_")
         dev = ",".join(str(i) for i in range(args.gpus))
         cmd = [binp, "--deltap", str(kw["dp"]), "--maxiter", str(maxiter), "--nosave", "--dir", d,
-               "--device", dev, "--density-diffusion", "1", "--num_obstacles", "0"]
+               "--device", dev, "--density-diffusion", "1", "--num_obstacles", "0",
+               "--debug", "benchmark_command_runtimes"]
         t0 = time.perf_counter()
         p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
         el = time.perf_counter() - t0
@@ -146,15 +147,28 @@ def run_reference(args):
     m = re.findall(r"iteration=[\d,]+, dt=[0-9.eE+-]+s, ([\d,]+) parts", out_k)
     nparts = int(m[-1].replace(",", "")) if m else None
     c_w, c_k = cycle_seconds(out_w), cycle_seconds(out_k)
-    if rc_k != 0 or nparts is None or c_w is None or c_k is None:
+
+    def cmdtimes(text):
+        # per-command totals printed by the reference itself (--debug benchmark_command_runtimes,
+        # src/GPUSPH.cc:118-131): CMDTIMES:<name>\t<num>\t<calls>\t<max ms>\t<total ms>
+        out = {}
+        for ln in text.splitlines():
+            if ln.startswith("CMDTIMES:") and not ln.startswith("CMDTIMES:COMMAND"):
+                f = ln[len("CMDTIMES:"):].split("\t")
+                try:
+                    out[f[0]] = float(f[4])
+                except Exception:
+                    pass
+        return out
+    ct_w, ct_k = cmdtimes(out_w), cmdtimes(out_k)
+    if rc_k != 0 or nparts is None or not ct_k or not ct_w:
         line.update({"unavailable": f"reference binary failed (rc={rc_k}): {out_k[-300:]!r}"})
         print(json.dumps(line))
         return 0
-    # the printed cycle time has 10 ms resolution: use the wall-clock difference of the two runs when the
-    # cycle difference is too coarse to resolve
-    sec = c_k - c_w
-    if sec < 0.2:
-        sec = max(sec, 1e-3)
+    phases = {k: ct_k[k] - ct_w.get(k, 0.0) for k in ct_k}
+    sec = sum(phases.values()) / 1e3
+    line["reference_phase_ms_per_step"] = {k: v / args.steps for k, v in sorted(phases.items(), key=lambda kv: -kv[1])[:8]}
+    line["reference_cycle_seconds_2digits"] = [c_w, c_k]
     ups = nparts * args.steps / sec
     # interactions per particle: measured by our neighbour engine on the same geometry/dp (the reference
     # does not print its numInteractions counter); see DESIGN.md "Measurement"
@@ -176,7 +190,7 @@ def run_reference(args):
                  "particles": nparts, "neibs_per_particle": npp,
                  "cpu_baseline": {"value": val, "unit": "M interactions/s", "cores": 1 + args.gpus, "kind": "reference",
                                   "sample": f"oracle/_ref/DamBreak3D --deltap {kw['dp']} --density-diffusion 1 --num_obstacles 0: "
-                                            f"its printed main-loop time for {args.warmup}+{args.steps} iterations minus that for {args.warmup}; the reference's own CUDA engines "
+                                            f"sum of its own per-command timers (--debug benchmark_command_runtimes) for {args.warmup}+{args.steps} iterations minus that for {args.warmup}; the reference's own CUDA engines "
                                             "on the same GPU (it has no CPU compute path), 1 orchestrator + 1 worker host thread per GPU"},
                  "e2e": {"value": val, "unit": "M interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))

@@ -65,6 +65,10 @@ static void fill_devparams(const b200sph_params *p, DevParams *d)
 		d->gravity[a] = p->gravity[a];
 	}
 	d->periodic = p->periodic;
+	// calcGridHash (src/cuda/cellgrid.cuh:101-106): COORD1 has stride 1, COORD2 stride G.C1, COORD3 stride G.C1*G.C2
+	d->hstride[p->coord[0]] = 1;
+	d->hstride[p->coord[1]] = (int)p->grid_size[p->coord[0]];
+	d->hstride[p->coord[2]] = (int)(p->grid_size[p->coord[0]] * p->grid_size[p->coord[1]]);
 	d->neiblistsize = p->neiblistsize; d->neibboundpos = p->neibboundpos; d->stride = p->neiblist_stride;
 	d->nlSqInflRad = p->nl_sq_influence_radius;
 	d->kerneltype = p->kerneltype; d->densitydiffusiontype = p->densitydiffusiontype; d->boundarytype = p->boundarytype;
@@ -99,6 +103,7 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	fill_devparams(p, &ctx->dp);
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
+	{ const char *e = getenv("B200SPH_FORCES_BATCH"); ctx->forces_batch = e ? atoi(e) : 0; }
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
 	CUDA_TRY(cudaMalloc(&ctx->d_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));

@@ -37,6 +37,7 @@ struct DevParams {
 	float cellSize[3];
 	int gridSize[3];
 	int coord[3];           // axis of COORD1,2,3
+	int hstride[3];         // linear-hash stride of one cell step along x, y, z (derived from coord + gridSize)
 	uint periodic;
 	uint neiblistsize, neibboundpos, stride;
 	float nlSqInflRad;
@@ -69,11 +70,12 @@ struct b200sph_ctx {
 	// scratch (grown on demand)
 	void *sort_tmp; size_t sort_tmp_bytes;
 	uint64_t *keys_in, *keys_out; uint32_t *vals_out; void *info_tmp; size_t sort_cap;
-	float2 *eos; size_t eos_cap;           // per-particle {P/rho^2, sound speed}
+	void *eos; size_t eos_cap;             // packed 48-byte neighbour records (forces.cu pack_kernel)
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions
 	float *h_scalar;                        // pinned host scalar
 	int *d_flag; int *h_flag;
+	int forces_batch;                       // software-pipeline depth of the forces kernel (1,2,4,8)
 };
 
 // ---- error plumbing ----
@@ -97,11 +99,8 @@ __device__ __forceinline__ bool inactive_w(float w) { return !isfinite(w); }
 // linear cell index from grid position, reference calcGridHash (src/cuda/cellgrid.cuh:101-106)
 __device__ __forceinline__ uint grid_hash(const DevParams &P, int gx, int gy, int gz)
 {
-	const int g[3] = { gx, gy, gz };
-	// select by coord without dynamic register indexing
-	auto sel = [&](int c) { return c == 0 ? g[0] : (c == 1 ? g[1] : g[2]); };
-	auto selG = [&](int c) { return c == 0 ? P.gridSize[0] : (c == 1 ? P.gridSize[1] : P.gridSize[2]); };
-	return (uint)(sel(P.coord[2]) * selG(P.coord[1]) * selG(P.coord[0]) + sel(P.coord[1]) * selG(P.coord[0]) + sel(P.coord[0]));
+	// gp.C3*G.C2*G.C1 + gp.C2*G.C1 + gp.C1 with the axis strides precomputed on the host
+	return (uint)(gx * P.hstride[0] + gy * P.hstride[1] + gz * P.hstride[2]);
 }
 // reference calcGridPosFromCellHash (src/cuda/cellgrid.cuh:117-128)
 __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
@@ -123,4 +122,4 @@ __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
 #endif
 
 // ---- internal launchers implemented in the .cu files ----
-int b200_eos_precompute(b200sph_ctx *ctx, const float4 *vel, const ushort4 *info, uint n);
+int b200_eos_precompute(b200sph_ctx *ctx, const float4 *pos, const float4 *vel, const ushort4 *info, uint n);

@@ -1,0 +1,346 @@
+"""Multi-GPU: 1-D slab decomposition with one halo cell layer per side.
+
+Host-side mirror of the reference's multi-device machinery, re-done for one process per GPU and
+torch.distributed (NCCL over NVLink; gloo for the CPU tests):
+
+* cells are owned by ranks in slabs of whole cell layers along the SLOWEST linearisation axis (COORD3;
+  x for the default yzx), so a slab is one contiguous range of cell hashes and, after the sort, one
+  contiguous range of particles (reference: ProblemCore::fillDeviceMapByAxis, src/ProblemCore.cc:1061-1116);
+* every cell gets a 2-bit type — inner / inner-edge / outer-edge (halo) / outer — in the compact device
+  map, OR-ed into hash bits 30-31 by calcHash/fixHash (src/multi_gpu_defines.h:58-72,
+  src/GPUWorker.cc:1560-1634, src/cuda/buildneibs_kernel.cu:768-769), so the sort lays every rank's particles
+  out as [inner | inner-edge | outer-edge] and reorder reports the segment starts;
+* halo copies are integrated locally with the owner's forces, so a particle that crosses a slab face changes
+  owner simply because its new hash falls into the neighbour's cells (reference: CROP + APPEND_EXTERNAL at
+  every neighbour rebuild, src/Integrator.cc:216-221);
+* per force evaluation the owner's FORCES of its inner-edge particles are sent to the neighbour's
+  outer-edge range (reference: UPDATE_EXTERNAL(FORCES), PredictorCorrectorIntegrator.cc:514-519) — one
+  contiguous range per side and buffer, no packing; dt is the MIN over ranks (src/GPUSPH.cc:650-657).
+
+Because neighbour-list order is (cell, type, id) on every rank, the per-particle summation order does not
+depend on the decomposition: N-rank results are bitwise equal to single-rank results.
+
+The numerical work is delegated to a backend: ``CudaBackend`` (the C-ABI engines) in production;
+tests plug in a CPU backend to run the same decomposition/exchange logic at world_size 2 on gloo.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+from .problems import ParticleArrays, initial_dt
+
+CELLTYPE_INNER, CELLTYPE_INNER_EDGE, CELLTYPE_OUTER_EDGE, CELLTYPE_OUTER = 0, 1, 2, 3
+CELLMASK = 0x3FFFFFFF
+
+
+def _i32(v: int) -> int:
+    """uint32 bit pattern as a python int that fits torch.int32."""
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def slab_partition(params: capi.Params, hashes: np.ndarray, world: int) -> list[tuple[int, int]]:
+    """Split the COORD3 cell layers into `world` contiguous slabs with balanced particle counts
+    (reference: fillDeviceMapByAxisBalanced, src/ProblemCore.cc:1119-1200). Every slab gets >= 2 layers."""
+    c3 = params.coord[2]
+    G3 = int(params.grid_size[c3])
+    S = int(params.grid_size[params.coord[0]]) * int(params.grid_size[params.coord[1]])
+    if G3 < 2 * world:
+        raise ValueError(f"cannot split {G3} cell layers over {world} devices (need >= 2 layers each)")
+    layer = (hashes.astype(np.int64) & CELLMASK) // S
+    counts = np.bincount(layer, minlength=G3).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(counts)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        x = int(np.searchsorted(cum, target, side="left"))
+        x = max(x, bounds[-1] + 2)                    # at least 2 layers for the previous slab
+        x = min(x, G3 - 2 * (world - r))              # leave room for the remaining slabs
+        bounds.append(x)
+    bounds.append(G3)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def compact_device_map(params: capi.Params, slab: tuple[int, int], rank: int, world: int) -> np.ndarray:
+    """Per-cell type bits (already shifted to bits 30-31), reference createCompactDeviceMap
+    (src/GPUWorker.cc:1560-1634). Periodicity along the split axis is not supported."""
+    c3 = params.coord[2]
+    if params.periodic & (1 << c3):
+        raise capi.B200Unsupported("periodicity along the slab axis is not implemented for multi-GPU")
+    G3 = int(params.grid_size[c3])
+    S = int(params.grid_size[params.coord[0]]) * int(params.grid_size[params.coord[1]])
+    xs, xe = slab
+    t = np.full(G3, CELLTYPE_OUTER, dtype=np.uint32)
+    t[xs:xe] = CELLTYPE_INNER
+    if rank > 0:
+        t[xs] = CELLTYPE_INNER_EDGE
+        t[xs - 1] = CELLTYPE_OUTER_EDGE
+    if rank < world - 1:
+        t[xe - 1] = CELLTYPE_INNER_EDGE
+        t[xe] = CELLTYPE_OUTER_EDGE
+    return np.repeat(t << 30, S).astype(np.uint32)
+
+
+class CudaBackend:
+    """Numerical work through the C ABI (gpusph_b200.engines)."""
+
+    def __init__(self, params: capi.Params, device):
+        from .engines import SimFramework
+        self.fw = SimFramework(params, device)
+        self.device = self.fw.ctx.device
+
+    def _b(self, **kw):
+        from . import engines as E
+        m = {"pos": E.BUFFER_POS, "vel": E.BUFFER_VEL, "info": E.BUFFER_INFO, "hash": E.BUFFER_HASH,
+             "pidx": E.BUFFER_PARTINDEX, "cs": E.BUFFER_CELLSTART, "ce": E.BUFFER_CELLEND, "nl": E.BUFFER_NEIBSLIST,
+             "forces": E.BUFFER_FORCES, "cfl": E.BUFFER_CFL, "cdm": E.BUFFER_COMPACT_DEV_MAP}
+        return E.BufferList({m[k]: v for k, v in kw.items() if v is not None})
+
+    def hash_update(self, first, pos, hashv, pidx, info, cdm, n):
+        b = self._b(pos=pos, hash=hashv, pidx=pidx, info=info, cdm=cdm)
+        (self.fw.neibsEngine.fixHash if first else self.fw.neibsEngine.calcHash)(b, b, n)
+
+    def sort(self, hashv, info, pidx, n):
+        b = self._b(hash=hashv, info=info, pidx=pidx)
+        self.fw.neibsEngine.sort(b, b, n)
+
+    def reorder(self, cs, ce, seg, spos, svel, pos, vel, info, hashv, pidx, n, newn):
+        srt = self._b(pos=spos, vel=svel, info=info, hash=hashv, pidx=pidx, cs=cs, ce=ce)
+        uns = self._b(pos=pos, vel=vel)
+        self.fw.neibsEngine.reorderDataAndFindCellStart(seg, srt, uns, n, newn)
+
+    def build_neibs(self, pos, info, hashv, cs, ce, nl, n, range_end):
+        b = self._b(pos=pos, info=info, hash=hashv, cs=cs, ce=ce, nl=nl)
+        self.fw.neibsEngine.resetinfo()
+        self.fw.neibsEngine.buildNeibsList(b, b, n, range_end)
+        return self.fw.neibsEngine.getinfo()
+
+    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to):
+        b = self._b(pos=pos, vel=vel, info=info, hash=hashv, cs=cs, nl=nl, forces=forces, cfl=cfl)
+        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, 0)
+
+    def dtreduce(self, cfl, nblocks):
+        b = self._b(cfl=cfl)
+        return self.fw.forcesEngine.dtreduce(b, b, nblocks)
+
+    def euler(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, dt, step):
+        rd = self._b(pos=opos, vel=ovel, info=info, hash=hashv, forces=forces)
+        wr = self._b(pos=npos, vel=nvel)
+        self.fw.integrationEngine.basicstep(rd, wr, n, range_end, dt, step)
+
+    def fmax_elements(self, n):
+        return self.fw.forcesEngine.getFmaxElements(n)
+
+
+class SlabWorker:
+    """One rank's particle system in a slab decomposition; same stepping interface as simulation.Worker."""
+
+    def __init__(self, params: capi.Params, particles: ParticleArrays, device=None, *, rank: int, world: int,
+                 backend=None, buildneibsfreq: int = 10, fixed_dt: float | None = None, alloc_factor: float = 1.5,
+                 group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.buildneibsfreq = buildneibsfreq
+        self.fixed_dt = fixed_dt
+        self.slabs = slab_partition(params, particles.hash, world)
+        self.slab = self.slabs[rank]
+        c3 = params.coord[2]
+        S = int(params.grid_size[params.coord[0]]) * int(params.grid_size[params.coord[1]])
+        self.S = S
+        xs, xe = self.slab
+        layer = (particles.hash.astype(np.int64) & CELLMASK) // S
+        lo, hi = xs - (1 if rank > 0 else 0), xe + (1 if rank < world - 1 else 0)
+        sel = np.flatnonzero((layer >= lo) & (layer < hi))          # own cells + halo layers
+        n = sel.shape[0]
+        self.allocated = int(n * alloc_factor) + 1024
+        p = params.copy()
+        p.neiblist_stride = self.allocated
+        self.params = p
+        # backend: None -> the CUDA engines; or a factory called with this rank's params (stride = local allocation)
+        self.backend = backend(p) if backend is not None else CudaBackend(p, device)
+        dev = self.backend.device
+        self.device = dev
+        A = self.allocated
+        f4 = lambda: torch.zeros((A, 4), dtype=torch.float32, device=dev)
+        self.pos, self.vel, self.cur = [f4(), f4()], [f4(), f4()], 0
+        self.info = torch.zeros((A, 4), dtype=torch.int16, device=dev)
+        self.hash = torch.zeros(A, dtype=torch.int32, device=dev)
+        self.partindex = torch.zeros(A, dtype=torch.int32, device=dev)
+        self.forces_buf = f4()
+        nc = p.num_cells
+        self.cellstart = torch.empty(nc, dtype=torch.int32, device=dev)
+        self.cellend = torch.empty(nc, dtype=torch.int32, device=dev)
+        self.neibslist = torch.full((int(p.neiblistsize), A), -1, dtype=torch.int16, device=dev)
+        self.cfl = torch.zeros(self.backend.fmax_elements(A), dtype=torch.float32, device=dev)
+        self.segments = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.new_num = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cdm = torch.from_numpy(compact_device_map(p, self.slab, rank, world).view(np.int32)).to(dev)
+        self.pos[0][:n].copy_(torch.from_numpy(particles.pos[sel]).to(dev))
+        self.vel[0][:n].copy_(torch.from_numpy(particles.vel[sel]).to(dev))
+        self.info[:n].copy_(torch.from_numpy(particles.info[sel].view(np.int16)).to(dev))
+        self.hash[:n].copy_(torch.from_numpy(particles.hash[sel].view(np.int32)).to(dev))
+        self.numParticles = n          # own + halo
+        self.numOwn = 0                # set by the first rebuild
+        self.iterations, self.t = 0, 0.0
+        self.dt = float(fixed_dt) if fixed_dt is not None else initial_dt(p)
+        self.last_neibs_info = None
+        self.total_interactions = 0
+        self.launches = 0
+        # ranges for the per-evaluation force exchange: (start, count)
+        self.edge_left = self.edge_right = self.halo_left = self.halo_right = (0, 0)
+
+    # ------------------------------------------------------------------ communication helpers
+    def _left(self):
+        return self.rank - 1 if self.rank > 0 else None
+
+    def _right(self):
+        return self.rank + 1 if self.rank < self.world - 1 else None
+
+    def _exchange(self, sends, recvs):
+        """sends/recvs: lists of (tensor, peer). One batched NCCL group (reference: transferBursts)."""
+        # raw bytes: NCCL has no int16, and the payload is opaque to the transport anyway
+        ops = [dist.P2POp(dist.isend, t.view(torch.uint8), peer, self.group) for t, peer in sends if t.numel()]
+        ops += [dist.P2POp(dist.irecv, t.view(torch.uint8), peer, self.group) for t, peer in recvs if t.numel()]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _exchange_counts(self, n_to_left: int, n_to_right: int):
+        dev = self.device
+        out = {}
+        sends, recvs = [], []
+        sl = torch.tensor([n_to_left], dtype=torch.int64, device=dev)
+        sr = torch.tensor([n_to_right], dtype=torch.int64, device=dev)
+        rl = torch.zeros(1, dtype=torch.int64, device=dev)
+        rr = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self._left() is not None:
+            sends.append((sl, self._left())); recvs.append((rl, self._left()))
+        if self._right() is not None:
+            sends.append((sr, self._right())); recvs.append((rr, self._right()))
+        self._exchange(sends, recvs)
+        out["from_left"] = int(rl.item()) if self._left() is not None else 0
+        out["from_right"] = int(rr.item()) if self._right() is not None else 0
+        return out
+
+    # ------------------------------------------------------------------ neighbour rebuild
+    def build_neibs(self) -> None:
+        be = self.backend
+        n = self.numParticles
+        cur, oth = self.cur, 1 - self.cur
+        # CALCHASH (with the compact device map) + SORT + REORDER  (src/Integrator.cc:93-160)
+        be.hash_update(self.iterations == 0, self.pos[cur], self.hash, self.partindex, self.info, self.cdm, n)
+        be.sort(self.hash, self.info, self.partindex, n)
+        self.cellstart.fill_(-1)
+        be.reorder(self.cellstart, self.cellend, self.segments, self.pos[oth], self.vel[oth], self.pos[cur], self.vel[cur],
+                   self.info, self.hash, self.partindex, n, self.new_num)
+        self.cur = cur = oth
+        oth = 1 - cur
+        seg = self.segments.cpu().numpy().view(np.uint32)
+        n_active = int(self.new_num.item())
+        # CROP: keep what this rank owns = [inner | inner-edge]; drop stale halo copies and outer particles
+        first_ext = min([int(s) for s in seg[2:4] if s != 0xFFFFFFFF] + [n_active])
+        n_own = first_ext
+        # inner-edge sub-ranges facing each neighbour (contiguous: the slab axis is the slowest hash digit)
+        h = self.hash[:n_own]
+        layer = torch.div(torch.bitwise_and(h, CELLMASK), self.S, rounding_mode="floor")
+        xs, xe = self.slab
+        zero = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+        def layer_range(x):
+            m = (layer == x).nonzero()
+            if m.numel() == 0:
+                return (0, 0)
+            a, b = int(m[0].item()), int(m[-1].item()) + 1
+            return (a, b - a)
+        self.edge_left = layer_range(xs) if self._left() is not None else (0, 0)
+        self.edge_right = layer_range(xe - 1) if self._right() is not None else (0, 0)
+        # APPEND_EXTERNAL: fresh halo copies from the owners (pos, vel, info, hash)
+        cnt = self._exchange_counts(self.edge_left[1], self.edge_right[1])
+        nl_, nr_ = cnt["from_left"], cnt["from_right"]
+        if n_own + nl_ + nr_ > self.allocated:
+            raise MemoryError(f"rank {self.rank}: {n_own + nl_ + nr_} particles exceed the allocation {self.allocated}")
+        self.halo_left = (n_own, nl_)
+        self.halo_right = (n_own + nl_, nr_)
+        sends, recvs = [], []
+        for buf in (self.pos[cur], self.vel[cur], self.info, self.hash):
+            if self._left() is not None:
+                a, c = self.edge_left
+                sends.append((buf[a:a + c], self._left()))
+                recvs.append((buf[self.halo_left[0]:self.halo_left[0] + nl_], self._left()))
+            if self._right() is not None:
+                a, c = self.edge_right
+                sends.append((buf[a:a + c], self._right()))
+                recvs.append((buf[self.halo_right[0]:self.halo_right[0] + nr_], self._right()))
+        self._exchange(sends, recvs)
+        n = n_own + nl_ + nr_
+        # received hashes carry the sender's INNER_EDGE bits: they are OUTER_EDGE here
+        ext = self.hash[n_own:n]
+        ext.copy_(torch.bitwise_or(torch.bitwise_and(ext, CELLMASK), _i32(CELLTYPE_OUTER_EDGE << 30)))
+        self.numParticles, self.numOwn = n, n_own
+        # cell ranges over own + halo (the concatenation is already sorted): identity permutation through reorder
+        self.partindex[:n].copy_(torch.arange(n, dtype=torch.int32, device=self.device))
+        self.cellstart.fill_(-1)
+        be.reorder(self.cellstart, self.cellend, self.segments, self.pos[oth], self.vel[oth], self.pos[cur], self.vel[cur],
+                   self.info, self.hash, self.partindex, n, self.new_num)
+        self.cur = oth
+        # BUILDNEIBS for the particles this rank owns (their neighbours include the halo)
+        self.last_neibs_info = be.build_neibs(self.pos[self.cur], self.info, self.hash, self.cellstart, self.cellend,
+                                              self.neibslist, n, n_own)
+        self.launches += 8
+
+    # ------------------------------------------------------------------ time stepping
+    def _forces(self, which: int) -> float:
+        be = self.backend
+        n, n_own = self.numParticles, self.numOwn
+        nblocks = be.forces(self.pos[which], self.vel[which], self.info, self.hash, self.cellstart, self.neibslist,
+                            self.forces_buf, self.cfl, n, 0, n_own)
+        self.launches += 2
+        # UPDATE_EXTERNAL(FORCES): owner's inner-edge forces -> neighbour's halo range
+        f = self.forces_buf
+        sends, recvs = [], []
+        if self._left() is not None:
+            sends.append((f[self.edge_left[0]:self.edge_left[0] + self.edge_left[1]], self._left()))
+            recvs.append((f[self.halo_left[0]:self.halo_left[0] + self.halo_left[1]], self._left()))
+        if self._right() is not None:
+            sends.append((f[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
+            recvs.append((f[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
+        self._exchange(sends, recvs)
+        if self.fixed_dt is not None:
+            return self.fixed_dt
+        dt = be.dtreduce(self.cfl, nblocks) if n_own > 0 else float("inf")
+        self.launches += 1
+        t = torch.tensor([dt], dtype=torch.float32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)      # src/GPUSPH.cc:650-657
+        return float(t.item())
+
+    def step(self) -> None:
+        if self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None:
+            self.build_neibs()
+        be = self.backend
+        n = self.numParticles
+        cur, oth = self.cur, 1 - self.cur
+        dt = self.dt
+        dt1 = self._forces(cur)
+        be.euler(self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n, dt / 2, 1)
+        dt2 = self._forces(oth)
+        be.euler(self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n, dt, 2)
+        self.launches += 2
+        self.cur = oth
+        self.iterations += 1
+        self.t += dt
+        self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
+        if self.fixed_dt is None:
+            self.dt = min(dt1, dt2)
+
+    def download_own(self) -> ParticleArrays:
+        n = self.numOwn
+        return ParticleArrays(self.pos[self.cur][:n].cpu().numpy(), self.vel[self.cur][:n].cpu().numpy(),
+                              self.info[:n].cpu().numpy().view(np.uint16), self.hash[:n].cpu().numpy().view(np.uint32))
+
+    def forces_once(self) -> None:
+        """One force evaluation on the current state without exchange (bench.py roofline timing)."""
+        self.backend.forces(self.pos[self.cur], self.vel[self.cur], self.info, self.hash, self.cellstart, self.neibslist,
+                            self.forces_buf, self.cfl, self.numParticles, 0, self.numOwn)

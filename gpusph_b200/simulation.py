@@ -156,6 +156,11 @@ class Worker:
         if self.fixed_dt is None:
             self.dt = min(dt1, dt2)                # src/GPUWorker.cc:2224-2229, src/GPUSPH.cc:650-657
 
+    def forces_once(self) -> None:
+        """One force evaluation on the current state (bench.py roofline timing)."""
+        s = self.state(self.cur)
+        self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0)
+
     # ---- host copies ----
     def download(self) -> ParticleArrays:
         n = self.numParticles

@@ -103,13 +103,20 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	fill_devparams(p, &ctx->dp);
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
-	{ const char *e = getenv("B200SPH_FORCES_BATCH"); ctx->forces_batch = e ? atoi(e) : 0; }
+	{ const char *e = getenv("B200SPH_FORCES_TILES"); ctx->use_tiles = e ? atoi(e) : 0; }   // staged kernel is opt-in: measured slower than the gather kernel
+	{	// tile configurations: keep in sync with pick_kernels() in forces.cu
+		static const int cfgs[7][2] = { {64, 1024}, {128, 1536}, {128, 1152}, {64, 1024}, {64, 768}, {128, 1536}, {64, 1024} };
+		const char *e = getenv("B200SPH_TILE_CFG"); int c = e ? atoi(e) : 0; if (c < 0 || c > 5) c = 0;
+		ctx->tile_cfg = c; ctx->tile_p = cfgs[c][0]; ctx->tile_s = cfgs[c][1]; }
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
 	CUDA_TRY(cudaMalloc(&ctx->d_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_flag, sizeof(int)));
 	CUDA_TRY(cudaMemset(ctx->d_counters, 0, sizeof(NeibsCounters)));
+	CUDA_TRY(cudaMalloc(&ctx->d_tile_info, 4 * sizeof(uint)));
+	CUDA_TRY(cudaMallocHost(&ctx->h_tile_info, 4 * sizeof(uint)));
+	CUDA_TRY(cudaEventCreateWithFlags(&ctx->tiles_event, cudaEventDisableTiming));
 	*out = ctx;
 	return B200SPH_OK;
 }
@@ -119,7 +126,7 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 	if (!ctx) return B200SPH_OK;
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
-	cudaFree(ctx->info_tmp); cudaFree(ctx->eos); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);
 	free(ctx);
 	return B200SPH_OK;

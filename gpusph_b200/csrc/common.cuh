@@ -53,6 +53,15 @@ struct DevParams {
 	float gravity[3];
 };
 
+// One CTA of the staged forces kernel: a run of consecutive non-empty cells along COORD1 inside one
+// (COORD2, COORD3) row, plus the particle ranges of the 9 neighbouring rows that cover its 27-cell
+// neighbourhood (each row of cells is one contiguous particle range because COORD1 is the fastest hash digit).
+struct Tile {
+	uint first, count;      // central particles [first, first+count)
+	uint row_start[9];      // first staged particle of neighbour row r = (d2+1) + 3*(d3+1)
+	uint row_count[9];      // staged particles of that row (0 = none)
+};
+
 struct NeibsCounters {     // mirrors the reference's device counters, src/cuda/buildneibs_kernel.cu:108-112
 	int numInteractions;
 	int maxFluidBoundaryNeibs;
@@ -70,12 +79,18 @@ struct b200sph_ctx {
 	// scratch (grown on demand)
 	void *sort_tmp; size_t sort_tmp_bytes;
 	uint64_t *keys_in, *keys_out; uint32_t *vals_out; void *info_tmp; size_t sort_cap;
-	void *eos; size_t eos_cap;             // packed 48-byte neighbour records (forces.cu pack_kernel)
+	float4 *aux; size_t aux_cap;           // per-particle {P/rho^2, sound speed, density, fluid#} (forces.cu aux_kernel)
+	// tiles of the staged forces kernel, rebuilt with the neighbour list
+	Tile *tiles; size_t tiles_cap; uint *row_tiles; size_t row_tiles_cap;
+	uint *d_tile_info; uint *h_tile_info;   // {numTiles, overflow flag}
+	cudaEvent_t tiles_event; int tiles_state;   // 0 none, 1 copy in flight, 2 valid
+	uint num_tiles; uint tiles_range_end; const uint32_t *tiles_cellstart;
+	int use_tiles;                          // env B200SPH_FORCES_TILES (default 0)
+	int tile_cfg, tile_p, tile_s;           // tile configuration (env B200SPH_TILE_CFG): threads per tile, staged slots
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions
 	float *h_scalar;                        // pinned host scalar
 	int *d_flag; int *h_flag;
-	int forces_batch;                       // software-pipeline depth of the forces kernel (1,2,4,8)
 };
 
 // ---- error plumbing ----
@@ -122,4 +137,5 @@ __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
 #endif
 
 // ---- internal launchers implemented in the .cu files ----
-int b200_eos_precompute(b200sph_ctx *ctx, const float4 *pos, const float4 *vel, const ushort4 *info, uint n);
+int b200_build_tiles(b200sph_ctx *ctx, const uint32_t *cell_start, const uint32_t *cell_end, uint range_end);
+void b200_invalidate_tiles(b200sph_ctx *ctx);

@@ -1,86 +1,59 @@
-// forces.cu — forces engine: fused pair-interaction kernel, CFL reduction, dt.
+// forces.cu — forces engine: fused pair-interaction kernels, CFL reduction, dt.
 //
-// Behavioural specification: GPUSPH src/cuda/forces.cu + forces_kernel.def (cited inline).
-// The reference evaluates one half-step with FOUR launches (forcesDevice<fluid,fluid>,
-// <fluid,boundary>, <boundary,fluid>, finalizeforcesDevice), each re-reading the particle and
-// read-modify-writing forces[] in global memory, and re-evaluates the equation of state
-// (two __powf = 4 MUFU + an IEEE division) for BOTH particles of every pair.
-// Here:
-//  * one pre-pass evaluates P/rho^2 and the sound speed ONCE per particle (same __powf
-//    expressions, so the values are the ones the reference recomputes per pair);
-//  * one launch walks both neighbour-list sections of a particle, keeps the accumulator in
-//    registers, applies the finalize step (1/rho0, gravity) and reduces the CFL term with
-//    warp shuffles — forces[] is written exactly once.
-// Summation order inside each list section is the reference's (list order); the fluid and
-// boundary partial sums are combined as  (0 + sum_fluid) + sum_boundary  like the reference's
-// RMW sequence, so results differ from the reference only through FMA contraction choices.
-#include "common.cuh"
+// Behavioural specification: GPUSPH src/cuda/forces.cu + forces_kernel.def (cited inline and in pair_physics.cuh).
+// The reference evaluates one half-step with FOUR launches (forcesDevice<fluid,fluid>, <fluid,boundary>,
+// <boundary,fluid>, finalizeforcesDevice), each re-reading the particle and read-modify-writing forces[] in
+// global memory, gathers every neighbour through the texture path and re-evaluates the equation of state
+// (two __powf = 4 MUFU + an IEEE division) for BOTH particles of every pair. Here:
+//  * `aux_kernel` evaluates P/rho^2, the sound speed and the density ONCE per particle (same __powf expressions,
+//    so the values are the ones the reference recomputes per pair);
+//  * ONE launch walks both neighbour-list sections of a particle with the accumulator in registers, applies the
+//    finalize step and reduces the CFL term — forces[] is written exactly once;
+//  * physics options are template parameters, per-pair divisions/roots are MUFU approximations (the bit-exact
+//    distance test belongs to the list builder);
+//  * two kernels share that physics:
+//      - forces_tile_kernel  (default): one CTA per *tile* (tiles.cu); the tile's 9 neighbouring particle ranges
+//        (pos, vel, aux) are staged into shared memory with TMA bulk copies (cp.async.bulk + mbarrier) while the
+//        threads compute their 27 cell bases; every per-pair gather is then an LDS;
+//      - forces_gather_kernel (fallback: periodic COORD1, tiles that do not fit, no tiles built): gathers through
+//        L1/L2 like the reference, still single-pass and fused.
+// Summation order inside each list section is the reference's (list order); the fluid and boundary partial sums
+// are combined as (0 + sum_fluid) + sum_boundary like the reference's RMW sequence.
+#include "pair_physics.cuh"
+#include <stdlib.h>
 
-// ---- equation of state, reference src/cuda/phys_core.cu:99-151 ----
-__device__ __forceinline__ float eos_pressure(const DevParams &P, float rho_tilde, int f)
-{
-	const float rho_ratio = rho_tilde + 1.0f;
-	return P.bcoeff[f] * (__powf(rho_ratio, P.gammacoeff[f]) - 1.0f);
-}
-__device__ __forceinline__ float eos_sound_speed(const DevParams &P, float rho_tilde, int f)
-{
-	const float rho_ratio = rho_tilde + 1.0f;
-	return P.sscoeff[f] * __powf(rho_ratio, P.sspowercoeff[f]);
-}
-__device__ __forceinline__ float phys_density(const DevParams &P, float rho_tilde, int f)
-{
-	return (rho_tilde + 1.0f) * P.rho0[f];
-}
-
-// per particle: x = P/rho^2 (precalc_pressure<SPH_F1>, forces_kernel.def:419-429), y = sound speed
+// ---------------------------------------------------------------------------
+// per-particle pre-pass
+// ---------------------------------------------------------------------------
+// x = P/rho^2 (precalc_pressure<SPH_F1>, forces_kernel.def:419-429), y = sound speed, z = physical density, w = fluid#
 __global__ void __launch_bounds__(BLOCK_STREAM)
-eos_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ vel, const ushort4 *__restrict__ info,
-	float2 *__restrict__ eos, const uint n)
+aux_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ vel, const ushort4 *__restrict__ info,
+	float4 *__restrict__ aux, const uint n)
 {
 	const uint i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const float rho_tilde = vel[i].w;
-	const int f = fluid_num_of(info[i]);
-	const float rho = phys_density(P, rho_tilde, f);
-	float2 e;
-	e.x = eos_pressure(P, rho_tilde, f) / (rho * rho);
-	e.y = eos_sound_speed(P, rho_tilde, f);
-	eos[i] = e;
+	aux[i] = eos_from_density(P, vel[i].w, fluid_num_of(info[i]));
 }
 
-// Packed neighbour record, 48 bytes = 3 x float4, written once per force evaluation:
-//   [0] pos.xyz (cell-local), mass          [1] vel.xyz, rho~
-//   [2] P/rho^2, sound speed, physical density, fluid number (as int bits)
-// One base address + three 128-bit loads per neighbour instead of three separately addressed gathers,
-// and the neighbour's EOS terms / density come precomputed (the reference re-evaluates __powf twice per pair).
 __global__ void __launch_bounds__(BLOCK_STREAM)
-pack_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
-	const ushort4 *__restrict__ info, float4 *__restrict__ rec, const uint n)
+eos_probe_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ vel, const ushort4 *__restrict__ info,
+	float2 *__restrict__ out, const uint n)
 {
 	const uint i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const float4 v = vel[i];
-	const int f = fluid_num_of(info[i]);
-	const float rho = phys_density(P, v.w, f);
-	float4 e;
-	e.x = eos_pressure(P, v.w, f) / (rho * rho);
-	e.y = eos_sound_speed(P, v.w, f);
-	e.z = rho;
-	e.w = __int_as_float(f);
-	rec[3 * (size_t)i + 0] = pos[i];
-	rec[3 * (size_t)i + 1] = v;
-	rec[3 * (size_t)i + 2] = e;
+	const float4 e = eos_from_density(P, vel[i].w, fluid_num_of(info[i]));
+	out[i] = make_float2(e.x, e.y);
 }
 
-int b200_eos_precompute(b200sph_ctx *ctx, const float4 *pos, const float4 *vel, const ushort4 *info, uint n)
+static int aux_precompute(b200sph_ctx *ctx, const float4 *vel, const ushort4 *info, uint n)
 {
-	if (ctx->eos_cap < n) {
-		cudaFree(ctx->eos); ctx->eos = NULL; ctx->eos_cap = 0;
+	if (ctx->aux_cap < n) {
+		cudaFree(ctx->aux); ctx->aux = NULL; ctx->aux_cap = 0;
 		const size_t cap = (size_t)n + (n >> 3) + 1024;
-		CUDA_TRY(cudaMalloc(&ctx->eos, cap * 3 * sizeof(float4)));
-		ctx->eos_cap = cap;
+		CUDA_TRY(cudaMalloc(&ctx->aux, cap * sizeof(float4)));
+		ctx->aux_cap = cap;
 	}
-	pack_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, pos, vel, info, (float4 *)ctx->eos, n);
+	aux_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, vel, info, ctx->aux, n);
 	KERNEL_TRY();
 	return B200SPH_OK;
 }
@@ -90,151 +63,118 @@ extern "C" int b200sph_eos_probe(b200sph_ctx *ctx, const void *vel, const void *
 	CHECK_CTX(ctx);
 	if (n == 0) return B200SPH_OK;
 	if (!vel || !info || !out) { b200_set_error("eos_probe: null buffer"); return B200SPH_EINVAL; }
-	eos_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)vel, (const ushort4 *)info, (float2 *)out, n);
+	eos_probe_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)vel, (const ushort4 *)info, (float2 *)out, n);
 	KERNEL_TRY();
 	return B200SPH_OK;
 }
 
-// density-only viscous averaging, reference src/cuda/visc_avg.cu
-__device__ __forceinline__ float visc_avg_density(const DevParams &P, float rho, float nrho, float nmass)
-{
-	switch (P.viscavgop) {
-	case B200SPH_AVG_ARITHMETIC: return nmass * (rho + nrho) / (rho * nrho);
-	case B200SPH_AVG_HARMONIC: return 4 * nmass / (rho + nrho);
-	default: return 2 * nmass * rsqrtf(rho * nrho);
-	}
-}
-__device__ __forceinline__ float visc_avg_dyn(const DevParams &P, float v, float nv, float rho, float nrho, float nmass)
-{
-	switch (P.viscavgop) {
-	case B200SPH_AVG_ARITHMETIC: return nmass * (v + nv) / (rho * nrho);
-	case B200SPH_AVG_HARMONIC: return 4 * nmass * (v * nv) / (v + nv) / (rho * nrho);
-	default: return 2 * nmass * sqrtf(v * nv) / (rho * nrho);
-	}
-}
-
 // ---------------------------------------------------------------------------
-// The pair kernel. It is instruction-issue bound (ncu: profiles/forces_r01_*.txt), so everything here
-// is about instructions per pair:
-//  * physics options are TEMPLATE parameters (the reference does the same through its SFINAE
-//    specialisations, forces_kernel.def:1560-2770): no run-time branches, no loads of unused constants;
-//  * per-thread constants live in registers; the only per-pair divisions/roots are MUFU approximations
-//    (rsqrt, rcp) — the neighbour-list builder, not this kernel, owns the bit-exact distance test;
-//  * the 27 neighbour-cell base indices are staged in shared memory once per particle (the reference's
-//    getNeibIndex re-reads cellStart from global memory at every cell change, cellgrid.cuh:198-226);
-//  * the list column is read one row ahead (software prefetch), the three gathers of a pair are issued
-//    together.
-// Accumulation order is the list order, exactly as in the reference (neibs_iteration.cuh:56-200).
+// shared pieces of the two kernels
 // ---------------------------------------------------------------------------
-struct PairConsts {
-	float inv_h, fc, R2;       // 1/h, Wendland gradient coefficient, squared influence radius
-	float h_alpha, eps;        // artificial viscosity: h*alpha, eps
-	float g0, g1, g2;          // gravity
-	float diff;                // density diffusion coefficient (Colagrossi single-fluid: xi*2h*c0)
-	float grav_scale;          // Ferrari: rho0/c0^2
-	float h;
-};
+// cellStart of the 27 neighbouring cells of a particle in cell h0 -> out[cell * stride_out] (27 independent loads).
+// calcGridHashPeriodic, cellgrid.cuh:174-185 (cells outside a non-periodic domain are never listed, the wrapped
+// index only keeps the load in bounds).
+__device__ __forceinline__ void load_cell_starts(const DevParams &P, const int h0, const uint *__restrict__ cellStart,
+	uint *out, const int stride_out)
+{
+	const int3 gp = grid_pos(P, (uint)h0);
+	const int sx = P.hstride[0], sy = P.hstride[1], sz = P.hstride[2];
+	const int Gx = P.gridSize[0], Gy = P.gridSize[1], Gz = P.gridSize[2];
+	const int dx[3] = { gp.x == 0 ? (Gx - 1) * sx : -sx, 0, gp.x == Gx - 1 ? -(Gx - 1) * sx : sx };
+	const int dy[3] = { gp.y == 0 ? (Gy - 1) * sy : -sy, 0, gp.y == Gy - 1 ? -(Gy - 1) * sy : sy };
+	const int dz[3] = { gp.z == 0 ? (Gz - 1) * sz : -sz, 0, gp.z == Gz - 1 ? -(Gz - 1) * sz : sz };
+#pragma unroll
+	for (int cell = 0; cell < 27; ++cell)
+		out[cell * stride_out] = __ldg(cellStart + (h0 + dx[cell % 3] + dy[(cell / 3) % 3] + dz[cell / 9]));
+}
 
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// 16-bit neighbour-list entry, zero-extended, through the read-only path
-__device__ __forceinline__ uint ld_neib(const ushort *p) { uint v; asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// neighbour-cell offset times cell size, for pos_corr = pos - offset*cellSize (cellgrid.cuh:215)
+__device__ __forceinline__ float4 cell_offset(const DevParams &P, const int c)
+{
+	return make_float4((float)(c % 3 - 1) * P.cellSize[0], (float)((c / 3) % 3 - 1) * P.cellSize[1],
+		(float)(c / 9 - 1) * P.cellSize[2], 0.f);
+}
 
-template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
+// Walk one section of a particle's neighbour-list column. fetch(slot, np, nv, ne) loads the neighbour record
+// `slot` = base-of-its-cell + offset-in-cell (global index for the gather kernel, shared-memory slot for the
+// staged kernel). PF list rows are read ahead of use (row indices clamped to the list).
+// Accumulation order = list order, as in the reference (neibs_iteration.cuh:56-200).
+template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int BASE_STRIDE, int PF, typename Fetch>
 __device__ __forceinline__ void
-walk_section(const DevParams &P, const PairConsts &k, const uint index, const float4 pos, const float4 vel,
-	const float rho, const float p_precalc, const float sspeed, const int fnum, const bool momentum,
-	const uint *s_base /* [27][BLOCK_FORCES] + tid */, const float4 *s_off /* [27] cell offset * cell size */,
-	const float4 *__restrict__ rec, const ushort *__restrict__ neibsList, float4 &acc)
+walk_section(const DevParams &P, const PairConsts &k, const Central &c, const uint index,
+	const uint *s_base /* [27][BASE_STRIDE] + tid */, const float4 *s_off /* [27] */,
+	const ushort *__restrict__ neibsList, Fetch fetch, float4 &acc)
 {
 	const size_t stride = P.stride;
 	// list column of this particle; fluid section grows up from row 0, boundary section down from neibboundpos
-	const ushort *row = neibsList + index + (NFLUID ? (size_t)0 : (size_t)P.neibboundpos * stride);
-	const ptrdiff_t rstep = NFLUID ? (ptrdiff_t)stride : -(ptrdiff_t)stride;
+	const ushort *col = neibsList + index;
+	const int rstep = NFLUID ? 1 : -1;
+	const int last_row = (int)P.neiblistsize - 1;
+	int slot = NFLUID ? 0 : (int)P.neibboundpos;
 	uint base = 0;
 	float pcx = 0.f, pcy = 0.f, pcz = 0.f;
-	uint nd = ld_neib(row);
-	while (nd != NEIBS_END) {
-		// prefetch the next row: always in bounds, the section is terminated by NEIBS_END before the list ends
-		// (buildneibs_kernel.cu:1108-1137)
-		row += rstep;
-		const uint nd_next = ld_neib(row);
+	// PF list rows are kept in flight: the column is a stride-N walk through HBM/L2 (one row = one sector per warp),
+	// and there are only a few warps per SM to hide that latency when the neighbourhood is staged in shared memory
+	uint q[PF];
+#pragma unroll
+	for (int i = 0; i < PF; ++i) q[i] = ld_neib(col + (size_t)min(max(slot + i * rstep, 0), last_row) * stride);
+	while (q[0] != NEIBS_END) {
+		uint nd = q[0];
+#pragma unroll
+		for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
+		q[PF - 1] = ld_neib(col + (size_t)min(max(slot + PF * rstep, 0), last_row) * stride);   // clamped: rows past the marker are never used
+		slot += rstep;
 		if (nd >= CELLNUM_ENCODED) {                                    // getNeibIndex, cellgrid.cuh:198-226
 			const uint cell = (nd >> CELLNUM_SHIFT) - 1;
 			nd &= NEIBINDEX_MASK;
-			base = s_base[cell * BLOCK_FORCES];
-			const float4 o = s_off[cell];                               // pos_corr = pos - offset*cellSize (:215)
-			pcx = pos.x - o.x; pcy = pos.y - o.y; pcz = pos.z - o.z;
+			base = s_base[cell * BASE_STRIDE];
+			const float4 o = s_off[cell];
+			pcx = c.pos.x - o.x; pcy = c.pos.y - o.y; pcz = c.pos.z - o.z;
 		}
-		const float4 *nr = rec + 3 * (size_t)(base + nd);
-		const float4 np = __ldg(nr);
-		const float4 nv = __ldg(nr + 1);
-		const float4 ne = __ldg(nr + 2);
-		nd = nd_next;
+		float4 np, nv, ne;
+		fetch(base + nd, np, nv, ne);
 		const float rx = pcx - np.x, ry = pcy - np.y, rz = pcz - np.z;
-		const float nmass = np.w;
 		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
-		if (!(r2 < k.R2) || !(fabsf(nmass) < __int_as_float(0x7f800000))) continue;
-		const int nfnum = MULTIFLUID ? __float_as_int(ne.w) : 0;
-		const float r = r2 * rsqrt_approx(r2 + 1e-30f);
-		// common_neib_data :1099-1130
-		const float rvx = vel.x - nv.x, rvy = vel.y - nv.y, rvz = vel.z - nv.z;
-		const float vel_dot_pos = fmaf(rvz, rz, fmaf(rvy, ry, rvx * rx));
-		const float qm2 = fmaf(r, k.inv_h, -2.0f);                       // F<WENDLAND>, sph_core.cu:168-174
-		const float f = qm2 * qm2 * qm2 * k.fc;
-		const float mf = nmass * f;
-		const float np_precalc = ne.x, nsspeed = ne.y, nrho = ne.z;
-
-		// --- continuity: mass_continuity_div_vel_term :2140-2150 ---
-		float DrDt = mf * vel_dot_pos;
-		if (NFLUID) {   // no density diffusion from DYN boundary neighbours, :1594-1606
-			if (RHODIFF == B200SPH_RHODIFF_FERRARI) {                   // :1614-1636
-				const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
-				const float grav_corr = -gdot * (MULTIFLUID ? P.rho0[fnum] / P.sqC0[fnum] : k.grav_scale);
-				// ferraricor . relPos = max(c) (rho - rho_j + corr)/rho / r * r^2   (zero for r <= 1e-4 h)
-				const float s = (r > 1e-4f * k.h) ? fmaxf(sspeed, nsspeed) * (rho - nrho + grav_corr) * rcp_approx(rho) * r : 0.0f;
-				DrDt = fmaf(k.diff * mf, s, DrDt);
-			} else if (RHODIFF == B200SPH_RHODIFF_COLAGROSSI) {         // :1916-1951
-				if (!MULTIFLUID || fnum == nfnum) {
-					const float Pi = p_precalc * (rho * rho), Pj = np_precalc * (nrho * nrho);
-					const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
-					if (!(fabsf(Pi - Pj) < fabsf(gdot * rho)))
-						DrDt -= k.diff * (MULTIFLUID ? P.sscoeff[fnum] : 1.0f) * (nrho * rcp_approx(rho) - 1.0f) * mf;
-				}
-			}
-		}
-		acc.w += DrDt;                                                  // :2189
-
-		if (momentum) {
-			// compute_pressure_contrib, general formulation :2450-2466:  -(P_i/rho_i^2 + P_j/rho_j^2) m_j F r_ij
-			float coef = -(p_precalc + np_precalc) * mf;
-			// artificial viscosity :2744-2764, artvisc visc_kernel.cu:75-85
-			if (ARTVISC) {
-				const float visc = vel_dot_pos * k.h_alpha * (sspeed + nsspeed) * rcp_approx((r2 + k.eps) * (rho + nrho));
-				coef = (vel_dot_pos < 0.0f) ? fmaf(visc, mf, coef) : coef;
-			}
-			float dvx = coef * rx, dvy = coef * ry, dvz = coef * rz;
-			// laminar (Morris) :2605-2625
-			if (LAMINAR) {
-				const float vc = P.visccoeff[fnum], nvc = P.visccoeff[nfnum];
-				float visc;
-				if (P.compvisc == B200SPH_COMPVISC_KINEMATIC)
-					visc = P.is_const_visc ? vc * visc_avg_density(P, rho, nrho, nmass) : visc_avg_dyn(P, vc * rho, nvc * nrho, rho, nrho, nmass);
-				else
-					visc = P.is_const_visc ? 2 * nmass * vc / (rho * nrho) : visc_avg_dyn(P, vc, nvc, rho, nrho, nmass);
-				const float s = visc * f;
-				dvx = fmaf(s, rvx, dvx); dvy = fmaf(s, rvy, dvy); dvz = fmaf(s, rvz, dvz);
-			}
-			acc.x += dvx; acc.y += dvy; acc.z += dvz;                   // :3590
-		}
+		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
+		pair_interaction<NFLUID, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, acc);
 	}
 }
 
+// all sections of one particle (forces.cu:759,782,792 in the reference) + finalize; returns the CFL term
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int BASE_STRIDE, int PF, typename Fetch>
+__device__ __forceinline__ float
+particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
+	const float4 pos, const float4 vel, const float4 e, const uint *s_base, const float4 *s_off,
+	const ushort *__restrict__ neibsList, Fetch fetch, float4 *__restrict__ forces)
+{
+	Central c;
+	c.pos = pos; c.vel = vel;
+	c.p_precalc = e.x; c.sspeed = e.y; c.rho = e.z;
+	c.fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (type == PT_FLUID) {
+		// fluid<-fluid then fluid<-boundary; DYN boundary neighbours interact like fluid ones (forces_kernel.def:3717-3726)
+		c.momentum = true;
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
+		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
+	} else {
+		// boundary<-fluid: density always, momentum only with force feedback (forces_kernel.def:3634-3667)
+		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
+	}
+	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, acc);
+	forces[index] = acc;
+	return cfl_term;
+}
+
+// ---------------------------------------------------------------------------
+// gather kernel (fallback): neighbours through L1/L2
+// ---------------------------------------------------------------------------
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
 __global__ void __launch_bounds__(BLOCK_FORCES)
-forces_kernel(const __grid_constant__ DevParams P, const ushort4 *__restrict__ infoArray,
-	const uint *__restrict__ particleHash, const float4 *__restrict__ rec,
+forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
+	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
 	float4 *__restrict__ forces, float *__restrict__ cfl,
 	const uint fromParticle, const uint toParticle, const uint cflOffset)
@@ -243,67 +183,25 @@ forces_kernel(const __grid_constant__ DevParams P, const ushort4 *__restrict__ i
 	__shared__ float4 s_celloff[27];
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x + fromParticle;
 	float cfl_term = 0.0f;
-	if (threadIdx.x < 27) {
-		const int c = threadIdx.x;
-		s_celloff[c] = make_float4((float)(c % 3 - 1) * P.cellSize[0], (float)((c / 3) % 3 - 1) * P.cellSize[1],
-			(float)(c / 9 - 1) * P.cellSize[2], 0.f);
-	}
+	if (threadIdx.x < 27) s_celloff[threadIdx.x] = cell_offset(P, threadIdx.x);
 	__syncthreads();
 
 	if (index < toParticle) {
 		const ushort4 info = infoArray[index];
 		const int type = ptype_of(info);
-		const float4 pos = rec[3 * (size_t)index];
+		const float4 pos = posArray[index];
 		if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000)) {
-			const float4 vel = rec[3 * (size_t)index + 1];
-			const float4 e = rec[3 * (size_t)index + 2];
-			const int fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
-			const float rho = e.z;
-			PairConsts k;
-			k.h = P.slength; k.inv_h = 1.0f / P.slength; k.fc = P.fcoeff_wendland;
-			k.R2 = P.influenceradius * P.influenceradius;
-			k.h_alpha = P.slength * P.artvisccoeff; k.eps = P.epsartvisc;
-			k.g0 = P.gravity[0]; k.g1 = P.gravity[1]; k.g2 = P.gravity[2];
-			k.diff = RHODIFF == B200SPH_RHODIFF_COLAGROSSI && !MULTIFLUID ? P.densityDiffCoeff * P.sscoeff[0] : P.densityDiffCoeff;
-			k.grav_scale = P.rho0[0] / P.sqC0[0];
-			// first particle of each of the 27 neighbouring cells -> shared memory (27 independent loads);
-			// calcGridHashPeriodic, cellgrid.cuh:174-185 (cells outside a non-periodic domain are never listed)
+			const PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
 			uint *my_base = s_cellbase + threadIdx.x;
-			{
-				const int h0 = (int)(particleHash[index] & CELLTYPE_BITMASK);
-				const int3 gp = grid_pos(P, (uint)h0);
-				const int sx = P.hstride[0], sy = P.hstride[1], sz = P.hstride[2];
-				const int Gx = P.gridSize[0], Gy = P.gridSize[1], Gz = P.gridSize[2];
-				// hash delta of a step of -1 / 0 / +1 cells along each axis, wrapped at the domain faces
-				const int dx[3] = { gp.x == 0 ? (Gx - 1) * sx : -sx, 0, gp.x == Gx - 1 ? -(Gx - 1) * sx : sx };
-				const int dy[3] = { gp.y == 0 ? (Gy - 1) * sy : -sy, 0, gp.y == Gy - 1 ? -(Gy - 1) * sy : sy };
-				const int dz[3] = { gp.z == 0 ? (Gz - 1) * sz : -sz, 0, gp.z == Gz - 1 ? -(Gz - 1) * sz : sz };
-#pragma unroll
-				for (int cell = 0; cell < 27; ++cell)
-					my_base[cell * BLOCK_FORCES] = __ldg(cellStart + (h0 + dx[cell % 3] + dy[(cell / 3) % 3] + dz[cell / 9]));
-			}
-			float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (type == PT_FLUID) {
-				// forcesDevice<fluid,fluid> then <fluid,boundary> (forces.cu:759,782); DYN boundary neighbours
-				// interact like fluid ones (forces_kernel.def:3717-3726)
-				walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, index, pos, vel, rho, e.x, e.y, fnum, true,
-					my_base, s_celloff, rec, neibsList, acc);
-				walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, index, pos, vel, rho, e.x, e.y, fnum, true,
-					my_base, s_celloff, rec, neibsList, acc);
-			} else {
-				// forcesDevice<boundary,fluid> (forces.cu:792): density always, momentum only with force feedback
-				// (forces_kernel.def:3634-3667)
-				walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, index, pos, vel, rho, e.x, e.y, fnum,
-					(info.x & B200SPH_FG_COMPUTE_FORCE) != 0, my_base, s_celloff, rec, neibsList, acc);
-			}
-			// finalizeforcesDevice :4037-4153
-			acc.w /= P.rho0[fnum];                                          // forces_fixup :3212-3219
-			if (type == PT_FLUID) {
-				acc.x += P.gravity[0]; acc.y += P.gravity[1]; acc.z += P.gravity[2];   // :4091
-				// dyndt_forces_shared_data::store :3436-3456
-				cfl_term = fmaxf(sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z), e.y * e.y / P.slength);
-			}
-			forces[index] = acc;
+			load_cell_starts(P, (int)(particleHash[index] & CELLTYPE_BITMASK), cellStart, my_base, BLOCK_FORCES);
+			// two gathers per pair straight from the reference's own pos / vel buffers; EOS terms from rho~ on the fly
+			auto fetch = [&](const uint j, float4 &np, float4 &nv, float4 &ne) {
+				np = __ldg(posArray + j); nv = __ldg(velArray + j);
+				ne = eos_from_density(P, nv.w, MULTIFLUID ? fluid_num_of(__ldg(infoArray + j)) : 0);
+			};
+			const float4 vel = velArray[index];
+			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BLOCK_FORCES, 2>(P, k, index, info, type, pos,
+				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), my_base, s_celloff, neibsList, fetch, forces);
 		}
 	}
 
@@ -323,18 +221,158 @@ forces_kernel(const __grid_constant__ DevParams P, const ushort4 *__restrict__ i
 	}
 }
 
-typedef void (*forces_kernel_t)(const DevParams, const ushort4 *, const uint *, const float4 *,
+// ---------------------------------------------------------------------------
+// staged kernel: one CTA per tile, neighbourhood in shared memory via TMA bulk copies
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint smem_u32(const void *p) { return (uint)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint count)
+{ asm volatile("mbarrier.init.shared.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint parity)
+{
+	uint ok;
+	asm volatile("{\n\t.reg .pred P_OUT;\n\tmbarrier.try_wait.parity.shared::cta.b64 P_OUT, [%1], %2;\n\tselp.b32 %0, 1, 0, P_OUT;\n\t}"
+		: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template<int TP, int TS>
+struct TileSmem {
+	float4 pos[TS];
+	float4 vel[TS];
+	float4 aux[TS];
+	uint cellbase[27 * TP];
+	float4 celloff[27];
+	uint row_off[9], row_start[9];
+	int rowof[27];            // neighbour cell code -> neighbour row index
+	unsigned long long bar;
+};
+
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int TP, int TS, int PF>
+__global__ void __launch_bounds__(TP)
+forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__ tiles,
+	const float4 *__restrict__ posArray, const float4 *__restrict__ velArray, const float4 *__restrict__ aux,
+	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
+	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
+	float4 *__restrict__ forces, float *__restrict__ cfl,
+	const uint fromParticle, const uint toParticle, const uint cflOffset)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	typedef TileSmem<TP, TS> Smem;
+	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+	const Tile &T = tiles[blockIdx.x];
+	const uint tid = threadIdx.x;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(&S.bar);
+
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		uint off = 0;
+#pragma unroll
+		for (int r = 0; r < 9; ++r) { S.row_off[r] = off; S.row_start[r] = T.row_start[r]; off += T.row_count[r]; }
+	}
+	if (tid < 27) {
+		S.celloff[tid] = cell_offset(P, tid);
+		// cell code = (x+1) + 3(y+1) + 9(z+1); the row of a neighbour is chosen by its COORD2 / COORD3 offsets
+		const int d[3] = { (int)tid % 3 - 1, ((int)tid / 3) % 3 - 1, (int)tid / 9 - 1 };
+		const int d2 = P.coord[1] == 0 ? d[0] : (P.coord[1] == 1 ? d[1] : d[2]);
+		const int d3 = P.coord[2] == 0 ? d[0] : (P.coord[2] == 1 ? d[1] : d[2]);
+		S.rowof[tid] = (d2 + 1) + 3 * (d3 + 1);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint total = 0;
+#pragma unroll
+		for (int r = 0; r < 9; ++r) total += T.row_count[r];
+		mbar_expect_tx(bar, total * 48u);
+#pragma unroll
+		for (int r = 0; r < 9; ++r) {
+			const uint cnt = T.row_count[r];
+			if (cnt) {
+				const uint off = S.row_off[r], src = T.row_start[r];
+				bulk_g2s(&S.pos[off], posArray + src, cnt * 16u, bar);
+				bulk_g2s(&S.vel[off], velArray + src, cnt * 16u, bar);
+				bulk_g2s(&S.aux[off], aux + src, cnt * 16u, bar);
+			}
+		}
+	}
+
+	const PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
+	auto fetch = [&](const uint slot, float4 &np, float4 &nv, float4 &ne) {
+		np = S.pos[slot]; nv = S.vel[slot]; ne = S.aux[slot];
+	};
+	bool staged = false;
+	float cfl_term = 0.0f;
+	uint cfl_slot = 0xFFFFFFFFu;
+	const uint tend = T.first + T.count;
+	for (uint index = T.first + tid; index < tend; index += TP) {
+		if (index < fromParticle || index >= toParticle) continue;
+		const ushort4 info = infoArray[index];
+		const int type = ptype_of(info);
+		const float4 pos = posArray[index];
+		if (!((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000))) continue;
+		const float4 vel = velArray[index];
+		const float4 e = aux[index];
+		// shared-memory slot of the first particle of each of the 27 neighbouring cells (while the copies fly)
+		uint *my_base = S.cellbase + tid;
+		load_cell_starts(P, (int)(particleHash[index] & CELLTYPE_BITMASK), cellStart, my_base, TP);
+#pragma unroll
+		for (int cell = 0; cell < 27; ++cell) {
+			const int r = S.rowof[cell];
+			const uint cs = my_base[cell * TP];
+			my_base[cell * TP] = cs - S.row_start[r] + S.row_off[r];   // meaningless (and unused) for empty cells
+		}
+		if (!staged) { while (!mbar_try_wait(bar, 0)) { } staged = true; }
+		const float t = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, TP, PF>(P, k, index, info, type, pos, vel, e,
+			my_base, S.celloff, neibsList, fetch, forces);
+		cfl_term = fmaxf(cfl_term, t);
+		cfl_slot = (index - fromParticle) / BLOCK_FORCES;
+	}
+	// every thread must have observed the copies before the CTA (and its shared memory) may retire
+	if (!staged) { while (!mbar_try_wait(bar, 0)) { } }
+
+	// CFL: one slot per 128 particles like the reference's per-block maxima; tiles do not align with those blocks,
+	// so non-negative floats are max-combined with integer atomics (slots are zeroed by the launcher)
+	if (cfl && cfl_slot != 0xFFFFFFFFu)
+		atomicMax(reinterpret_cast<unsigned int *>(cfl + cflOffset + cfl_slot), __float_as_uint(cfl_term));
+}
+
+// ---------------------------------------------------------------------------
+// launcher
+// ---------------------------------------------------------------------------
+typedef void (*gather_kernel_t)(const DevParams, const float4 *, const float4 *, const ushort4 *, const uint *,
 	const uint *, const ushort *, float4 *, float *, const uint, const uint, const uint);
+typedef void (*tile_kernel_t)(const DevParams, const Tile *, const float4 *, const float4 *, const float4 *, const ushort4 *,
+	const uint *, const uint *, const ushort *, float4 *, float *, const uint, const uint, const uint);
 
 template<int RHODIFF>
-static forces_kernel_t pick_forces_kernel(bool artvisc, bool laminar, bool multifluid)
+static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather_kernel_t *g, tile_kernel_t *t, size_t *smem)
 {
-	if (multifluid) {
-		if (artvisc) return laminar ? forces_kernel<RHODIFF, true, true, true> : forces_kernel<RHODIFF, true, false, true>;
-		return laminar ? forces_kernel<RHODIFF, false, true, true> : forces_kernel<RHODIFF, false, false, true>;
+	// tile configurations (threads, staged slots, list prefetch depth); must match b200_tile_limits() in tiles.cu
+#define PICK(A, L, M) do { *g = forces_gather_kernel<RHODIFF, A, L, M>; \
+	switch (cfg) { \
+	case 1: *t = forces_tile_kernel<RHODIFF, A, L, M, 128, 1536, 4>; *smem = sizeof(TileSmem<128, 1536>); break; \
+	case 2: *t = forces_tile_kernel<RHODIFF, A, L, M, 128, 1152, 4>; *smem = sizeof(TileSmem<128, 1152>); break; \
+	case 3: *t = forces_tile_kernel<RHODIFF, A, L, M, 64, 1024, 4>; *smem = sizeof(TileSmem<64, 1024>); break; \
+	case 4: *t = forces_tile_kernel<RHODIFF, A, L, M, 64, 768, 4>; *smem = sizeof(TileSmem<64, 768>); break; \
+	case 5: *t = forces_tile_kernel<RHODIFF, A, L, M, 128, 1536, 8>; *smem = sizeof(TileSmem<128, 1536>); break; \
+	default: *t = forces_tile_kernel<RHODIFF, A, L, M, 64, 1024, 8>; *smem = sizeof(TileSmem<64, 1024>); break; \
+	} } while (0)
+	if (multi) {
+		if (artvisc) { if (laminar) PICK(true, true, true); else PICK(true, false, true); }
+		else { if (laminar) PICK(false, true, true); else PICK(false, false, true); }
+	} else {
+		if (artvisc) { if (laminar) PICK(true, true, false); else PICK(true, false, false); }
+		else { if (laminar) PICK(false, true, false); else PICK(false, false, false); }
 	}
-	if (artvisc) return laminar ? forces_kernel<RHODIFF, true, true, false> : forces_kernel<RHODIFF, true, false, false>;
-	return laminar ? forces_kernel<RHODIFF, false, true, false> : forces_kernel<RHODIFF, false, false, false>;
+#undef PICK
 }
 
 extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel, const void *info,
@@ -347,22 +385,37 @@ extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel
 	if (to <= from) return B200SPH_OK;
 	if (!pos || !vel || !info || !hash || !cell_start || !neibs_list || !forces) { b200_set_error("forces: null buffer"); return B200SPH_EINVAL; }
 	if (to > num_particles) { b200_set_error("forces: range end beyond numParticles"); return B200SPH_EINVAL; }
-	int rc = b200_eos_precompute(ctx, (const float4 *)pos, (const float4 *)vel, (const ushort4 *)info, num_particles);
-	if (rc) return rc;
-	// grid rounded to a multiple of 4 blocks like the reference (forces.cu:741-744) so that the CFL
-	// array can be reduced as float4
+	// CFL blocks: grid of the reference rounded to a multiple of 4 (forces.cu:741-744) so that the array can be
+	// reduced as float4
 	uint nblocks = div_up(to - from, BLOCK_FORCES);
 	nblocks = (nblocks + 3) / 4 * 4;
 	const DevParams &d = ctx->dp;
 	const bool artvisc = d.turbmodel == B200SPH_TURB_ARTIFICIAL, laminar = !d.inviscid, multi = d.numFluids > 1;
-	forces_kernel_t kern;
+	gather_kernel_t gk; tile_kernel_t tk; size_t smem = 0;
+	const int cfg = ctx->tile_cfg;
 	switch (d.densitydiffusiontype) {
-	case B200SPH_RHODIFF_FERRARI: kern = pick_forces_kernel<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi); break;
-	case B200SPH_RHODIFF_COLAGROSSI: kern = pick_forces_kernel<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi); break;
-	default: kern = pick_forces_kernel<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi); break;
+	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, cfg, &gk, &tk, &smem); break;
+	case B200SPH_RHODIFF_COLAGROSSI: pick_kernels<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi, cfg, &gk, &tk, &smem); break;
+	default: pick_kernels<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi, cfg, &gk, &tk, &smem); break;
 	}
-	kern<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const ushort4 *)info, hash, (const float4 *)ctx->eos,
-		cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
+	// tiles built by the last buildNeibsList for these cell ranges?
+	if (ctx->tiles_state == 1) {
+		CUDA_TRY(cudaEventSynchronize(ctx->tiles_event));
+		ctx->num_tiles = ctx->h_tile_info[0];
+		ctx->tiles_state = ctx->h_tile_info[1] ? 0 : 2;      // overflow: a tile does not fit in shared memory
+	}
+	const bool use_tiles = ctx->tiles_state == 2 && ctx->tiles_cellstart == cell_start && to <= ctx->tiles_range_end && ctx->num_tiles > 0;
+	if (use_tiles) {
+		int rc = aux_precompute(ctx, (const float4 *)vel, (const ushort4 *)info, num_particles);
+		if (rc) return rc;
+		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
+		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		tk<<<ctx->num_tiles, ctx->tile_p, smem, ctx->stream>>>(ctx->dp, ctx->tiles, (const float4 *)pos, (const float4 *)vel, ctx->aux,
+			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
+	} else {
+		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel,
+			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
+	}
 	KERNEL_TRY();
 	if (num_cfl_blocks) *num_cfl_blocks = nblocks;
 	return B200SPH_OK;

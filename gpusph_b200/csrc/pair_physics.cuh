@@ -1,0 +1,173 @@
+// pair_physics.cuh — per-pair WCSPH physics shared by the two forces kernels (gather and staged).
+// Behavioural specification: GPUSPH src/cuda/forces_kernel.def (lines cited inline), sph_core.cu, phys_core.cu,
+// visc_kernel.cu, visc_avg.cu.
+#pragma once
+#include "common.cuh"
+
+// ---- equation of state, reference src/cuda/phys_core.cu:99-151 ----
+__device__ __forceinline__ float eos_pressure(const DevParams &P, float rho_tilde, int f)
+{
+	const float rho_ratio = rho_tilde + 1.0f;
+	return P.bcoeff[f] * (__powf(rho_ratio, P.gammacoeff[f]) - 1.0f);
+}
+__device__ __forceinline__ float eos_sound_speed(const DevParams &P, float rho_tilde, int f)
+{
+	const float rho_ratio = rho_tilde + 1.0f;
+	return P.sscoeff[f] * __powf(rho_ratio, P.sspowercoeff[f]);
+}
+__device__ __forceinline__ float phys_density(const DevParams &P, float rho_tilde, int f)
+{
+	return (rho_tilde + 1.0f) * P.rho0[f];
+}
+
+// density-only viscous averaging, reference src/cuda/visc_avg.cu
+__device__ __forceinline__ float visc_avg_density(const DevParams &P, float rho, float nrho, float nmass)
+{
+	switch (P.viscavgop) {
+	case B200SPH_AVG_ARITHMETIC: return nmass * (rho + nrho) / (rho * nrho);
+	case B200SPH_AVG_HARMONIC: return 4 * nmass / (rho + nrho);
+	default: return 2 * nmass * rsqrtf(rho * nrho);
+	}
+}
+__device__ __forceinline__ float visc_avg_dyn(const DevParams &P, float v, float nv, float rho, float nrho, float nmass)
+{
+	switch (P.viscavgop) {
+	case B200SPH_AVG_ARITHMETIC: return nmass * (v + nv) / (rho * nrho);
+	case B200SPH_AVG_HARMONIC: return 4 * nmass * (v * nv) / (v + nv) / (rho * nrho);
+	default: return 2 * nmass * sqrtf(v * nv) / (rho * nrho);
+	}
+}
+
+
+struct PairConsts {
+	float inv_h, fc, R2;       // 1/h, Wendland gradient coefficient, squared influence radius
+	float h_alpha, eps;        // artificial viscosity: h*alpha, eps
+	float g0, g1, g2;          // gravity
+	float diff;                // density diffusion coefficient (Colagrossi single-fluid: xi*2h*c0)
+	float grav_scale;          // Ferrari: rho0/c0^2
+	float h;
+};
+
+template<int RHODIFF, bool MULTIFLUID>
+__device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P)
+{
+	PairConsts k;
+	k.h = P.slength; k.inv_h = 1.0f / P.slength; k.fc = P.fcoeff_wendland;
+	k.R2 = P.influenceradius * P.influenceradius;
+	k.h_alpha = P.slength * P.artvisccoeff; k.eps = P.epsartvisc;
+	k.g0 = P.gravity[0]; k.g1 = P.gravity[1]; k.g2 = P.gravity[2];
+	k.diff = RHODIFF == B200SPH_RHODIFF_COLAGROSSI && !MULTIFLUID ? P.densityDiffCoeff * P.sscoeff[0] : P.densityDiffCoeff;
+	k.grav_scale = P.rho0[0] / P.sqC0[0];
+	return k;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 16-bit neighbour-list entry, zero-extended, through the read-only path
+__device__ __forceinline__ uint ld_neib(const ushort *p) { uint v; asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// {P/rho^2, sound speed, density, fluid#} of a particle from its relative density, evaluated per pair like the
+// reference does (P() and soundSpeed() with __powf = ex2(y*lg2(x)), phys_core.cu:99-136; precalc_pressure
+// forces_kernel.def:419-429) but sharing the logarithm between the two powers. Trading ~12 ALU/MUFU instructions
+// for one scattered 128-bit gather is a win because the pair kernel is L1-wavefront bound, not issue bound.
+__device__ __forceinline__ float4 eos_from_density(const DevParams &P, const float rho_tilde, const int f)
+{
+	const float ratio = rho_tilde + 1.0f;
+	const float lg = lg2_approx(ratio);
+	const float pw = ex2_approx(P.gammacoeff[f] * lg);
+	const float rho = ratio * P.rho0[f];
+	float4 e;
+	e.x = P.bcoeff[f] * (pw - 1.0f) * rcp_approx(rho * rho);
+	e.y = P.sscoeff[f] * ex2_approx(P.sspowercoeff[f] * lg);
+	e.z = rho;
+	e.w = __int_as_float(f);
+	return e;
+}
+
+// the central particle of a pair
+struct Central {
+	float4 pos, vel;
+	float rho, p_precalc, sspeed;
+	int fnum;
+	bool momentum;    // accumulate the momentum equation (false for DYN boundary particles without force feedback)
+};
+
+// One pair interaction. (rx,ry,rz) = relPos, r2 its squared length (already known to be inside the support),
+// np/nv = neighbour position|mass and velocity|rho~, ne = neighbour {P/rho^2, sound speed, density, fluid#}.
+// NFLUID: the neighbour is a fluid particle (density diffusion applies), else a DYN boundary particle
+// (forces_kernel.def:1594-1606, 3717-3726).
+template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
+__device__ __forceinline__ void
+pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
+	const float r2, const float nmass, const float4 nv, const float4 ne, float4 &acc)
+{
+	const int nfnum = MULTIFLUID ? __float_as_int(ne.w) : 0;
+	const float r = r2 * rsqrt_approx(r2 + 1e-30f);
+	// common_neib_data :1099-1130
+	const float rvx = c.vel.x - nv.x, rvy = c.vel.y - nv.y, rvz = c.vel.z - nv.z;
+	const float vel_dot_pos = fmaf(rvz, rz, fmaf(rvy, ry, rvx * rx));
+	const float qm2 = fmaf(r, k.inv_h, -2.0f);                       // F<WENDLAND>, sph_core.cu:168-174
+	const float f = qm2 * qm2 * qm2 * k.fc;
+	const float mf = nmass * f;
+	const float np_precalc = ne.x, nsspeed = ne.y, nrho = ne.z;
+	const float rho = c.rho;
+
+	// --- continuity: mass_continuity_div_vel_term :2140-2150 ---
+	float DrDt = mf * vel_dot_pos;
+	if (NFLUID) {
+		if (RHODIFF == B200SPH_RHODIFF_FERRARI) {                   // :1614-1636
+			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
+			const float grav_corr = -gdot * (MULTIFLUID ? P.rho0[c.fnum] / P.sqC0[c.fnum] : k.grav_scale);
+			// ferraricor . relPos = max(c) (rho - rho_j + corr)/rho / r * r^2   (zero for r <= 1e-4 h)
+			const float s = (r > 1e-4f * k.h) ? fmaxf(c.sspeed, nsspeed) * (rho - nrho + grav_corr) * rcp_approx(rho) * r : 0.0f;
+			DrDt = fmaf(k.diff * mf, s, DrDt);
+		} else if (RHODIFF == B200SPH_RHODIFF_COLAGROSSI) {         // :1916-1951
+			if (!MULTIFLUID || c.fnum == nfnum) {
+				const float Pi = c.p_precalc * (rho * rho), Pj = np_precalc * (nrho * nrho);
+				const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
+				if (!(fabsf(Pi - Pj) < fabsf(gdot * rho)))
+					DrDt -= k.diff * (MULTIFLUID ? P.sscoeff[c.fnum] : 1.0f) * (nrho * rcp_approx(rho) - 1.0f) * mf;
+			}
+		}
+	}
+	acc.w += DrDt;                                                  // :2189
+
+	if (c.momentum) {
+		// compute_pressure_contrib, general formulation :2450-2466:  -(P_i/rho_i^2 + P_j/rho_j^2) m_j F r_ij
+		float coef = -(c.p_precalc + np_precalc) * mf;
+		// artificial viscosity :2744-2764, artvisc visc_kernel.cu:75-85
+		if (ARTVISC) {
+			const float visc = vel_dot_pos * k.h_alpha * (c.sspeed + nsspeed) * rcp_approx((r2 + k.eps) * (rho + nrho));
+			coef = (vel_dot_pos < 0.0f) ? fmaf(visc, mf, coef) : coef;
+		}
+		float dvx = coef * rx, dvy = coef * ry, dvz = coef * rz;
+		// laminar (Morris) :2605-2625
+		if (LAMINAR) {
+			const float vc = P.visccoeff[c.fnum], nvc = P.visccoeff[nfnum];
+			float visc;
+			if (P.compvisc == B200SPH_COMPVISC_KINEMATIC)
+				visc = P.is_const_visc ? vc * visc_avg_density(P, rho, nrho, nmass) : visc_avg_dyn(P, vc * rho, nvc * nrho, rho, nrho, nmass);
+			else
+				visc = P.is_const_visc ? 2 * nmass * vc / (rho * nrho) : visc_avg_dyn(P, vc, nvc, rho, nrho, nmass);
+			const float s = visc * f;
+			dvx = fmaf(s, rvx, dvx); dvy = fmaf(s, rvy, dvy); dvz = fmaf(s, rvz, dvz);
+		}
+		acc.x += dvx; acc.y += dvy; acc.z += dvz;                   // :3590
+	}
+}
+
+// finalizeforcesDevice :4037-4153: 1/rho0 on the continuity term (forces_fixup :3212-3219), gravity on fluid
+// particles (:4091), CFL term max(|a|, c^2/h) (dyndt_forces_shared_data::store :3436-3456)
+__device__ __forceinline__ float finalize_particle(const DevParams &P, const int type, const int fnum, const float sspeed, float4 &acc)
+{
+	acc.w /= P.rho0[fnum];
+	float cfl_term = 0.0f;
+	if (type == PT_FLUID) {
+		acc.x += P.gravity[0]; acc.y += P.gravity[1]; acc.z += P.gravity[2];
+		cfl_term = fmaxf(sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z), sspeed * sspeed / P.slength);
+	}
+	return cfl_term;
+}

@@ -410,9 +410,14 @@ extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel
 		if (rc) return rc;
 		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
 		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		tk<<<ctx->num_tiles, ctx->tile_p, smem, ctx->stream>>>(ctx->dp, ctx->tiles, (const float4 *)pos, (const float4 *)vel, ctx->aux,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
 	} else {
+		// The kernel wants ~9 resident CTAs x 15 KB of shared memory per SM. Say so explicitly: a host application may
+		// have set a device-wide cache preference (GPUSPH sets cudaFuncCachePreferL1, src/cuda/cudautil.cc:71-79),
+		// which would otherwise shrink the carve-out and cut the occupancy of this kernel by 5x.
+		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, 66));
 		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
 	}

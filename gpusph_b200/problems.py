@@ -226,3 +226,50 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
     info = np.concatenate([make_info(capi.PT_FLUID, ids=np.arange(nfl)),
                            make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, N))], axis=0)
     return params, ParticleArrays(pos, vel, info, hashv)
+
+
+def poiseuille_problem(ppH: int = 32, *, lz: float = 1.0, kinvisc: float = 0.1, driving_force: float = 0.05,
+                       rho0: float = 1.0, viscavgop: int = capi.AVG_ARITHMETIC, steady_init: bool = True,
+                       layers: int = 3, alloc_extra: float = 0.0):
+    """Plane Poiseuille flow like src/problems/Poiseuille.inc:60-232: fluid between two DYN-boundary plates at
+    z = +-lz/2, periodic in x and y, Newtonian laminar (Morris) viscosity with constant kinematic viscosity,
+    driven by a body force along x. Analytic steady profile (Poiseuille.inc:187-232, scripts/validate-poiseuille.py:32-37):
+        v_x(z) = F/(2 nu) ((lz/2)^2 - z^2).
+    Sizes follow the reference: lx = ly = 12 h? — here a thin periodic box of 6 x 6 cells is enough because the flow
+    is invariant in x and y."""
+    dp = lz / ppH
+    max_vel = driving_force / (2 * kinvisc) * (lz / 2) ** 2
+    hydro = math.sqrt(2 * driving_force * lz)
+    c0 = 20 * max(hydro, max_vel)                                  # Poiseuille.inc:147
+    h = 1.3 * dp
+    cell = 2 * h
+    ncell = 4
+    lx = ly = round(ncell * cell / dp) * dp                         # multiple of dp (periodicity, ProblemCore.cc:1436-1456)
+    zpad = (layers - 0.5) * dp
+    origin = np.array([-lx / 2, -ly / 2, -lz / 2 - zpad])
+    size = np.array([lx, ly, lz + 2 * zpad])
+    nx, ny = int(round(lx / dp)), int(round(ly / dp))
+    xs = origin[0] + (np.arange(nx) + 0.5) * dp
+    ys = origin[1] + (np.arange(ny) + 0.5) * dp
+    # as in the reference: the first wall layer sits AT z = +-lz/2 (addRect at +-lz/2, further layers outwards) and the
+    # fluid box is lz - 2 dp high (Poiseuille.inc:152-160)
+    zf = -lz / 2 + (np.arange(ppH - 1) + 1.0) * dp
+    zb = np.concatenate([-lz / 2 - np.arange(layers) * dp, lz / 2 + np.arange(layers) * dp])
+    X, Y, Z = np.meshgrid(xs, ys, zf, indexing="ij")
+    fluid = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    X, Y, Z = np.meshgrid(xs, ys, zb, indexing="ij")
+    wall = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    nfl, nb = fluid.shape[0], wall.shape[0]
+    N = nfl + nb
+    params = make_params(origin=origin, size=size, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
+                         rho0=rho0, c0=c0, gravity=(driving_force, 0.0, 0.0), periodic=capi.PERIODIC_X | capi.PERIODIC_Y,
+                         rheology=capi.RHEOLOGY_NEWTONIAN, turbmodel=capi.TURB_LAMINAR, kinvisc=kinvisc, viscavgop=viscavgop)
+    gpos = np.concatenate([fluid, wall], axis=0)
+    mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
+    pos, hashv = localpos_and_hash(params, gpos, mass)
+    vel = np.zeros((N, 4), dtype=np.float32)
+    if steady_init:
+        vel[:nfl, 0] = driving_force / (2 * kinvisc) * ((lz / 2) ** 2 - fluid[:, 2] ** 2)
+    info = np.concatenate([make_info(capi.PT_FLUID, ids=np.arange(nfl)),
+                           make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, N))], axis=0)
+    return params, ParticleArrays(pos, vel, info, hashv)

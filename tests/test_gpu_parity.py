@@ -11,7 +11,7 @@ from gpusph_b200 import capi
 from gpusph_b200.engines import (BUFFER_CELLEND, BUFFER_CELLSTART, BUFFER_CFL, BUFFER_FORCES, BUFFER_HASH,
                                  BUFFER_INFO, BUFFER_NEIBSLIST, BUFFER_PARTINDEX, BUFFER_POS, BUFFER_VEL, BufferList,
                                  SimFramework)
-from gpusph_b200.problems import dambreak_problem, global_positions, lattice_problem
+from gpusph_b200.problems import dambreak_problem, global_positions, lattice_problem, poiseuille_problem
 from gpusph_b200.simulation import Worker
 
 pytestmark = pytest.mark.gpu
@@ -38,6 +38,11 @@ def problems():
     out["dambreak_ferrari"] = dambreak_problem(0.04, densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
     out["periodic"] = lattice_problem(16, jitter=0.3, periodic=capi.PERIODIC_X | capi.PERIODIC_Y)
     out["ragged"] = lattice_problem(7, ny=5, nz=3, jitter=0.2)      # fewer particles than one block row
+    # Newtonian laminar (Morris) viscosity, periodic XY, DYN plates: the Poiseuille specialisations
+    out["poiseuille"] = poiseuille_problem(12, viscavgop=capi.AVG_HARMONIC)
+    out["poiseuille_geo"] = poiseuille_problem(10, viscavgop=capi.AVG_GEOMETRIC)
+    out["laminar_artvisc"] = lattice_problem(12, jitter=0.3, rheology=capi.RHEOLOGY_NEWTONIAN, kinvisc=5e-3,
+                                             densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
     for params, parts in out.values():
         fl = (parts.info[:, 0] & 7) == 0
         parts.vel[:, :3] += rng.normal(0, 0.3, size=(parts.n, 3)).astype(np.float32) * fl[:, None]
@@ -56,7 +61,7 @@ def get(name):
     return params, parts
 
 
-NAMES = ["lattice", "dambreak", "dambreak_ferrari", "periodic", "ragged"]
+NAMES = ["lattice", "dambreak", "dambreak_ferrari", "periodic", "ragged", "poiseuille", "poiseuille_geo", "laminar_artvisc"]
 
 
 class Pipeline:
@@ -355,3 +360,24 @@ def test_full_size_properties():
     assert tot < 1e-6 * scale
     # continuity is symmetric for equal masses: sum_i drho_i over an isolated block need not vanish, but it is finite
     assert torch.isfinite(f).all()
+
+
+def test_poiseuille_steady_profile_is_preserved():
+    """Physics validation restated from scripts/validate-poiseuille.py:32-37,95-121 (which needs ParaView): started from
+    the analytic steady profile v_x(z) = F/(2 nu)((lz/2)^2 - z^2), the flow must stay on it. L-inf error of the fluid
+    velocity against the analytic profile after 300 steps, relative to the peak velocity: < 2 % at ppH = 16."""
+    params, parts = poiseuille_problem(16)
+    n_fluid = int(((parts.info[:, 0] & 7) == 0).sum())
+    w = Worker(params, parts, 0)
+    for _ in range(300):
+        w.step()
+    out = w.download()
+    gp = global_positions(params, out.pos, out.hash)
+    fl = (out.info[:, 0] & 7) == 0
+    assert fl.sum() == n_fluid
+    F, nu, lz = float(params.gravity[0]), float(params.visccoeff[0]), 1.0
+    exact = F / (2 * nu) * ((lz / 2) ** 2 - gp[fl, 2] ** 2)
+    vmax = F / (2 * nu) * (lz / 2) ** 2
+    err = np.abs(out.vel[fl, 0] - exact).max() / vmax
+    assert err < 0.02, f"L-inf error {err:.3%}"
+    assert np.abs(out.vel[fl, 1:3]).max() < 0.01 * vmax

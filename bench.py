@@ -272,21 +272,23 @@ def main():
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
-    if world == 1:
+    if True:
         n = w.numParticles
-        hp = [torch.empty((n, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
-        hi = torch.empty((n, 4), dtype=torch.int16).pin_memory()
-        hh = torch.empty(n, dtype=torch.int32).pin_memory()
-        hp[0].copy_(w.pos[w.cur][:n]); hp[1].copy_(w.vel[w.cur][:n]); hi.copy_(w.info[:n]); hh.copy_(w.hash[:n])
-        torch.cuda.synchronize()
+        A = w.pos[0].shape[0]
+        hp = [torch.empty((A, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hi = torch.empty((A, 4), dtype=torch.int16).pin_memory()
+        hh = torch.empty(A, dtype=torch.int32).pin_memory()
+        hp[0][:n].copy_(w.pos[w.cur][:n]); hp[1][:n].copy_(w.vel[w.cur][:n]); hi[:n].copy_(w.info[:n]); hh[:n].copy_(w.hash[:n])
+        barrier()
         esteps = max(args.steps // 2, 5)
         i0 = w.total_interactions
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         h2d = d2h = 0
         for _ in range(esteps):
-            # host -> device: the step's inputs = the evolving state n (pos, vel). info/hash are constant between
-            # neighbour rebuilds and already resident (the reference uploads them once, GPUWorker::uploadSubdomain)
+            # host -> device: the step's inputs = the evolving state n (pos, vel) of this rank's slab. info/hash are
+            # constant between neighbour rebuilds and already resident (the reference uploads them once,
+            # GPUWorker::uploadSubdomain)
             w.pos[w.cur][:n].copy_(hp[0][:n], non_blocking=True)
             w.vel[w.cur][:n].copy_(hp[1][:n], non_blocking=True)
             h2d += n * 32
@@ -303,11 +305,16 @@ def main():
                 d2h += n * 12
             torch.cuda.synchronize()
         e1.record()
-        torch.cuda.synchronize()
-        ems = e0.elapsed_time(e1)
-        e2e = {"value": (w.total_interactions - i0) / (ems / 1e3) / 1e6, "unit": "M interactions/s",
-               "h2d_bytes_per_step": h2d // esteps, "d2h_bytes_per_step": d2h // esteps, "ms_per_step": ems / esteps,
-               "particle_updates_per_s": n * esteps / (ems / 1e3)}
+        barrier()
+        et = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        ei = torch.tensor([float(w.total_interactions - i0), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ei, op=dist.ReduceOp.SUM)
+        ems = float(et.item())
+        e2e = {"value": float(ei[0].item()) / (ems / 1e3) / 1e6, "unit": "M interactions/s",
+               "h2d_bytes_per_step": int(ei[1].item()) // esteps, "d2h_bytes_per_step": int(ei[2].item()) // esteps,
+               "ms_per_step": ems / esteps, "particle_updates_per_s": n_global * esteps / (ems / 1e3)}
 
     # ---- roofline of the dominant kernel (forces), timed live with CUDA events on the launching stream ----
     roofline = None

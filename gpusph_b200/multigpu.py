@@ -42,16 +42,18 @@ def _i32(v: int) -> int:
     return v - (1 << 32) if v >= (1 << 31) else v
 
 
-def slab_partition(params: capi.Params, hashes: np.ndarray, world: int) -> list[tuple[int, int]]:
-    """Split the COORD3 cell layers into `world` contiguous slabs with balanced particle counts
-    (reference: fillDeviceMapByAxisBalanced, src/ProblemCore.cc:1119-1200). Every slab gets >= 2 layers."""
+def slab_partition(params: capi.Params, hashes: np.ndarray, world: int, weights: np.ndarray | None = None) -> list[tuple[int, int]]:
+    """Split the COORD3 cell layers into `world` contiguous slabs with balanced (weighted) particle counts
+    (reference: fillDeviceMapByAxisBalanced, src/ProblemCore.cc:1119-1200). Every slab gets >= 2 layers.
+    `weights` = estimated work per particle (a fluid particle has ~75 pair interactions per force evaluation,
+    a DYN boundary particle far fewer)."""
     c3 = params.coord[2]
     G3 = int(params.grid_size[c3])
     S = int(params.grid_size[params.coord[0]]) * int(params.grid_size[params.coord[1]])
     if G3 < 2 * world:
         raise ValueError(f"cannot split {G3} cell layers over {world} devices (need >= 2 layers each)")
     layer = (hashes.astype(np.int64) & CELLMASK) // S
-    counts = np.bincount(layer, minlength=G3).astype(np.float64)
+    counts = np.bincount(layer, weights=weights, minlength=G3).astype(np.float64)
     cum = np.concatenate([[0.0], np.cumsum(counts)])
     total = cum[-1]
     bounds = [0]
@@ -119,9 +121,9 @@ class CudaBackend:
         self.fw.neibsEngine.buildNeibsList(b, b, n, range_end)
         return self.fw.neibsEngine.getinfo()
 
-    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to):
+    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to, cfl_offset=0):
         b = self._b(pos=pos, vel=vel, info=info, hash=hashv, cs=cs, nl=nl, forces=forces, cfl=cfl)
-        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, 0)
+        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, cfl_offset)
 
     def dtreduce(self, cfl, nblocks):
         b = self._b(cfl=cfl)
@@ -145,7 +147,8 @@ class SlabWorker:
         self.rank, self.world, self.group = rank, world, group
         self.buildneibsfreq = buildneibsfreq
         self.fixed_dt = fixed_dt
-        self.slabs = slab_partition(params, particles.hash, world)
+        work = np.where((particles.info[:, 0] & 7) == capi.PT_FLUID, 1.0, 0.25)
+        self.slabs = slab_partition(params, particles.hash, world, work)
         self.slab = self.slabs[rank]
         c3 = params.coord[2]
         S = int(params.grid_size[params.coord[0]]) * int(params.grid_size[params.coord[1]])
@@ -202,11 +205,15 @@ class SlabWorker:
     def _exchange(self, sends, recvs):
         """sends/recvs: lists of (tensor, peer). One batched NCCL group (reference: transferBursts)."""
         # raw bytes: NCCL has no int16, and the payload is opaque to the transport anyway
+        for w in self._exchange_start(sends, recvs):
+            w.wait()
+
+    def _exchange_start(self, sends, recvs):
+        """Enqueue the transfers and return the work handles (NCCL: they run on the communicator's stream after the
+        work already enqueued on the compute stream, so kernels launched next overlap with them)."""
         ops = [dist.P2POp(dist.isend, t.view(torch.uint8), peer, self.group) for t, peer in sends if t.numel()]
         ops += [dist.P2POp(dist.irecv, t.view(torch.uint8), peer, self.group) for t, peer in recvs if t.numel()]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
 
     def _exchange_counts(self, n_to_left: int, n_to_right: int):
         dev = self.device
@@ -257,6 +264,8 @@ class SlabWorker:
             return (a, b - a)
         self.edge_left = layer_range(xs) if self._left() is not None else (0, 0)
         self.edge_right = layer_range(xe - 1) if self._right() is not None else (0, 0)
+        # first inner-edge particle: [0, edge_start) is the inner stripe, [edge_start, n_own) the edge stripe
+        self.edge_start = int(seg[1]) if seg[1] != 0xFFFFFFFF else n_own
         # APPEND_EXTERNAL: fresh halo copies from the owners (pos, vel, info, hash)
         cnt = self._exchange_counts(self.edge_left[1], self.edge_right[1])
         nl_, nr_ = cnt["from_left"], cnt["from_right"]
@@ -295,9 +304,11 @@ class SlabWorker:
     def _forces(self, which: int) -> float:
         be = self.backend
         n, n_own = self.numParticles, self.numOwn
-        nblocks = be.forces(self.pos[which], self.vel[which], self.info, self.hash, self.cellstart, self.neibslist,
-                            self.forces_buf, self.cfl, n, 0, n_own)
-        self.launches += 2
+        # striping (reference: --striping, src/GPUWorker.cc:2086-2160): forces of the EDGE stripe first, then its
+        # exchange is enqueued and overlaps with the forces kernel of the INNER stripe
+        e0 = min(self.edge_start, n_own)
+        args = (self.pos[which], self.vel[which], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
+        nb_edge = be.forces(*args, e0, n_own, 0) if n_own > e0 else 0
         # UPDATE_EXTERNAL(FORCES): owner's inner-edge forces -> neighbour's halo range
         f = self.forces_buf
         sends, recvs = [], []
@@ -307,7 +318,12 @@ class SlabWorker:
         if self._right() is not None:
             sends.append((f[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
             recvs.append((f[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
-        self._exchange(sends, recvs)
+        works = self._exchange_start(sends, recvs)
+        nb_inner = be.forces(*args, 0, e0, nb_edge) if e0 > 0 else 0
+        for w_ in works:
+            w_.wait()
+        nblocks = nb_edge + nb_inner
+        self.launches += 2
         if self.fixed_dt is not None:
             return self.fixed_dt
         dt = be.dtreduce(self.cfl, nblocks) if n_own > 0 else float("inf")

@@ -46,14 +46,14 @@ class OracleBackend:
                                C.c_uint32(n), C.c_uint32(range_end), C.byref(out))
         return out
 
-    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to):
+    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to, cfl_offset=0):
         lib = ob.lib()
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         f = _np(forces)
         f[frm:to] = 0
         return int(lib.oracle_forces(C.byref(self.params), p(_np(pos)), p(_np(vel)), p(_np(info, np.uint16)),
                                      p(_np(hashv, np.uint32)), p(_np(cs, np.uint32)), p(_np(nl, np.uint16)), None, None,
-                                     p(f), p(_np(cfl)), None, C.c_uint32(n), C.c_uint32(frm), C.c_uint32(to), C.c_uint32(0)))
+                                     p(f), p(_np(cfl)), None, C.c_uint32(n), C.c_uint32(frm), C.c_uint32(to), C.c_uint32(cfl_offset)))
 
     def dtreduce(self, cfl, nblocks):
         return ob.dtreduce(self.params, _np(cfl)[:nblocks])

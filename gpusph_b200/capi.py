@@ -120,6 +120,8 @@ PROTOTYPES = {
     "b200sph_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, C.POINTER(_U)]),
     "b200sph_eos_probe": (C.c_int, [_P, _P, _P, _P, _U]),
     "b200sph_dtreduce": (C.c_int, [_P, _P, _P, _U, C.POINTER(C.c_float)]),
+    "b200sph_cflmax": (C.c_int, [_P, _P, _U, _P]),
+    "b200sph_dt_from_cfl": (C.c_int, [_P, C.c_float, C.POINTER(C.c_float)]),
     "b200sph_euler": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_float, C.c_int]),
 }
 

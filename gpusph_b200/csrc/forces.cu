@@ -448,6 +448,33 @@ max_reduce_kernel(const float *__restrict__ in, const uint n, float *__restrict_
 	}
 }
 
+static float dt_from_cfl(const b200sph_params &hp, const float maxcfl)
+{
+	float dt = hp.dtadaptfactor * fminf(sqrtf(hp.slength / maxcfl), hp.slength / hp.max_sound_speed_cfl);
+	if (hp.rheologytype != B200SPH_RHEOLOGY_INVISCID || hp.turbmodel > B200SPH_TURB_ARTIFICIAL) {
+		float dt_visc = hp.slength * hp.slength / hp.max_kinvisc;
+		dt_visc *= 0.125f;
+		if (dt_visc < dt) dt = dt_visc;
+	}
+	return dt;
+}
+
+extern "C" int b200sph_cflmax(b200sph_ctx *ctx, const float *cfl, uint32_t num_blocks, float *max_out)
+{
+	CHECK_CTX(ctx);
+	if (!cfl || !max_out) { b200_set_error("cflmax: null buffer"); return B200SPH_EINVAL; }
+	max_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(cfl, num_blocks, max_out);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_dt_from_cfl(const b200sph_ctx *ctx, float max_cfl, float *dt_out)
+{
+	if (!ctx || !dt_out) { b200_set_error("dt_from_cfl: null argument"); return B200SPH_EINVAL; }
+	*dt_out = dt_from_cfl(ctx->hp, max_cfl);
+	return B200SPH_OK;
+}
+
 extern "C" int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl, uint32_t num_blocks, float *dt_out)
 {
 	CHECK_CTX(ctx);
@@ -458,13 +485,7 @@ extern "C" int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_
 	KERNEL_TRY();
 	CUDA_TRY(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-	const float maxcfl = ctx->h_scalar[0];
-	float dt = hp.dtadaptfactor * fminf(sqrtf(hp.slength / maxcfl), hp.slength / hp.max_sound_speed_cfl);
-	if (hp.rheologytype != B200SPH_RHEOLOGY_INVISCID || hp.turbmodel > B200SPH_TURB_ARTIFICIAL) {
-		float dt_visc = hp.slength * hp.slength / hp.max_kinvisc;
-		dt_visc *= 0.125f;
-		if (dt_visc < dt) dt = dt_visc;
-	}
+	const float dt = dt_from_cfl(hp, ctx->h_scalar[0]);
 	*dt_out = dt;
 	return B200SPH_OK;
 }

@@ -195,6 +195,16 @@ class ForcesEngine:
         return dt.value
 
 
+    def cflmax(self, bufread: BufferList, numBlocks: int, out: torch.Tensor) -> None:
+        """max of the CFL blocks into a device scalar, no synchronisation (multi-GPU: all-reduced on the device)."""
+        capi.check(self.lib.b200sph_cflmax(self.ctx.handle, bufread.ptr(BUFFER_CFL), numBlocks, out.data_ptr()))
+
+    def dt_from_cfl(self, max_cfl: float) -> float:
+        dt = C.c_float()
+        capi.check(self.lib.b200sph_dt_from_cfl(self.ctx.handle, C.c_float(max_cfl), C.byref(dt)))
+        return dt.value
+
+
 class IntegrationEngine:
     """AbstractIntegrationEngine (src/engine_integration.h:40-143) — basicstep."""
 

@@ -129,6 +129,12 @@ class CudaBackend:
         b = self._b(cfl=cfl)
         return self.fw.forcesEngine.dtreduce(b, b, nblocks)
 
+    def cflmax(self, cfl, nblocks, out):
+        self.fw.forcesEngine.cflmax(self._b(cfl=cfl), nblocks, out)
+
+    def dt_from_cfl(self, m):
+        return self.fw.forcesEngine.dt_from_cfl(m)
+
     def euler(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, dt, step):
         rd = self._b(pos=opos, vel=ovel, info=info, hash=hashv, forces=forces)
         wr = self._b(pos=npos, vel=nvel)
@@ -179,6 +185,7 @@ class SlabWorker:
         self.neibslist = torch.full((int(p.neiblistsize), A), -1, dtype=torch.int16, device=dev)
         self.cfl = torch.zeros(self.backend.fmax_elements(A), dtype=torch.float32, device=dev)
         self.segments = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.cfl_scalar = torch.zeros(1, dtype=torch.float32, device=dev)
         self.new_num = torch.zeros(1, dtype=torch.int32, device=dev)
         self.cdm = torch.from_numpy(compact_device_map(p, self.slab, rank, world).view(np.int32)).to(dev)
         self.pos[0][:n].copy_(torch.from_numpy(particles.pos[sel]).to(dev))
@@ -326,10 +333,19 @@ class SlabWorker:
         self.launches += 2
         if self.fixed_dt is not None:
             return self.fixed_dt
+        # dt = min over ranks (src/GPUSPH.cc:650-657) = dt(max over ranks of the CFL maxima): the block maxima are
+        # reduced on the device, all-reduced(MAX) on the device, and read back once
+        if hasattr(be, "cflmax"):
+            if n_own > 0:
+                be.cflmax(self.cfl, nblocks, self.cfl_scalar)
+            else:
+                self.cfl_scalar.zero_()
+            dist.all_reduce(self.cfl_scalar, op=dist.ReduceOp.MAX, group=self.group)
+            self.launches += 1
+            return be.dt_from_cfl(float(self.cfl_scalar.item()))
         dt = be.dtreduce(self.cfl, nblocks) if n_own > 0 else float("inf")
-        self.launches += 1
         t = torch.tensor([dt], dtype=torch.float32, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)      # src/GPUSPH.cc:650-657
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         return float(t.item())
 
     def step(self) -> None:

@@ -191,12 +191,14 @@ def _box_shell(lo, hi, dp, layers):
 
 
 def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_COLAGROSSI, layers: int = 3,
-                     alloc_extra: float = 0.0, **kw):
+                     alloc_extra: float = 0.0, width_scale: int = 1, **kw):
     """DamBreak3D-like setup (src/problems/DamBreak3D.cu:36-205 with --num_obstacles 0): a 1.6 x 0.67 x 0.6 m
     tank lined with `layers` layers of DYN boundary particles, a 0.4 m long, 0.4 m high water column,
     Wendland kernel, artificial viscosity, c0 = 20, gamma = 7. Fill order/ids are ours, not the reference's
-    (bit-level parity with the reference is tested from the reference's own initial state instead)."""
-    dim = np.array([1.6, 0.67, 0.6])
+    (bit-level parity with the reference is tested from the reference's own initial state instead).
+    width_scale = N widens the tank (and the water column) N times along y: the weak-scaling variant used by
+    bench.py on N GPUs (same physics per unit width, N times the particles)."""
+    dim = np.array([1.6, 0.67 * width_scale, 0.6])
     H = 0.4
     bd = dp * layers
     wall = _box_shell(np.zeros(3), dim, dp, layers)

@@ -233,6 +233,13 @@ int b200sph_eos_probe(b200sph_ctx *ctx, const void *vel, const void *info, void 
 int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl,
 	uint32_t num_blocks, float *dt_out);
 
+/* The two halves of dtreduce for callers that combine CFL maxima across devices ON the device (multi-GPU: one
+ * NCCL all-reduce(MAX) on `max_out` instead of a host loop over per-device dt, src/GPUSPH.cc:650-657):
+ * b200sph_cflmax writes max(cfl[0..num_blocks)) to the DEVICE float *max_out without synchronising;
+ * b200sph_dt_from_cfl applies the reference's formula (src/cuda/forces.cu:571-600) to a host value. */
+int b200sph_cflmax(b200sph_ctx *ctx, const float *cfl, uint32_t num_blocks, float *max_out);
+int b200sph_dt_from_cfl(const b200sph_ctx *ctx, float max_cfl, float *dt_out);
+
 /* ---- integration engine -------------------------------------------------- */
 
 /* AbstractIntegrationEngine::basicstep (src/engine_integration.h:117; src/cuda/euler.cu:330-372;

@@ -224,6 +224,9 @@ def main():
     import torch
     import torch.distributed as dist
 
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -381,7 +384,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -342,8 +342,11 @@ def main():
                 torch.cuda.synchronize()
                 tot += a.elapsed_time(b)
             return tot / reps
-        # one force evaluation = streaming pre-pass (packs pos/vel/EOS records) + the fused pair kernel
+        # one force evaluation = the fused pair kernel (forces_gather_kernel: fluid<-fluid, fluid<-boundary,
+        # boundary<-fluid, finalize and CFL in one launch)
         t_kernel = timed(w.forces_once)
+        # a streaming kernel for comparison: euler reads pos, vel, forces, info (56 B) and writes pos, vel (32 B)
+        t_euler = timed(w.euler_once)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -351,13 +354,15 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = FORCES_BYTES_PER_PARTICLE * n / (t_kernel / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "forces_kernel (+pack pre-pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "forces_gather_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_particle": FORCES_BYTES_PER_PARTICLE, "kernel_ms": t_kernel,
-                    "timed": "pack_kernel + forces_kernel (one force evaluation), CUDA events, L2 flushed between launches",
+                    "timed": "one forces_gather_kernel launch (= one force evaluation), CUDA events, L2 flushed between launches",
+                    "streaming_reference": {"kernel": "euler_kernel", "algorithmic_bytes_per_particle": 88, "kernel_ms": t_euler,
+                                            "achieved": 88 * n / (t_euler / 1e3) / 1e9, "frac": 88 * n / (t_euler / 1e3) / 1e9 / peak},
                     "pair_rate_G_per_s": w.last_neibs_info.num_interactions / (t_kernel / 1e3) / 1e9,
-                    "note": "pair kernel is FP32-issue/LSU bound, not HBM bound (SURVEY.md 8d); the HBM fraction is reported as required"}
+                    "note": "the pair kernel is instruction-issue / L1-gather bound (ncu: issue 76 %, L1TEX 87 %, DRAM 8 %; profiles/r01_forces_gather_dambreak2m_ncu.txt), not HBM bound (SURVEY.md 8d); the HBM fraction is reported because the contract asks for it"}
         tr = os.path.join(ROOT, "profiles", "forces_traffic.json")
         if os.path.exists(tr):
             try:

@@ -372,6 +372,11 @@ class SlabWorker:
         return ParticleArrays(self.pos[self.cur][:n].cpu().numpy(), self.vel[self.cur][:n].cpu().numpy(),
                               self.info[:n].cpu().numpy().view(np.uint16), self.hash[:n].cpu().numpy().view(np.uint32))
 
+    def euler_once(self) -> None:
+        cur, oth = self.cur, 1 - self.cur
+        self.backend.euler(self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth],
+                           self.numParticles, self.numParticles, 0.0, 1)
+
     def forces_once(self) -> None:
         """One force evaluation on the current state without exchange (bench.py roofline timing)."""
         self.backend.forces(self.pos[self.cur], self.vel[self.cur], self.info, self.hash, self.cellstart, self.neibslist,

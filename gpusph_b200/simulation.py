@@ -161,6 +161,11 @@ class Worker:
         s = self.state(self.cur)
         self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0)
 
+    def euler_once(self) -> None:
+        """One predictor sub-step into the scratch state (bench.py: streaming-kernel reference point)."""
+        rd, wr = self.state(self.cur), self.state(1 - self.cur)
+        self.integration.basicstep(rd, wr, self.numParticles, self.particleRangeEnd, 0.0, 1)
+
     # ---- host copies ----
     def download(self) -> ParticleArrays:
         n = self.numParticles

@@ -369,15 +369,22 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 				const float pz = __fmaf_rn(-(float)z, P.cellSize[2], pos.z);
 				bool encode_cell = true;
 				int neib_type = PT_FLUID;
+				// Particles of a cell are sorted by type (sort key: cell, type, id), so first == last type means the
+				// whole cell has one type: no per-candidate info load, and cells that cannot contribute at all
+				// (test points; boundary cells seen from a DYN/LJ boundary particle) are skipped without touching
+				// their particles. The list produced is the reference's, entry for entry.
+				const int t_first = ptype_of(__ldg(infoArray + bucketStart));
+				const int t_last = ptype_of(__ldg(infoArray + bucketEnd - 1));
+				const bool uniform = t_first == t_last;
+				const bool skip_bb = boundary && (P.boundarytype == B200SPH_DYN_BOUNDARY || P.boundarytype == B200SPH_LJ_BOUNDARY);
+				if (uniform && (t_first == PT_TESTPOINT || (skip_bb && t_first == PT_BOUNDARY))) continue;
 				for (uint j = bucketStart; j < bucketEnd; ++j) {
 					if (j == index) continue;
-					const ushort4 ninfo = __ldg(infoArray + j);
-					const int nt = ptype_of(ninfo);
+					const int nt = uniform ? t_first : ptype_of(__ldg(infoArray + j));
 					if (nt == PT_TESTPOINT) continue;                                     // :584
 					if (!encode_cell && neib_type != nt) encode_cell = true;             // :588
 					neib_type = nt;
-					if (boundary && nt == PT_BOUNDARY &&
-						(P.boundarytype == B200SPH_DYN_BOUNDARY || P.boundarytype == B200SPH_LJ_BOUNDARY)) continue;   // :591-602
+					if (skip_bb && nt == PT_BOUNDARY) continue;                           // :591-602
 					const float4 np = __ldg(posArray + j);
 					if (inactive_w(np.w)) continue;                                       // :612
 					const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);

@@ -104,10 +104,7 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
 	{ const char *e = getenv("B200SPH_FORCES_TILES"); ctx->use_tiles = e ? atoi(e) : 0; }   // staged kernel is opt-in: measured slower than the gather kernel
-	{	// tile configurations: keep in sync with pick_kernels() in forces.cu
-		static const int cfgs[7][2] = { {64, 1024}, {128, 1536}, {128, 1152}, {64, 1024}, {64, 768}, {128, 1536}, {64, 1024} };
-		const char *e = getenv("B200SPH_TILE_CFG"); int c = e ? atoi(e) : 0; if (c < 0 || c > 5) c = 0;
-		ctx->tile_cfg = c; ctx->tile_p = cfgs[c][0]; ctx->tile_s = cfgs[c][1]; }
+	ctx->tile_cfg = 0; ctx->tile_p = TILE_P; ctx->tile_s = TILE_S;
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
 	CUDA_TRY(cudaMalloc(&ctx->d_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));

@@ -56,6 +56,10 @@ struct DevParams {
 // One CTA of the staged forces kernel: a run of consecutive non-empty cells along COORD1 inside one
 // (COORD2, COORD3) row, plus the particle ranges of the 9 neighbouring rows that cover its 27-cell
 // neighbourhood (each row of cells is one contiguous particle range because COORD1 is the fastest hash digit).
+// tile shape of the opt-in staged kernel: 128 threads, 1152 staged particles (3 x 16 B x 1152 = 54 KB + 14 KB of cell
+// bases -> 3 CTAs per SM); the best of (128,1536) (128,1152) (64,1024) (64,768) measured on B200
+#define TILE_P 128
+#define TILE_S 1152
 struct Tile {
 	uint first, count;      // central particles [first, first+count)
 	uint row_start[9];      // first staged particle of neighbour row r = (d2+1) + 3*(d3+1)
@@ -86,7 +90,7 @@ struct b200sph_ctx {
 	cudaEvent_t tiles_event; int tiles_state;   // 0 none, 1 copy in flight, 2 valid
 	uint num_tiles; uint tiles_range_end; const uint32_t *tiles_cellstart;
 	int use_tiles;                          // env B200SPH_FORCES_TILES (default 0)
-	int tile_cfg, tile_p, tile_s;           // tile configuration (env B200SPH_TILE_CFG): threads per tile, staged slots
+	int tile_cfg, tile_p, tile_s;           // tile shape handed to the tile builder
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions
 	float *h_scalar;                        // pinned host scalar

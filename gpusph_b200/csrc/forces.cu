@@ -22,6 +22,10 @@
 #include "pair_physics.cuh"
 #include <stdlib.h>
 
+// list rows kept in flight by the gather kernel: measured on B200 at 2 M particles (dambreak2m / lattice2m):
+// 1 row 0.585 / 0.769 ms, 2 rows 0.535 / 0.805 ms, 4 rows 0.651 / 0.808 ms
+#define GATHER_PF 2
+
 // ---------------------------------------------------------------------------
 // per-particle pre-pass
 // ---------------------------------------------------------------------------
@@ -200,7 +204,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 				ne = eos_from_density(P, nv.w, MULTIFLUID ? fluid_num_of(__ldg(infoArray + j)) : 0);
 			};
 			const float4 vel = velArray[index];
-			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BLOCK_FORCES, 2>(P, k, index, info, type, pos,
+			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BLOCK_FORCES, GATHER_PF>(P, k, index, info, type, pos,
 				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), my_base, s_celloff, neibsList, fetch, forces);
 		}
 	}
@@ -355,16 +359,10 @@ typedef void (*tile_kernel_t)(const DevParams, const Tile *, const float4 *, con
 template<int RHODIFF>
 static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather_kernel_t *g, tile_kernel_t *t, size_t *smem)
 {
-	// tile configurations (threads, staged slots, list prefetch depth); must match b200_tile_limits() in tiles.cu
+	// the staged kernel's tile shape (TILE_P threads, TILE_S staged slots: common.cuh) is the best of the five measured
 #define PICK(A, L, M) do { *g = forces_gather_kernel<RHODIFF, A, L, M>; \
-	switch (cfg) { \
-	case 1: *t = forces_tile_kernel<RHODIFF, A, L, M, 128, 1536, 4>; *smem = sizeof(TileSmem<128, 1536>); break; \
-	case 2: *t = forces_tile_kernel<RHODIFF, A, L, M, 128, 1152, 4>; *smem = sizeof(TileSmem<128, 1152>); break; \
-	case 3: *t = forces_tile_kernel<RHODIFF, A, L, M, 64, 1024, 4>; *smem = sizeof(TileSmem<64, 1024>); break; \
-	case 4: *t = forces_tile_kernel<RHODIFF, A, L, M, 64, 768, 4>; *smem = sizeof(TileSmem<64, 768>); break; \
-	case 5: *t = forces_tile_kernel<RHODIFF, A, L, M, 128, 1536, 8>; *smem = sizeof(TileSmem<128, 1536>); break; \
-	default: *t = forces_tile_kernel<RHODIFF, A, L, M, 64, 1024, 8>; *smem = sizeof(TileSmem<64, 1024>); break; \
-	} } while (0)
+	(void)cfg; *t = forces_tile_kernel<RHODIFF, A, L, M, TILE_P, TILE_S, 4>; *smem = sizeof(TileSmem<TILE_P, TILE_S>); \
+} while (0)
 	if (multi) {
 		if (artvisc) { if (laminar) PICK(true, true, true); else PICK(true, false, true); }
 		else { if (laminar) PICK(false, true, true); else PICK(false, false, true); }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU box: parity tests (default gather kernel, then the opt-in staged kernel), then quick benches
 (timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6) > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
-(B200SPH_FORCES_TILES=1 B200SPH_TILE_CFG=2 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x 2>&1 | tail -4)
+(B200SPH_FORCES_TILES=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x 2>&1 | tail -4)
 for wl in ${WORKLOADS:-dambreak2m lattice2m}; do
   timeout 300 python bench.py --workload $wl --steps 20 --warmup 10 --no-cpu-baseline 2>gpurun_out/bench_err.log > gpurun_out/bench_${wl}.json
   python - <<PY

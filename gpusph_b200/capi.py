@@ -122,6 +122,11 @@ PROTOTYPES = {
     "b200sph_dtreduce": (C.c_int, [_P, _P, _P, _U, C.POINTER(C.c_float)]),
     "b200sph_cflmax": (C.c_int, [_P, _P, _U, _P]),
     "b200sph_dt_from_cfl": (C.c_int, [_P, C.c_float, C.POINTER(C.c_float)]),
+    "b200sph_step_set_dt": (C.c_int, [_P, C.c_float]),
+    "b200sph_dtreduce_async": (C.c_int, [_P, _P, _U, C.c_int]),
+    "b200sph_euler_async": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_int]),
+    "b200sph_step_end": (C.c_int, [_P]),
+    "b200sph_step_query": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "b200sph_euler": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_float, C.c_int]),
 }
 

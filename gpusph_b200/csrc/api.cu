@@ -111,6 +111,9 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	CUDA_TRY(cudaMallocHost(&ctx->h_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_flag, sizeof(int)));
 	CUDA_TRY(cudaMemset(ctx->d_counters, 0, sizeof(NeibsCounters)));
+	CUDA_TRY(cudaMalloc(&ctx->d_step, sizeof(StepState)));
+	CUDA_TRY(cudaMemset(ctx->d_step, 0, sizeof(StepState)));
+	CUDA_TRY(cudaMallocHost(&ctx->h_step, sizeof(StepState)));
 	CUDA_TRY(cudaMalloc(&ctx->d_tile_info, 4 * sizeof(uint)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_tile_info, 4 * sizeof(uint)));
 	CUDA_TRY(cudaEventCreateWithFlags(&ctx->tiles_event, cudaEventDisableTiming));
@@ -123,7 +126,7 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 	if (!ctx) return B200SPH_OK;
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
-	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);
 	free(ctx);
 	return B200SPH_OK;

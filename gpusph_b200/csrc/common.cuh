@@ -75,6 +75,13 @@ struct NeibsCounters {     // mirrors the reference's device counters, src/cuda/
 	int pad;
 };
 
+// device-resident time-stepping record (b200sph_step_* entry points)
+struct StepState {
+	double t;
+	unsigned long long iterations;
+	float dt, dt1, dt2, pad;
+};
+
 struct b200sph_ctx {
 	b200sph_params hp;      // host copy
 	DevParams dp;
@@ -95,6 +102,7 @@ struct b200sph_ctx {
 	float *d_scalar;                        // device scalar for reductions
 	float *h_scalar;                        // pinned host scalar
 	int *d_flag; int *h_flag;
+	StepState *d_step; StepState *h_step;
 };
 
 // ---- error plumbing ----

@@ -7,10 +7,14 @@ template<int STEP>
 __global__ void __launch_bounds__(BLOCK_STREAM)
 euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ oldPos, const float4 *__restrict__ oldVel,
 	const ushort4 *__restrict__ infoArray, const float4 *__restrict__ forces,
-	float4 *__restrict__ newPos, float4 *__restrict__ newVel, const uint numParticles, const float dt)
+	float4 *__restrict__ newPos, float4 *__restrict__ newVel, const uint numParticles, const float dt_arg,
+	const StepState *__restrict__ dev_state)
 {
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
 	if (index >= numParticles) return;
+	// dt either as an argument (reference-style call) or from the device-resident record: dt/2 on the predictor
+	// (PredictorCorrector::getDtOperatorForStep), dt on the corrector
+	const float dt = dev_state ? (STEP == 1 ? dev_state->dt / 2 : dev_state->dt) : dt_arg;
 	float4 pos = oldPos[index];
 	float4 vel = oldVel[index];
 	const float4 force = forces[index];
@@ -50,10 +54,31 @@ extern "C" int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *
 	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
 	if (step == 1)
 		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt);
+			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL);
 	else
 		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt);
+			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_euler_async(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
+	const uint32_t *hash, const void *forces, void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, int step)
+{
+	CHECK_CTX(ctx);
+	(void)hash;
+	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }
+	if (particle_range_end == 0) return B200SPH_OK;
+	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
+	const uint nb = div_up(particle_range_end, BLOCK_STREAM);
+	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
+	if (step == 1)
+		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
+			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step);
+	else
+		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
+			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step);
 	KERNEL_TRY();
 	return B200SPH_OK;
 }

@@ -487,3 +487,86 @@ extern "C" int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_
 	*dt_out = dt;
 	return B200SPH_OK;
 }
+
+// ---------------------------------------------------------------------------
+// device-resident dt (b200sph_step_* in include/b200sph.h)
+// ---------------------------------------------------------------------------
+struct DtConsts { float dtadaptfactor, slength, max_ss_cfl, max_kinvisc; int viscous; };
+
+__device__ __forceinline__ float dt_from_cfl_dev(const DtConsts c, const float maxcfl)
+{	// same arithmetic as dt_from_cfl() above (src/cuda/forces.cu:571-600)
+	float dt = c.dtadaptfactor * fminf(sqrtf(c.slength / maxcfl), c.slength / c.max_ss_cfl);
+	if (c.viscous) {
+		float dt_visc = c.slength * c.slength / c.max_kinvisc;
+		dt_visc *= 0.125f;
+		if (dt_visc < dt) dt = dt_visc;
+	}
+	return dt;
+}
+
+__global__ void __launch_bounds__(1024)
+dtreduce_async_kernel(const float *__restrict__ in, const uint n, const DtConsts c, StepState *__restrict__ st, const int which)
+{
+	float m = 0.0f;
+	for (uint i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, in[i]);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	__shared__ float s[32];
+	if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		m = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0f;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+		if (threadIdx.x == 0) { const float dt = dt_from_cfl_dev(c, m); if (which == 1) st->dt1 = dt; else st->dt2 = dt; }
+	}
+}
+
+__global__ void step_end_kernel(StepState *st)
+{
+	st->t += (double)st->dt;
+	st->iterations += 1;
+	st->dt = fminf(st->dt1, st->dt2);
+}
+
+__global__ void step_set_dt_kernel(StepState *st, const float dt) { st->dt = dt; st->dt1 = dt; st->dt2 = dt; }
+
+extern "C" int b200sph_step_set_dt(b200sph_ctx *ctx, float dt)
+{
+	CHECK_CTX(ctx);
+	step_set_dt_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_step, dt);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_dtreduce_async(b200sph_ctx *ctx, const float *cfl, uint32_t num_blocks, int which)
+{
+	CHECK_CTX(ctx);
+	if (!cfl || (which != 1 && which != 2)) { b200_set_error("dtreduce_async: bad argument"); return B200SPH_EINVAL; }
+	const b200sph_params &hp = ctx->hp;
+	DtConsts c;
+	c.dtadaptfactor = hp.dtadaptfactor; c.slength = hp.slength; c.max_ss_cfl = hp.max_sound_speed_cfl; c.max_kinvisc = hp.max_kinvisc;
+	c.viscous = (hp.rheologytype != B200SPH_RHEOLOGY_INVISCID || hp.turbmodel > B200SPH_TURB_ARTIFICIAL) ? 1 : 0;
+	dtreduce_async_kernel<<<1, 1024, 0, ctx->stream>>>(cfl, num_blocks, c, ctx->d_step, which);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_step_end(b200sph_ctx *ctx)
+{
+	CHECK_CTX(ctx);
+	step_end_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_step);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}
+
+extern "C" int b200sph_step_query(b200sph_ctx *ctx, double *t, float *dt, uint64_t *iterations)
+{
+	CHECK_CTX(ctx);
+	CUDA_TRY(cudaMemcpyAsync(ctx->h_step, ctx->d_step, sizeof(StepState), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	if (t) *t = ctx->h_step->t;
+	if (dt) *dt = ctx->h_step->dt;
+	if (iterations) *iterations = ctx->h_step->iterations;
+	return B200SPH_OK;
+}

@@ -195,6 +195,21 @@ class ForcesEngine:
         return dt.value
 
 
+    # ---- device-resident dt (include/b200sph.h "device-resident time stepping") ----
+    def dtreduce_async(self, bufread: BufferList, numBlocks: int, which: int) -> None:
+        capi.check(self.lib.b200sph_dtreduce_async(self.ctx.handle, bufread.ptr(BUFFER_CFL), numBlocks, which))
+
+    def step_set_dt(self, dt: float) -> None:
+        capi.check(self.lib.b200sph_step_set_dt(self.ctx.handle, C.c_float(dt)))
+
+    def step_end(self) -> None:
+        capi.check(self.lib.b200sph_step_end(self.ctx.handle))
+
+    def step_query(self):
+        t, dt, it = C.c_double(), C.c_float(), C.c_uint64()
+        capi.check(self.lib.b200sph_step_query(self.ctx.handle, C.byref(t), C.byref(dt), C.byref(it)))
+        return t.value, dt.value, it.value
+
     def cflmax(self, bufread: BufferList, numBlocks: int, out: torch.Tensor) -> None:
         """max of the CFL blocks into a device scalar, no synchronisation (multi-GPU: all-reduced on the device)."""
         capi.check(self.lib.b200sph_cflmax(self.ctx.handle, bufread.ptr(BUFFER_CFL), numBlocks, out.data_ptr()))
@@ -218,6 +233,15 @@ class IntegrationEngine:
             self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
             bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES),
             bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, dt, step))
+
+
+    def basicstep_async(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
+                        step: int) -> None:
+        """basicstep with dt taken from the context's device-resident record (no host round trip)."""
+        capi.check(self.lib.b200sph_euler_async(
+            self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
+            bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES),
+            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, step))
 
 
 class SimFramework:

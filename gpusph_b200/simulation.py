@@ -29,7 +29,8 @@ class Worker:
 
     def __init__(self, params: capi.Params, particles: ParticleArrays, device=None, *,
                  buildneibsfreq: int = 10, clobber: bool = False, fixed_dt: float | None = None,
-                 compact_dev_map: np.ndarray | None = None, start_iteration: int = 0, dt: float | None = None):
+                 compact_dev_map: np.ndarray | None = None, start_iteration: int = 0, dt: float | None = None,
+                 device_dt: bool = True):
         self.framework = SimFramework(params, device)
         self.params = self.framework.params
         self.device = self.framework.ctx.device
@@ -71,11 +72,43 @@ class Worker:
         self.info[:n].copy_(_dev(particles.info.view(np.int16), dev))
         self.hash[:n].copy_(_dev(particles.hash.view(np.int32), dev))
         self.iterations = start_iteration  # > 0 when resuming from a checkpoint: the first rebuild then uses calcHash
-        self.t = 0.0
-        self.dt = float(fixed_dt) if fixed_dt is not None else (float(dt) if dt is not None else initial_dt(self.params))
+        # adaptive dt lives on the device by default: no host round trip per force evaluation (the reference does two
+        # blocking 4-byte readbacks per step); `dt` and `t` are fetched on demand
+        self.device_dt = device_dt and fixed_dt is None
+        self._t = 0.0
+        self._dt = float(fixed_dt) if fixed_dt is not None else (float(dt) if dt is not None else initial_dt(self.params))
+        self._stale = False
+        if self.device_dt:
+            self.forces.step_set_dt(self._dt)
         self.last_neibs_info = None
         self.total_interactions = 0       # sum over steps of list entries x 2 force evaluations
         self.launches = 0                 # hand-written kernels launched (CUB's sort passes not counted)
+
+    def _sync_time(self) -> None:
+        if self._stale:
+            self._t, self._dt, _ = self.forces.step_query()
+            self._stale = False
+
+    @property
+    def dt(self) -> float:
+        self._sync_time()
+        return self._dt
+
+    @dt.setter
+    def dt(self, v: float) -> None:
+        self._sync_time()
+        self._dt = float(v)
+        if self.device_dt:
+            self.forces.step_set_dt(self._dt)
+
+    @property
+    def t(self) -> float:
+        self._sync_time()
+        return self._t
+
+    @t.setter
+    def t(self, v: float) -> None:
+        self._t = float(v)
 
     # ---- buffer lists ----
     def _common(self) -> dict:
@@ -126,7 +159,7 @@ class Worker:
         if self.clobber:
             self.forces_buf.zero_()                # pre_forces: clobber FORCES, src/GPUWorker.cc:1949
         nblocks = self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0)
-        self.launches += 2                # eos pre-pass + fused forces kernel
+        self.launches += 1                # fused forces kernel
         if self.fixed_dt is not None:
             return self.fixed_dt
         self.launches += 1                # CFL max-reduce
@@ -138,23 +171,35 @@ class Worker:
             self.build_neibs()
         n, end = self.numParticles, self.particleRangeEnd
         cur, oth = self.cur, 1 - self.cur
-        dt = self.dt
-        # predictor: forces(n) -> euler step 1 with dt/2 writes n*
-        dt1 = self._forces(cur)
-        rd = self.state(cur)
-        wr = self.state(oth)
-        self.integration.basicstep(rd, wr, n, end, dt / 2, 1)
-        # corrector: forces(n*) -> euler step 2 with dt, reading pos/vel of n, updating n* in place -> n+1
-        dt2 = self._forces(oth)
-        self.integration.basicstep(rd, wr, n, end, dt, 2)
-        self.launches += 2                # two euler launches
+        rd, wr = self.state(cur), self.state(oth)
+        if self.device_dt:
+            # everything enqueued, nothing read back: forces(n) -> dt candidate 1 -> euler step 1 (dt/2) ->
+            # forces(n*) -> dt candidate 2 -> euler step 2 (dt) -> t += dt, dt = min(candidates)
+            for which, st in ((1, rd), (2, wr)):
+                if self.clobber:
+                    self.forces_buf.zero_()
+                nblocks = self.forces.basicstep(st, st, n, 0, end, 0)
+                self.forces.dtreduce_async(st, nblocks, which)
+                self.integration.basicstep_async(rd, wr, n, end, which)
+            self.forces.step_end()
+            self.launches += 2 * 3 + 1
+            self._stale = True
+        else:
+            dt = self._dt
+            # predictor: forces(n) -> euler step 1 with dt/2 writes n*
+            dt1 = self._forces(cur)
+            self.integration.basicstep(rd, wr, n, end, dt / 2, 1)
+            # corrector: forces(n*) -> euler step 2 with dt, reading pos/vel of n, updating n* in place -> n+1
+            dt2 = self._forces(oth)
+            self.integration.basicstep(rd, wr, n, end, dt, 2)
+            self.launches += 2                # two euler launches
+            self._t += dt
+            if self.fixed_dt is None:
+                self._dt = min(dt1, dt2)      # src/GPUWorker.cc:2224-2229, src/GPUSPH.cc:650-657
         self.cur = oth
         self.iterations += 1
-        self.t += dt
         if self.last_neibs_info is not None:
             self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
-        if self.fixed_dt is None:
-            self.dt = min(dt1, dt2)                # src/GPUWorker.cc:2224-2229, src/GPUSPH.cc:650-657
 
     def forces_once(self) -> None:
         """One force evaluation on the current state (bench.py roofline timing)."""

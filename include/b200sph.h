@@ -250,6 +250,27 @@ int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
 	void *new_pos, void *new_vel,
 	uint32_t num_particles, uint32_t particle_range_end, float dt, int step);
 
+/* ---- device-resident time stepping (no reference counterpart) ---------------
+ * The reference reads the CFL maximum back to the host after every force evaluation (two blocking 4-byte copies
+ * per step, src/cuda/forces.cu:153-177) and hands dt back down as a kernel argument. These entry points keep
+ * {dt, dt candidates, t, iteration} in a small device record owned by the context so that a caller can enqueue
+ * whole time steps without synchronising:
+ *   b200sph_step_set_dt      host -> device: dt for the next step (first step / after a checkpoint)
+ *   b200sph_dtreduce_async   dtreduce, result stored as candidate `which` (1 = predictor, 2 = corrector)
+ *   b200sph_euler_async      b200sph_euler with dt taken from the device record (dt/2 for step 1)
+ *   b200sph_step_end         t += dt, iteration++, dt = min(candidate 1, candidate 2)
+ *                            (src/GPUWorker.cc:2224-2229, src/GPUSPH.cc:636-699)
+ *   b200sph_step_query       device -> host (synchronises)
+ * Results are identical to the host-dt path: same kernels, same arithmetic. */
+int b200sph_step_set_dt(b200sph_ctx *ctx, float dt);
+int b200sph_dtreduce_async(b200sph_ctx *ctx, const float *cfl, uint32_t num_blocks, int which);
+int b200sph_euler_async(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
+	const void *info, const uint32_t *hash, const void *forces,
+	void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, int step);
+int b200sph_step_end(b200sph_ctx *ctx);
+int b200sph_step_query(b200sph_ctx *ctx, double *t, float *dt, uint64_t *iterations);
+
 #ifdef __cplusplus
 }
 #endif

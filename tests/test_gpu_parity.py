@@ -381,3 +381,19 @@ def test_poiseuille_steady_profile_is_preserved():
     err = np.abs(out.vel[fl, 0] - exact).max() / vmax
     assert err < 0.02, f"L-inf error {err:.3%}"
     assert np.abs(out.vel[fl, 1:3]).max() < 0.01 * vmax
+
+
+def test_device_resident_dt_matches_host_dt_path_bitwise():
+    """The b200sph_step_* entry points (dt kept on the device, nothing read back during a step) must reproduce the
+    reference-style host-dt call sequence bit for bit, including the adaptive dt sequence and the simulated time."""
+    params, parts = get("dambreak")
+    a = Worker(params, parts, 0, device_dt=True)
+    b = Worker(params, parts, 0, device_dt=False)
+    for _ in range(13):
+        a.step()
+        b.step()
+    assert a.dt == b.dt and a.t == pytest.approx(b.t, rel=1e-15)
+    ga, gb = a.download(), b.download()
+    assert np.array_equal(ga.hash, gb.hash) and np.array_equal(ga.info, gb.info)
+    assert np.array_equal(ga.pos.view(np.uint32), gb.pos.view(np.uint32))
+    assert np.array_equal(ga.vel.view(np.uint32), gb.vel.view(np.uint32))

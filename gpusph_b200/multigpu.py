@@ -135,6 +135,24 @@ class CudaBackend:
     def dt_from_cfl(self, m):
         return self.fw.forcesEngine.dt_from_cfl(m)
 
+    # device-resident dt (no host round trip per force evaluation)
+    def dtreduce_async(self, cfl, nblocks, which):
+        self.fw.forcesEngine.dtreduce_async(self._b(cfl=cfl), nblocks, which)
+
+    def euler_async(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, step):
+        rd = self._b(pos=opos, vel=ovel, info=info, hash=hashv, forces=forces)
+        wr = self._b(pos=npos, vel=nvel)
+        self.fw.integrationEngine.basicstep_async(rd, wr, n, range_end, step)
+
+    def step_set_dt(self, dt):
+        self.fw.forcesEngine.step_set_dt(dt)
+
+    def step_end(self):
+        self.fw.forcesEngine.step_end()
+
+    def step_query(self):
+        return self.fw.forcesEngine.step_query()
+
     def euler(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, dt, step):
         rd = self._b(pos=opos, vel=ovel, info=info, hash=hashv, forces=forces)
         wr = self._b(pos=npos, vel=nvel)
@@ -194,13 +212,35 @@ class SlabWorker:
         self.hash[:n].copy_(torch.from_numpy(particles.hash[sel].view(np.int32)).to(dev))
         self.numParticles = n          # own + halo
         self.numOwn = 0                # set by the first rebuild
-        self.iterations, self.t = 0, 0.0
-        self.dt = float(fixed_dt) if fixed_dt is not None else initial_dt(p)
+        self.iterations = 0
+        self._t = 0.0
+        self._dt = float(fixed_dt) if fixed_dt is not None else initial_dt(p)
+        self._stale = False
+        # adaptive dt stays on the device when the backend supports it (CUDA engines): CFL maxima are reduced on the
+        # device, all-reduced (MAX) over NCCL on the device and turned into dt on the device
+        self.device_dt = fixed_dt is None and hasattr(self.backend, "dtreduce_async")
+        if self.device_dt:
+            self.backend.step_set_dt(self._dt)
         self.last_neibs_info = None
         self.total_interactions = 0
         self.launches = 0
         # ranges for the per-evaluation force exchange: (start, count)
         self.edge_left = self.edge_right = self.halo_left = self.halo_right = (0, 0)
+
+    def _sync_time(self):
+        if self._stale:
+            self._t, self._dt, _ = self.backend.step_query()
+            self._stale = False
+
+    @property
+    def dt(self):
+        self._sync_time()
+        return self._dt
+
+    @property
+    def t(self):
+        self._sync_time()
+        return self._t
 
     # ------------------------------------------------------------------ communication helpers
     def _left(self):
@@ -252,25 +292,28 @@ class SlabWorker:
                    self.info, self.hash, self.partindex, n, self.new_num)
         self.cur = cur = oth
         oth = 1 - cur
-        seg = self.segments.cpu().numpy().view(np.uint32)
-        n_active = int(self.new_num.item())
-        # CROP: keep what this rank owns = [inner | inner-edge]; drop stale halo copies and outer particles
-        first_ext = min([int(s) for s in seg[2:4] if s != 0xFFFFFFFF] + [n_active])
-        n_own = first_ext
-        # inner-edge sub-ranges facing each neighbour (contiguous: the slab axis is the slowest hash digit)
-        h = self.hash[:n_own]
-        layer = torch.div(torch.bitwise_and(h, CELLMASK), self.S, rounding_mode="floor")
+        # one packed readback: segment starts, active count and the particle ranges of the two edge layers
+        # (contiguous: the slab axis is the slowest hash digit, so a cell layer is one run of cells)
         xs, xe = self.slab
-        zero = torch.zeros(1, dtype=torch.int64, device=self.device)
+        cs2, ce2 = self.cellstart.view(-1, self.S), self.cellend.view(-1, self.S)
+        big = torch.iinfo(torch.int32).max
 
-        def layer_range(x):
-            m = (layer == x).nonzero()
-            if m.numel() == 0:
-                return (0, 0)
-            a, b = int(m[0].item()), int(m[-1].item()) + 1
-            return (a, b - a)
-        self.edge_left = layer_range(xs) if self._left() is not None else (0, 0)
-        self.edge_right = layer_range(xe - 1) if self._right() is not None else (0, 0)
+        def layer_range_dev(x):
+            lcs = cs2[x]
+            valid = lcs != -1
+            return torch.stack([torch.where(valid, lcs, big).min(), torch.where(valid, ce2[x], 0).max()])
+        packed = torch.cat([self.segments, self.new_num, layer_range_dev(xs), layer_range_dev(xe - 1)]).cpu().numpy()
+        seg = packed[:4].view(np.uint32)
+        n_active = int(packed[4])
+        # CROP: keep what this rank owns = [inner | inner-edge]; drop stale halo copies and outer particles
+        first_ext = min([int(s_) for s_ in seg[2:4] if s_ != 0xFFFFFFFF] + [n_active])
+        n_own = first_ext
+
+        def rng(a, b_):
+            a, b_ = int(a), int(b_)
+            return (a, b_ - a) if b_ > a and a != big else (0, 0)
+        self.edge_left = rng(packed[5], packed[6]) if self._left() is not None else (0, 0)
+        self.edge_right = rng(packed[7], packed[8]) if self._right() is not None else (0, 0)
         # first inner-edge particle: [0, edge_start) is the inner stripe, [edge_start, n_own) the edge stripe
         self.edge_start = int(seg[1]) if seg[1] != 0xFFFFFFFF else n_own
         # APPEND_EXTERNAL: fresh halo copies from the owners (pos, vel, info, hash)
@@ -308,7 +351,7 @@ class SlabWorker:
         self.launches += 8
 
     # ------------------------------------------------------------------ time stepping
-    def _forces(self, which: int) -> float:
+    def _forces(self, which: int, cand: int = 0) -> float:
         be = self.backend
         n, n_own = self.numParticles, self.numOwn
         # striping (reference: --striping, src/GPUWorker.cc:2086-2160): forces of the EDGE stripe first, then its
@@ -333,6 +376,15 @@ class SlabWorker:
         self.launches += 2
         if self.fixed_dt is not None:
             return self.fixed_dt
+        if self.device_dt:
+            if n_own > 0:
+                be.cflmax(self.cfl, nblocks, self.cfl_scalar)
+            else:
+                self.cfl_scalar.zero_()
+            dist.all_reduce(self.cfl_scalar, op=dist.ReduceOp.MAX, group=self.group)
+            be.dtreduce_async(self.cfl_scalar, 1, cand)      # dt candidate from the global maximum, on the device
+            self.launches += 2
+            return 0.0
         # dt = min over ranks (src/GPUSPH.cc:650-657) = dt(max over ranks of the CFL maxima): the block maxima are
         # reduced on the device, all-reduced(MAX) on the device, and read back once
         if hasattr(be, "cflmax"):
@@ -354,18 +406,27 @@ class SlabWorker:
         be = self.backend
         n = self.numParticles
         cur, oth = self.cur, 1 - self.cur
-        dt = self.dt
-        dt1 = self._forces(cur)
-        be.euler(self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n, dt / 2, 1)
-        dt2 = self._forces(oth)
-        be.euler(self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n, dt, 2)
-        self.launches += 2
+        eargs = (self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n)
+        if self.device_dt:
+            self._forces(cur, 1)
+            be.euler_async(*eargs, 1)
+            self._forces(oth, 2)
+            be.euler_async(*eargs, 2)
+            be.step_end()
+            self._stale = True
+        else:
+            dt = self._dt
+            dt1 = self._forces(cur)
+            be.euler(*eargs, dt / 2, 1)
+            dt2 = self._forces(oth)
+            be.euler(*eargs, dt, 2)
+            self._t += dt
+            if self.fixed_dt is None:
+                self._dt = min(dt1, dt2)
+        self.launches += 3
         self.cur = oth
         self.iterations += 1
-        self.t += dt
         self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
-        if self.fixed_dt is None:
-            self.dt = min(dt1, dt2)
 
     def download_own(self) -> ParticleArrays:
         n = self.numOwn

@@ -118,6 +118,14 @@ PROTOTYPES = {
     "b200sph_fmax_temp_elements": (_U, [_U]),
     "b200sph_round_particles": (_U, [_U]),
     "b200sph_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, C.POINTER(_U)]),
+    "b200sph_set_rbcg": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
+    "b200sph_set_rbstart": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
+    "b200sph_set_rbtrans": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
+    "b200sph_set_rbsteprot": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
+    "b200sph_set_rblinearvel": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
+    "b200sph_set_rbangularvel": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
+    "b200sph_forces_bodies": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, C.POINTER(_U)]),
+    "b200sph_reduce_rb_forces": (C.c_int, [_P, _P, _P, _P, C.POINTER(_U), C.POINTER(C.c_float), C.POINTER(C.c_float), _U, _U]),
     "b200sph_eos_probe": (C.c_int, [_P, _P, _P, _P, _U]),
     "b200sph_dtreduce": (C.c_int, [_P, _P, _P, _U, C.POINTER(C.c_float)]),
     "b200sph_cflmax": (C.c_int, [_P, _P, _U, _P]),

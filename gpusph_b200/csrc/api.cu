@@ -111,6 +111,10 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	CUDA_TRY(cudaMallocHost(&ctx->h_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_flag, sizeof(int)));
 	CUDA_TRY(cudaMemset(ctx->d_counters, 0, sizeof(NeibsCounters)));
+	CUDA_TRY(cudaMalloc(&ctx->d_bodies, sizeof(BodyData)));
+	CUDA_TRY(cudaMemset(ctx->d_bodies, 0, sizeof(BodyData)));
+	CUDA_TRY(cudaMallocHost(&ctx->h_bodies, sizeof(BodyData)));
+	memset(ctx->h_bodies, 0, sizeof(BodyData));
 	CUDA_TRY(cudaMalloc(&ctx->d_step, sizeof(StepState)));
 	CUDA_TRY(cudaMemset(ctx->d_step, 0, sizeof(StepState)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_step, sizeof(StepState)));
@@ -126,7 +130,7 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 	if (!ctx) return B200SPH_OK;
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
-	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);
 	free(ctx);
 	return B200SPH_OK;
@@ -163,3 +167,54 @@ extern "C" uint32_t b200sph_fmax_temp_elements(uint32_t n)
 	return nb;
 }
 extern "C" uint32_t b200sph_round_particles(uint32_t n) { return (n / BLOCK_FORCES) * BLOCK_FORCES; }
+
+// ---- moving bodies: host copies are kept in pinned memory and pushed to the device record on the context's stream ----
+static int push_bodies(b200sph_ctx *ctx)
+{
+	// the copy must be stream-ordered with the kernels that read it, but the pinned source is reused by the next
+	// set call: synchronise (these are per-step host calls in the reference too, each a blocking symbol upload)
+	CUDA_TRY(cudaMemcpyAsync(ctx->d_bodies, ctx->h_bodies, sizeof(BodyData), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	ctx->have_bodies = 1;
+	return B200SPH_OK;
+}
+#define CHECK_BODIES(n, p) do { CHECK_CTX(ctx); if ((n) < 0 || (n) > B200SPH_MAX_BODIES) { b200_set_error("too many bodies (%d > %d)", (n), B200SPH_MAX_BODIES); return B200SPH_EINVAL; } \
+	if ((n) && !(p)) { b200_set_error("null body array"); return B200SPH_EINVAL; } if ((n) == 0) return B200SPH_OK; } while (0)
+
+extern "C" int b200sph_set_rbcg(b200sph_ctx *ctx, const int *g, const float *c, int n)
+{
+	CHECK_BODIES(n, g);
+	if (!c) { b200_set_error("null body array"); return B200SPH_EINVAL; }
+	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) { ctx->h_bodies->cgGridPos[b][a] = g[3 * b + a]; ctx->h_bodies->cgPos[b][a] = c[3 * b + a]; }
+	return push_bodies(ctx);
+}
+extern "C" int b200sph_set_rbstart(b200sph_ctx *ctx, const int *first, int n)
+{
+	CHECK_BODIES(n, first);
+	for (int b = 0; b < n; ++b) ctx->h_bodies->startIndex[b] = first[b];
+	return push_bodies(ctx);
+}
+extern "C" int b200sph_set_rbtrans(b200sph_ctx *ctx, const float *t, int n)
+{
+	CHECK_BODIES(n, t);
+	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) ctx->h_bodies->trans[b][a] = t[3 * b + a];
+	return push_bodies(ctx);
+}
+extern "C" int b200sph_set_rbsteprot(b200sph_ctx *ctx, const float *r, int n)
+{
+	CHECK_BODIES(n, r);
+	for (int b = 0; b < n; ++b) for (int a = 0; a < 9; ++a) ctx->h_bodies->steprot[b][a] = r[9 * b + a];
+	return push_bodies(ctx);
+}
+extern "C" int b200sph_set_rblinearvel(b200sph_ctx *ctx, const float *v, int n)
+{
+	CHECK_BODIES(n, v);
+	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) ctx->h_bodies->linearvel[b][a] = v[3 * b + a];
+	return push_bodies(ctx);
+}
+extern "C" int b200sph_set_rbangularvel(b200sph_ctx *ctx, const float *v, int n)
+{
+	CHECK_BODIES(n, v);
+	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) ctx->h_bodies->angularvel[b][a] = v[3 * b + a];
+	return push_bodies(ctx);
+}

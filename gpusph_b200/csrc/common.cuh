@@ -25,6 +25,8 @@ typedef unsigned short ushort;
 #define PT_VERTEX 2
 #define PT_TESTPOINT 3
 
+__host__ __device__ static inline int object_of_y(unsigned short y) { return y & 0xFFF; }   // src/particleinfo.h:403-410
+
 // block sizes; forces uses 128 so that the CFL array has exactly the layout the
 // reference's getFmaxElements() sizes it for (src/cuda/forces.cu:56-68,540-544)
 #define BLOCK_STREAM 256
@@ -75,6 +77,18 @@ struct NeibsCounters {     // mirrors the reference's device counters, src/cuda/
 	int pad;
 };
 
+// moving / force-feedback bodies: device copy of what the reference keeps in __constant__ arrays
+// (src/cuda/forces_kernel.cu:81-83, src/cuda/euler_kernel.cu:45-50)
+struct BodyData {
+	int cgGridPos[B200SPH_MAX_BODIES][3];
+	float cgPos[B200SPH_MAX_BODIES][3];
+	int startIndex[B200SPH_MAX_BODIES];
+	float trans[B200SPH_MAX_BODIES][3];
+	float steprot[B200SPH_MAX_BODIES][9];
+	float linearvel[B200SPH_MAX_BODIES][3];
+	float angularvel[B200SPH_MAX_BODIES][3];
+};
+
 // device-resident time-stepping record (b200sph_step_* entry points)
 struct StepState {
 	double t;
@@ -103,6 +117,7 @@ struct b200sph_ctx {
 	float *h_scalar;                        // pinned host scalar
 	int *d_flag; int *h_flag;
 	StepState *d_step; StepState *h_step;
+	BodyData *d_bodies; BodyData *h_bodies; int have_bodies;
 };
 
 // ---- error plumbing ----

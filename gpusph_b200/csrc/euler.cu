@@ -6,9 +6,9 @@
 template<int STEP>
 __global__ void __launch_bounds__(BLOCK_STREAM)
 euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ oldPos, const float4 *__restrict__ oldVel,
-	const ushort4 *__restrict__ infoArray, const float4 *__restrict__ forces,
+	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash, const float4 *__restrict__ forces,
 	float4 *__restrict__ newPos, float4 *__restrict__ newVel, const uint numParticles, const float dt_arg,
-	const StepState *__restrict__ dev_state)
+	const StepState *__restrict__ dev_state, const BodyData *__restrict__ bodies)
 {
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
 	if (index >= numParticles) return;
@@ -32,7 +32,27 @@ euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ old
 			pos.x += vcx * dt; pos.y += vcy * dt; pos.z += vcz * dt;
 			vel.w += dt * force.w;
 			vel.x += dt * force.x; vel.y += dt * force.y; vel.z += dt * force.z;
-		} else if (type == PT_BOUNDARY || type == PT_VERTEX) {     // :468-512 (moving bodies: SURVEY section 8 row f1)
+		} else if (type == PT_BOUNDARY || type == PT_VERTEX) {     // :468-512
+			// particles of a moving / floating body follow the rigid motion of the body (:470-503)
+			if ((info.x & B200SPH_FG_MOVING_BOUNDARY) && bodies) {
+				const int obj = object_of_y(info.y);
+				const int3 gp = grid_pos(P, particleHash[index] & CELLTYPE_BITMASK);
+				// relPos = x - x_cg (globalDistance, cellgrid.cuh:152-160)
+				const float rx = (float)(gp.x - bodies->cgGridPos[obj][0]) * P.cellSize[0] + (pos.x - bodies->cgPos[obj][0]);
+				const float ry = (float)(gp.y - bodies->cgGridPos[obj][1]) * P.cellSize[1] + (pos.y - bodies->cgPos[obj][1]);
+				const float rz = (float)(gp.z - bodies->cgGridPos[obj][2]) * P.cellSize[2] + (pos.z - bodies->cgPos[obj][2]);
+				const float *rot = bodies->steprot[obj];
+				// applyrot, euler_kernel.cu:67-74
+				pos.x += (rot[0] - 1.0f) * rx + rot[1] * ry + rot[2] * rz;
+				pos.y += rot[3] * rx + (rot[4] - 1.0f) * ry + rot[5] * rz;
+				pos.z += rot[6] * rx + rot[7] * ry + (rot[8] - 1.0f) * rz;
+				pos.x += bodies->trans[obj][0]; pos.y += bodies->trans[obj][1]; pos.z += bodies->trans[obj][2];
+				// V(P) = V(Cg) + omega x PCg
+				const float *w = bodies->angularvel[obj], *lv = bodies->linearvel[obj];
+				vel.x = lv[0] + (w[1] * rz - w[2] * ry);
+				vel.y = lv[1] + (w[2] * rx - w[0] * rz);
+				vel.z = lv[2] + (w[0] * ry - w[1] * rx);
+			}
 			if (P.boundarytype == B200SPH_DYN_BOUNDARY) vel.w += dt * force.w;
 		}
 	}
@@ -45,8 +65,8 @@ extern "C" int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *
 	uint32_t num_particles, uint32_t particle_range_end, float dt, int step)
 {
 	CHECK_CTX(ctx);
-	(void)hash;
 	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }   // euler.cu:361-362
+	const BodyData *bodies = (ctx->have_bodies && hash) ? ctx->d_bodies : NULL;
 	if (particle_range_end == 0) return B200SPH_OK;
 	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
 	const uint nb = div_up(particle_range_end, BLOCK_STREAM);
@@ -54,10 +74,10 @@ extern "C" int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *
 	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
 	if (step == 1)
 		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL);
+			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL, bodies);
 	else
 		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL);
+			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL, bodies);
 	KERNEL_TRY();
 	return B200SPH_OK;
 }
@@ -67,18 +87,18 @@ extern "C" int b200sph_euler_async(b200sph_ctx *ctx, const void *old_pos, const 
 	uint32_t num_particles, uint32_t particle_range_end, int step)
 {
 	CHECK_CTX(ctx);
-	(void)hash;
 	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }
+	const BodyData *bodies = (ctx->have_bodies && hash) ? ctx->d_bodies : NULL;
 	if (particle_range_end == 0) return B200SPH_OK;
 	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
 	const uint nb = div_up(particle_range_end, BLOCK_STREAM);
 	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
 	if (step == 1)
 		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step);
+			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step, bodies);
 	else
 		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step);
+			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step, bodies);
 	KERNEL_TRY();
 	return B200SPH_OK;
 }

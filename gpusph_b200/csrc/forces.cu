@@ -21,6 +21,7 @@
 // are combined as (0 + sum_fluid) + sum_boundary like the reference's RMW sequence.
 #include "pair_physics.cuh"
 #include <stdlib.h>
+#include <cub/device/device_scan.cuh>
 
 // list rows kept in flight by the gather kernel: measured on B200 at 2 M particles (dambreak2m / lattice2m):
 // 1 row 0.585 / 0.769 ms, 2 rows 0.535 / 0.805 ms, 4 rows 0.651 / 0.808 ms
@@ -149,7 +150,8 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int BASE_STRIDE, int PF, typename Fetch>
 __device__ __forceinline__ float
 particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
-	const float4 pos, const float4 vel, const float4 e, const uint *s_base, const float4 *s_off,
+	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo,
+	const uint *s_base, const float4 *s_off,
 	const ushort *__restrict__ neibsList, Fetch fetch, float4 *__restrict__ forces)
 {
 	Central c;
@@ -167,7 +169,7 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
 		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
 	}
-	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, acc);
+	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, cellHash, bo, acc);
 	forces[index] = acc;
 	return cfl_term;
 }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(BLOCK_FORCES)
 forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
-	float4 *__restrict__ forces, float *__restrict__ cfl,
+	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
 	const uint fromParticle, const uint toParticle, const uint cflOffset)
 {
 	__shared__ uint s_cellbase[27 * BLOCK_FORCES];
@@ -197,7 +199,8 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 		if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000)) {
 			const PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
 			uint *my_base = s_cellbase + threadIdx.x;
-			load_cell_starts(P, (int)(particleHash[index] & CELLTYPE_BITMASK), cellStart, my_base, BLOCK_FORCES);
+			const uint cellHash = particleHash[index] & CELLTYPE_BITMASK;
+			load_cell_starts(P, (int)cellHash, cellStart, my_base, BLOCK_FORCES);
 			// two gathers per pair straight from the reference's own pos / vel buffers; EOS terms from rho~ on the fly
 			auto fetch = [&](const uint j, float4 &np, float4 &nv, float4 &ne) {
 				np = __ldg(posArray + j); nv = __ldg(velArray + j);
@@ -205,7 +208,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 			};
 			const float4 vel = velArray[index];
 			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BLOCK_FORCES, GATHER_PF>(P, k, index, info, type, pos,
-				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), my_base, s_celloff, neibsList, fetch, forces);
+				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, my_base, s_celloff, neibsList, fetch, forces);
 		}
 	}
 
@@ -265,7 +268,7 @@ forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__
 	const float4 *__restrict__ posArray, const float4 *__restrict__ velArray, const float4 *__restrict__ aux,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
-	float4 *__restrict__ forces, float *__restrict__ cfl,
+	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
 	const uint fromParticle, const uint toParticle, const uint cflOffset)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -326,7 +329,8 @@ forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__
 		const float4 e = aux[index];
 		// shared-memory slot of the first particle of each of the 27 neighbouring cells (while the copies fly)
 		uint *my_base = S.cellbase + tid;
-		load_cell_starts(P, (int)(particleHash[index] & CELLTYPE_BITMASK), cellStart, my_base, TP);
+		const uint cellHash = particleHash[index] & CELLTYPE_BITMASK;
+		load_cell_starts(P, (int)cellHash, cellStart, my_base, TP);
 #pragma unroll
 		for (int cell = 0; cell < 27; ++cell) {
 			const int r = S.rowof[cell];
@@ -335,7 +339,7 @@ forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__
 		}
 		if (!staged) { while (!mbar_try_wait(bar, 0)) { } staged = true; }
 		const float t = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, TP, PF>(P, k, index, info, type, pos, vel, e,
-			my_base, S.celloff, neibsList, fetch, forces);
+			cellHash, bo, my_base, S.celloff, neibsList, fetch, forces);
 		cfl_term = fmaxf(cfl_term, t);
 		cfl_slot = (index - fromParticle) / BLOCK_FORCES;
 	}
@@ -352,9 +356,9 @@ forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__
 // launcher
 // ---------------------------------------------------------------------------
 typedef void (*gather_kernel_t)(const DevParams, const float4 *, const float4 *, const ushort4 *, const uint *,
-	const uint *, const ushort *, float4 *, float *, const uint, const uint, const uint);
+	const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
 typedef void (*tile_kernel_t)(const DevParams, const Tile *, const float4 *, const float4 *, const float4 *, const ushort4 *,
-	const uint *, const uint *, const ushort *, float4 *, float *, const uint, const uint, const uint);
+	const uint *, const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
 
 template<int RHODIFF>
 static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather_kernel_t *g, tile_kernel_t *t, size_t *smem)
@@ -378,7 +382,23 @@ extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel
 	void *forces, float *cfl, uint32_t num_particles, uint32_t from, uint32_t to,
 	uint32_t cfl_offset, uint32_t *num_cfl_blocks)
 {
+	return b200sph_forces_bodies(ctx, pos, vel, info, hash, cell_start, neibs_list, forces, cfl, NULL, NULL,
+		num_particles, from, to, cfl_offset, num_cfl_blocks);
+}
+
+extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const void *vel, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	void *forces, float *cfl, void *rb_forces, void *rb_torques, uint32_t num_particles, uint32_t from, uint32_t to,
+	uint32_t cfl_offset, uint32_t *num_cfl_blocks)
+{
 	CHECK_CTX(ctx);
+	BodyOut bo;
+	bo.bodies = NULL; bo.rb_forces = (float4 *)rb_forces; bo.rb_torques = (float4 *)rb_torques;
+	if (rb_forces) {
+		if (!rb_torques) { b200_set_error("forces: rb_forces without rb_torques"); return B200SPH_EINVAL; }
+		if (!ctx->have_bodies) { b200_set_error("forces: body output requested before setrbcg/setrbstart"); return B200SPH_EINVAL; }
+		bo.bodies = ctx->d_bodies;
+	}
 	if (num_cfl_blocks) *num_cfl_blocks = 0;
 	if (to <= from) return B200SPH_OK;
 	if (!pos || !vel || !info || !hash || !cell_start || !neibs_list || !forces) { b200_set_error("forces: null buffer"); return B200SPH_EINVAL; }
@@ -410,17 +430,56 @@ extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel
 		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		tk<<<ctx->num_tiles, ctx->tile_p, smem, ctx->stream>>>(ctx->dp, ctx->tiles, (const float4 *)pos, (const float4 *)vel, ctx->aux,
-			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
+			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
 	} else {
 		// The kernel wants ~9 resident CTAs x 15 KB of shared memory per SM. Say so explicitly: a host application may
 		// have set a device-wide cache preference (GPUSPH sets cudaFuncCachePreferL1, src/cuda/cudautil.cc:71-79),
 		// which would otherwise shrink the carve-out and cut the occupancy of this kernel by 5x.
 		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, 66));
 		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel,
-			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, from, to, cfl_offset);
+			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
 	}
 	KERNEL_TRY();
 	if (num_cfl_blocks) *num_cfl_blocks = nblocks;
+	return B200SPH_OK;
+}
+
+// ---------------------------------------------------------------------------
+// reduceRbForces — reference src/cuda/forces.cu:967-1003 (thrust::inclusive_scan_by_key in place, then the last
+// element of every body's segment is read back)
+// ---------------------------------------------------------------------------
+struct Float4Plus { __host__ __device__ float4 operator()(const float4 &a, const float4 &b) const
+	{ return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); } };
+
+extern "C" int b200sph_reduce_rb_forces(b200sph_ctx *ctx, void *rb_forces, void *rb_torques, const uint32_t *rb_keys,
+	const uint32_t *lastindex, float *total_force, float *total_torque, uint32_t nb, uint32_t np)
+{
+	CHECK_CTX(ctx);
+	if (nb == 0 || np == 0) return B200SPH_OK;
+	if (!rb_forces || !rb_torques || !rb_keys || !lastindex || !total_force || !total_torque) { b200_set_error("reduceRbForces: null buffer"); return B200SPH_EINVAL; }
+	if (nb > B200SPH_MAX_BODIES) { b200_set_error("reduceRbForces: too many bodies"); return B200SPH_EINVAL; }
+	float4 *arrays[2] = { (float4 *)rb_forces, (float4 *)rb_torques };
+	for (int a = 0; a < 2; ++a) {
+		size_t tmp = 0;
+		CUDA_TRY(cub::DeviceScan::InclusiveScanByKey(NULL, tmp, rb_keys, arrays[a], arrays[a], Float4Plus(), (int)np, cub::Equality(), ctx->stream));
+		if (ctx->sort_tmp_bytes < tmp) {
+			cudaFree(ctx->sort_tmp); ctx->sort_tmp = NULL; ctx->sort_tmp_bytes = 0;
+			CUDA_TRY(cudaMalloc(&ctx->sort_tmp, tmp));
+			ctx->sort_tmp_bytes = tmp;
+		}
+		tmp = ctx->sort_tmp_bytes;
+		CUDA_TRY(cub::DeviceScan::InclusiveScanByKey(ctx->sort_tmp, tmp, rb_keys, arrays[a], arrays[a], Float4Plus(), (int)np, cub::Equality(), ctx->stream));
+	}
+	float4 host[2 * B200SPH_MAX_BODIES];
+	for (uint32_t b = 0; b < nb; ++b) {
+		CUDA_TRY(cudaMemcpyAsync(&host[2 * b], arrays[0] + lastindex[b], sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaMemcpyAsync(&host[2 * b + 1], arrays[1] + lastindex[b], sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	for (uint32_t b = 0; b < nb; ++b) {
+		total_force[3 * b] = host[2 * b].x; total_force[3 * b + 1] = host[2 * b].y; total_force[3 * b + 2] = host[2 * b].z;
+		total_torque[3 * b] = host[2 * b + 1].x; total_torque[3 * b + 1] = host[2 * b + 1].y; total_torque[3 * b + 2] = host[2 * b + 1].z;
+	}
 	return B200SPH_OK;
 }
 

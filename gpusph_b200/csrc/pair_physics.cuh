@@ -160,14 +160,34 @@ pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, cons
 }
 
 // finalizeforcesDevice :4037-4153: 1/rho0 on the continuity term (forces_fixup :3212-3219), gravity on fluid
-// particles (:4091), CFL term max(|a|, c^2/h) (dyndt_forces_shared_data::store :3436-3456)
-__device__ __forceinline__ float finalize_particle(const DevParams &P, const int type, const int fnum, const float sspeed, float4 &acc)
+// particles (:4091), CFL term max(|a|, c^2/h) (dyndt_forces_shared_data::store :3436-3456); for particles of a
+// force-feedback body (FG_COMPUTE_FORCE) the acceleration is turned into a force (x mass) and, with its torque
+// about the body's centre of gravity, scattered to the body buffers (:4116-4141).
+struct BodyOut {
+	const BodyData *bodies;     // NULL: no body output requested
+	float4 *rb_forces, *rb_torques;
+};
+
+__device__ __forceinline__ float finalize_particle(const DevParams &P, const int type, const int fnum, const float sspeed,
+	const ushort4 info, const float4 pos, const uint cellHash, const BodyOut &bo, float4 &acc)
 {
 	acc.w /= P.rho0[fnum];
 	float cfl_term = 0.0f;
 	if (type == PT_FLUID) {
 		acc.x += P.gravity[0]; acc.y += P.gravity[1]; acc.z += P.gravity[2];
 		cfl_term = fmaxf(sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z), sspeed * sspeed / P.slength);
+	}
+	if (bo.bodies && (info.x & B200SPH_FG_COMPUTE_FORCE) && type != PT_VERTEX) {
+		const int obj = object_of_y(info.y);
+		acc.x *= pos.w; acc.y *= pos.w; acc.z *= pos.w;               // :4130-4131 (the stored force is scaled too)
+		const uint rbindex = id_of(info) + (uint)bo.bodies->startIndex[obj];   // rb_particle_data :520-528
+		bo.rb_forces[rbindex] = acc;
+		// arm = globalDistance(gridPos, pos, cg cell, cg in-cell pos), cellgrid.cuh:152-160
+		const int3 gp = grid_pos(P, cellHash);
+		const float ax = (float)(gp.x - bo.bodies->cgGridPos[obj][0]) * P.cellSize[0] + (pos.x - bo.bodies->cgPos[obj][0]);
+		const float ay = (float)(gp.y - bo.bodies->cgGridPos[obj][1]) * P.cellSize[1] + (pos.y - bo.bodies->cgPos[obj][1]);
+		const float az = (float)(gp.z - bo.bodies->cgGridPos[obj][2]) * P.cellSize[2] + (pos.z - bo.bodies->cgPos[obj][2]);
+		bo.rb_torques[rbindex] = make_float4(ay * acc.z - az * acc.y, az * acc.x - ax * acc.z, ax * acc.y - ay * acc.x, 0.0f);
 	}
 	return cfl_term;
 }

@@ -36,6 +36,9 @@ BUFFER_FORCES = "BUFFER_FORCES"
 BUFFER_CFL = "BUFFER_CFL"
 BUFFER_CFL_TEMP = "BUFFER_CFL_TEMP"
 BUFFER_COMPACT_DEV_MAP = "BUFFER_COMPACT_DEV_MAP"
+BUFFER_RB_FORCES = "BUFFER_RB_FORCES"
+BUFFER_RB_TORQUES = "BUFFER_RB_TORQUES"
+BUFFER_RB_KEYS = "BUFFER_RB_KEYS"
 
 
 class BufferList(dict):
@@ -174,14 +177,45 @@ class ForcesEngine:
         return int(self.lib.b200sph_round_particles(n))
 
     def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, fromParticle: int,
-                  toParticle: int, cflOffset: int = 0) -> int:
+                  toParticle: int, cflOffset: int = 0, compute_object_forces: bool = False) -> int:
         nblocks = C.c_uint32()
-        capi.check(self.lib.b200sph_forces(
+        capi.check(self.lib.b200sph_forces_bodies(
             self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
             bufread.ptr(BUFFER_HASH), bufread.ptr(BUFFER_CELLSTART), bufread.ptr(BUFFER_NEIBSLIST),
             bufwrite.ptr(BUFFER_FORCES), bufwrite.ptr(BUFFER_CFL, False),
+            bufwrite.ptr(BUFFER_RB_FORCES) if compute_object_forces else 0,
+            bufwrite.ptr(BUFFER_RB_TORQUES) if compute_object_forces else 0,
             numParticles, fromParticle, toParticle, cflOffset, C.byref(nblocks)))
         return nblocks.value
+
+    # ---- moving / force-feedback bodies (src/engine_forces.h:62-74) ----
+    @staticmethod
+    def _farr(a, n, k):
+        import numpy as np
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(n, k))
+        return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def setrbcg(self, cgGridPos, cgPos, numbodies: int) -> None:
+        import numpy as np
+        g = np.ascontiguousarray(np.asarray(cgGridPos, dtype=np.int32).reshape(numbodies, 3))
+        c, cp = ForcesEngine._farr(cgPos, numbodies, 3)
+        capi.check(self.lib.b200sph_set_rbcg(self.ctx.handle, g.ctypes.data_as(C.POINTER(C.c_int)), cp, numbodies))
+
+    def setrbstart(self, rbfirstindex, numbodies: int) -> None:
+        import numpy as np
+        f = np.ascontiguousarray(np.asarray(rbfirstindex, dtype=np.int32))
+        capi.check(self.lib.b200sph_set_rbstart(self.ctx.handle, f.ctypes.data_as(C.POINTER(C.c_int)), numbodies))
+
+    def reduceRbForces(self, bufwrite: BufferList, lastindex, numbodies: int, numBodiesParticles: int):
+        import numpy as np
+        li = np.ascontiguousarray(np.asarray(lastindex, dtype=np.uint32))
+        tf = np.zeros((numbodies, 3), dtype=np.float32)
+        tt = np.zeros((numbodies, 3), dtype=np.float32)
+        capi.check(self.lib.b200sph_reduce_rb_forces(
+            self.ctx.handle, bufwrite.ptr(BUFFER_RB_FORCES), bufwrite.ptr(BUFFER_RB_TORQUES), bufwrite.ptr(BUFFER_RB_KEYS),
+            li.ctypes.data_as(C.POINTER(C.c_uint32)), tf.ctypes.data_as(C.POINTER(C.c_float)),
+            tt.ctypes.data_as(C.POINTER(C.c_float)), numbodies, numBodiesParticles))
+        return tf, tt
 
     def eos_probe(self, bufread: BufferList, out: torch.Tensor, numParticles: int) -> None:
         """Diagnostic: per-particle {P/rho^2, sound speed} as the forces kernel evaluates them."""
@@ -234,6 +268,26 @@ class IntegrationEngine:
             bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES),
             bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, dt, step))
 
+
+    # ---- moving bodies (src/engine_integration.h:54-68) ----
+    def setrbcg(self, cgGridPos, cgPos, numbodies: int) -> None:
+        ForcesEngine.setrbcg(self, cgGridPos, cgPos, numbodies)
+
+    def _setf(self, fn, a, numbodies, k):
+        arr, ptr = ForcesEngine._farr(a, numbodies, k)
+        capi.check(fn(self.ctx.handle, ptr, numbodies))
+
+    def setrbtrans(self, trans, numbodies: int) -> None:
+        self._setf(self.lib.b200sph_set_rbtrans, trans, numbodies, 3)
+
+    def setrbsteprot(self, rot, numbodies: int) -> None:
+        self._setf(self.lib.b200sph_set_rbsteprot, rot, numbodies, 9)
+
+    def setrblinearvel(self, v, numbodies: int) -> None:
+        self._setf(self.lib.b200sph_set_rblinearvel, v, numbodies, 3)
+
+    def setrbangularvel(self, v, numbodies: int) -> None:
+        self._setf(self.lib.b200sph_set_rbangularvel, v, numbodies, 3)
 
     def basicstep_async(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
                         step: int) -> None:

@@ -240,9 +240,20 @@ public:
 	void setplanes(PlaneList const& planes) override { if (!planes.empty()) unsupported("geometric planes (ENABLE_PLANES)"); }
 	void setgravity(float3 const& g) override
 	{ if (m_ref) m_ref->setgravity(g); const float v[3] = { g.x, g.y, g.z }; check(b200sph_set_gravity(m_c->get(), v)); }
-	void setrbcg(const int3*, const float3*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
-	void setrbstart(const int*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
-	void reduceRbForces(BufferList&, uint*, float3*, float3*, uint numbodies, uint) override { if (numbodies) unsupported("rigid bodies"); }
+	// moving / force-feedback bodies (src/cuda/forces.cu:430-447, 967-1003)
+	void setrbcg(const int3* cgGridPos, const float3* cgPos, int numbodies) override
+	{ if (m_ref) m_ref->setrbcg(cgGridPos, cgPos, numbodies);
+	  check(b200sph_set_rbcg(m_c->get(), (const int*)cgGridPos, (const float*)cgPos, numbodies)); }
+	void setrbstart(const int* rbfirstindex, int numbodies) override
+	{ if (m_ref) m_ref->setrbstart(rbfirstindex, numbodies);
+	  check(b200sph_set_rbstart(m_c->get(), rbfirstindex, numbodies)); }
+	void reduceRbForces(BufferList& bufwrite, uint *lastindex, float3 *totalforce, float3 *totaltorque,
+		uint numforcesbodies, uint numForcesBodiesParticles) override
+	{
+		check(b200sph_reduce_rb_forces(m_c->get(), bufwrite.getData<BUFFER_RB_FORCES>(), bufwrite.getData<BUFFER_RB_TORQUES>(),
+			bufwrite.getConstData<BUFFER_RB_KEYS>(), lastindex, (float*)totalforce, (float*)totaltorque,
+			numforcesbodies, numForcesBodiesParticles));
+	}
 
 	// no texture references on this architecture: neighbours are gathered through the read-only path directly
 	void bind_textures(const BufferList&, uint, RunMode) override {}
@@ -262,12 +273,15 @@ public:
 		const bool compute_object_forces) override
 	{
 		if (run_mode == REPACK) unsupported("repacking");
-		if (compute_object_forces) unsupported("rigid-body force feedback");
 		uint32_t nblocks = 0;
-		check(b200sph_forces(m_c->get(), bufread.getData<BUFFER_POS>(), bufread.getData<BUFFER_VEL>(),
+		// the reference's finalize kernel scatters body forces whenever the particle carries FG_COMPUTE_FORCE
+		// (forces_kernel.def:4116-4141); the RB buffers exist exactly when there are force-feedback bodies
+		float4 *rbf = bufwrite.getData<BUFFER_RB_FORCES>(), *rbt = bufwrite.getData<BUFFER_RB_TORQUES>();
+		(void)compute_object_forces;
+		check(b200sph_forces_bodies(m_c->get(), bufread.getData<BUFFER_POS>(), bufread.getData<BUFFER_VEL>(),
 			bufread.getData<BUFFER_INFO>(), bufread.getData<BUFFER_HASH>(), bufread.getData<BUFFER_CELLSTART>(),
 			bufread.getData<BUFFER_NEIBSLIST>(), bufwrite.getData<BUFFER_FORCES>(), bufwrite.getData<BUFFER_CFL>(),
-			numParticles, fromParticle, toParticle, cflOffset, &nblocks));
+			rbf, rbt, numParticles, fromParticle, toParticle, cflOffset, &nblocks));
 		return nblocks;
 	}
 
@@ -296,11 +310,17 @@ public:
 	{ if (m_ref) m_ref->setconstants(pp, o, g, c, a, n, h); }
 	void getconstants(PhysParams *pp) override { if (m_ref) m_ref->getconstants(pp); }
 
-	void setrbcg(const int3*, const float3*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
-	void setrbtrans(const float3*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
-	void setrbsteprot(const float*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
-	void setrblinearvel(const float3*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
-	void setrbangularvel(const float3*, int numbodies) override { if (numbodies) unsupported("rigid bodies"); }
+	// moving bodies (src/cuda/euler.cu:76-95)
+	void setrbcg(const int3* g, const float3* c, int n) override
+	{ if (m_ref) m_ref->setrbcg(g, c, n); check(b200sph_set_rbcg(m_c->get(), (const int*)g, (const float*)c, n)); }
+	void setrbtrans(const float3* t, int n) override
+	{ if (m_ref) m_ref->setrbtrans(t, n); check(b200sph_set_rbtrans(m_c->get(), (const float*)t, n)); }
+	void setrbsteprot(const float* r, int n) override
+	{ if (m_ref) m_ref->setrbsteprot(r, n); check(b200sph_set_rbsteprot(m_c->get(), r, n)); }
+	void setrblinearvel(const float3* v, int n) override
+	{ if (m_ref) m_ref->setrblinearvel(v, n); check(b200sph_set_rblinearvel(m_c->get(), (const float*)v, n)); }
+	void setrbangularvel(const float3* v, int n) override
+	{ if (m_ref) m_ref->setrbangularvel(v, n); check(b200sph_set_rbangularvel(m_c->get(), (const float*)v, n)); }
 
 	void density_sum(const BufferList&, BufferList&, const uint, const uint, const float, const int, const float,
 		const float, const float, const float, const float) override { unsupported("density summation (SA)"); }

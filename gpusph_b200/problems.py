@@ -191,7 +191,7 @@ def _box_shell(lo, hi, dp, layers):
 
 
 def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_COLAGROSSI, layers: int = 3,
-                     alloc_extra: float = 0.0, width_scale: int = 1, **kw):
+                     alloc_extra: float = 0.0, width_scale: int = 1, obstacle: bool = False, **kw):
     """DamBreak3D-like setup (src/problems/DamBreak3D.cu:36-205 with --num_obstacles 0): a 1.6 x 0.67 x 0.6 m
     tank lined with `layers` layers of DYN boundary particles, a 0.4 m long, 0.4 m high water column,
     Wendland kernel, artificial viscosity, c0 = 20, gamma = 7. Fill order/ids are ours, not the reference's
@@ -208,12 +208,21 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
     I, J, K = np.meshgrid(np.arange(nf[0] + 1), np.arange(nf[1] + 1), np.arange(nf[2] + 1), indexing="ij")
     fluid = lo + np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * (ext / nf)
     nfl, nb = fluid.shape[0], wall.shape[0]
-    N = nfl + nb
+    body = np.zeros((0, 3))
+    if obstacle:
+        # the force-feedback obstacle of DamBreak3D (src/problems/DamBreak3D.cu:169-180): a 0.12 x 0.12 x 0.6 column
+        # lined with DYN boundary particles, flagged FG_MOVING_BOUNDARY | FG_COMPUTE_FORCE, object number 1
+        # (axis-aligned here; the reference rotates it by 45 degrees)
+        side = 0.12
+        blo = np.array([0.9 - side / 2, dim[1] / 2 - side / 2, bd])
+        body = _box_shell(blo, blo + np.array([side, side, dim[2] - 2 * bd]), dp, min(layers, 2))
+    nob = body.shape[0]
+    N = nfl + nb + nob
     rho0 = 1000.0
     c0 = 20.0
     params = make_params(origin=np.zeros(3), size=dim, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
                          rho0=rho0, c0=c0, densitydiffusion=densitydiffusion, **kw)
-    gpos = np.concatenate([fluid, wall], axis=0)
+    gpos = np.concatenate([fluid, wall, body], axis=0)
     mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
     pos, hashv = localpos_and_hash(params, gpos, mass)
     vel = np.zeros((N, 4), dtype=np.float32)
@@ -226,7 +235,9 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
     dens = np.where(in_column, np.power(1.0 + rho0 * 9.81 * depth / B, 1.0 / gam) - 1.0, 0.0)
     vel[:, 3] = dens.astype(np.float32)
     info = np.concatenate([make_info(capi.PT_FLUID, ids=np.arange(nfl)),
-                           make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, N))], axis=0)
+                           make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, nfl + nb)),
+                           make_info(capi.PT_BOUNDARY, flags=capi.FG_MOVING_BOUNDARY | capi.FG_COMPUTE_FORCE, obj=1,
+                                     ids=np.arange(nfl + nb, N))], axis=0)
     return params, ParticleArrays(pos, vel, info, hashv)
 
 

@@ -240,6 +240,36 @@ int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl,
 int b200sph_cflmax(b200sph_ctx *ctx, const float *cfl, uint32_t num_blocks, float *max_out);
 int b200sph_dt_from_cfl(const b200sph_ctx *ctx, float max_cfl, float *dt_out);
 
+/* ---- moving / force-feedback bodies ------------
+ * AbstractForcesEngine::setrbcg / setrbstart (src/engine_forces.h:62-66; src/cuda/forces.cu:430-447) and
+ * AbstractIntegrationEngine::setrbcg / setrbtrans / setrbsteprot / setrblinearvel / setrbangularvel
+ * (src/engine_integration.h:54-68; src/cuda/euler.cu:76-95). Host arrays, at most B200SPH_MAX_BODIES bodies.
+ * cg_grid_pos: int[3*n] cell of each centre of gravity, cg_pos: float[3*n] in-cell coordinate. */
+#define B200SPH_MAX_BODIES 16
+int b200sph_set_rbcg(b200sph_ctx *ctx, const int *cg_grid_pos, const float *cg_pos, int numbodies);
+int b200sph_set_rbstart(b200sph_ctx *ctx, const int *rbfirstindex, int numbodies);
+int b200sph_set_rbtrans(b200sph_ctx *ctx, const float *trans, int numbodies);
+int b200sph_set_rbsteprot(b200sph_ctx *ctx, const float *rot /* 9 per body */, int numbodies);
+int b200sph_set_rblinearvel(b200sph_ctx *ctx, const float *linearvel, int numbodies);
+int b200sph_set_rbangularvel(b200sph_ctx *ctx, const float *angularvel, int numbodies);
+
+/* b200sph_forces with compute_object_forces = true (src/engine_forces.h:133-149): additionally scatters, for every
+ * particle flagged FG_COMPUTE_FORCE, force x mass and the torque about its body's centre of gravity into
+ * rb_forces / rb_torques (float4[num body particles], index = id + rbfirstindex[object]) exactly like
+ * finalizeforcesDevice (src/cuda/forces_kernel.def:4116-4141). rb_forces == NULL: same as b200sph_forces. */
+int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const void *vel, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	void *forces, float *cfl, void *rb_forces, void *rb_torques,
+	uint32_t num_particles, uint32_t from_particle, uint32_t to_particle,
+	uint32_t cfl_offset, uint32_t *num_cfl_blocks);
+
+/* AbstractForcesEngine::reduceRbForces (src/engine_forces.h:68-74; src/cuda/forces.cu:967-1003): in-place segmented
+ * inclusive scan of rb_forces / rb_torques keyed by rb_keys, then the last element of each body's segment
+ * (lastindex[b], host array) is copied to total_force / total_torque (host float[3*numbodies]). Synchronises. */
+int b200sph_reduce_rb_forces(b200sph_ctx *ctx, void *rb_forces, void *rb_torques, const uint32_t *rb_keys,
+	const uint32_t *lastindex, float *total_force, float *total_torque,
+	uint32_t numforcesbodies, uint32_t num_forces_bodies_particles);
+
 /* ---- integration engine -------------------------------------------------- */
 
 /* AbstractIntegrationEngine::basicstep (src/engine_integration.h:117; src/cuda/euler.cu:330-372;

@@ -508,13 +508,26 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 	}
 }
 
+/* moving / force-feedback bodies: host mirror of the reference's __constant__ arrays
+ * (src/cuda/forces_kernel.cu:81-83, src/cuda/euler_kernel.cu:45-50) */
+typedef struct {
+	int cgGridPos[B200SPH_MAX_BODIES][3];
+	float cgPos[B200SPH_MAX_BODIES][3];
+	int startIndex[B200SPH_MAX_BODIES];
+	float trans[B200SPH_MAX_BODIES][3];
+	float steprot[B200SPH_MAX_BODIES][9];
+	float linearvel[B200SPH_MAX_BODIES][3];
+	float angularvel[B200SPH_MAX_BODIES][3];
+} oracle_bodies;
+
 /* forces + finalize. Returns the number of CFL blocks written, like
  * CUDAForcesEngine::basicstep (src/cuda/forces.cu:901-932). forces must be zeroed by the caller. */
 uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, const us4 *info,
 	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
 	const float *eos_p_in, const float *eos_c_in,
 	f4 *forces, float *cfl, f4 *abssum,
-	uint32_t num_particles, uint32_t from, uint32_t to, uint32_t cfl_offset)
+	uint32_t num_particles, uint32_t from, uint32_t to, uint32_t cfl_offset,
+	const oracle_bodies *bodies, f4 *rb_forces, f4 *rb_torques)
 {
 	float *pprec = (float *)malloc(sizeof(float) * (num_particles ? num_particles : 1));
 	float *ssp = (float *)malloc(sizeof(float) * (num_particles ? num_particles : 1));
@@ -556,6 +569,19 @@ uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, co
 				const float v = fmaxf(sqrtf(fo.x * fo.x + fo.y * fo.y + fo.z * fo.z), c * c / P->slength);
 				if (v > m) m = v;
 			}
+			/* force-feedback bodies: :4116-4141 (force x mass, torque about the centre of gravity) */
+			if (bodies && rb_forces && compute_force(inf) && ptype(inf) != B200SPH_PT_VERTEX) {
+				const int obj = inf.y & 0xFFF;
+				fo.x *= p.w; fo.y *= p.w; fo.z *= p.w;
+				const uint32_t rbindex = pid(inf) + (uint32_t)bodies->startIndex[obj];
+				rb_forces[rbindex] = fo;
+				const i3 gp = grid_pos_from_hash(P, hash[index] & CELLTYPE_BITMASK);
+				const float ax = (float)(gp.x - bodies->cgGridPos[obj][0]) * P->cell_size[0] + (p.x - bodies->cgPos[obj][0]);
+				const float ay = (float)(gp.y - bodies->cgGridPos[obj][1]) * P->cell_size[1] + (p.y - bodies->cgPos[obj][1]);
+				const float az = (float)(gp.z - bodies->cgGridPos[obj][2]) * P->cell_size[2] + (p.z - bodies->cgPos[obj][2]);
+				f4 tq = { ay * fo.z - az * fo.y, az * fo.x - ax * fo.z, ax * fo.y - ay * fo.x, 0.0f };
+				rb_torques[rbindex] = tq;
+			}
 			forces[index] = fo;
 		}
 		if (cfl) cfl[cfl_offset + b] = m;
@@ -590,12 +616,12 @@ float oracle_dtreduce(const b200sph_params *P, const float *cfl, uint32_t num_bl
 }
 
 /* euler: src/cuda/euler_kernel.def:396-540, :117-134 (corrected velocity), :200-206 (continuity).
- * Moving bodies are not restated (row f1 of SURVEY.md section 8). */
+ * including the rigid motion of moving-body particles (:470-503). */
 void oracle_euler(const b200sph_params *P, const f4 *old_pos, const f4 *old_vel, const us4 *info,
 	const uint32_t *hash, const f4 *forces, f4 *new_pos, f4 *new_vel,
-	uint32_t num_particles, uint32_t range_end, float dt, int step)
+	uint32_t num_particles, uint32_t range_end, float dt, int step, const oracle_bodies *bodies)
 {
-	(void)hash; (void)num_particles;
+	(void)num_particles;
 	const int integrate_boundary = (P->boundarytype == B200SPH_DYN_BOUNDARY || P->boundarytype == B200SPH_SA_BOUNDARY);
 #pragma omp parallel for
 	for (uint32_t i = 0; i < range_end; ++i) {
@@ -611,6 +637,22 @@ void oracle_euler(const b200sph_params *P, const f4 *old_pos, const f4 *old_vel,
 				v.w += dt * f.w;
 				v.x += dt * f.x; v.y += dt * f.y; v.z += dt * f.z;
 			} else if (t == B200SPH_PT_BOUNDARY || t == B200SPH_PT_VERTEX) {
+				if (is_moving(inf) && bodies) {              /* :470-503, applyrot euler_kernel.cu:67-74 */
+					const int obj = inf.y & 0xFFF;
+					const i3 gp = grid_pos_from_hash(P, hash[i] & CELLTYPE_BITMASK);
+					const float rx = (float)(gp.x - bodies->cgGridPos[obj][0]) * P->cell_size[0] + (p.x - bodies->cgPos[obj][0]);
+					const float ry = (float)(gp.y - bodies->cgGridPos[obj][1]) * P->cell_size[1] + (p.y - bodies->cgPos[obj][1]);
+					const float rz = (float)(gp.z - bodies->cgGridPos[obj][2]) * P->cell_size[2] + (p.z - bodies->cgPos[obj][2]);
+					const float *rot = bodies->steprot[obj];
+					p.x += (rot[0] - 1.0f) * rx + rot[1] * ry + rot[2] * rz;
+					p.y += rot[3] * rx + (rot[4] - 1.0f) * ry + rot[5] * rz;
+					p.z += rot[6] * rx + rot[7] * ry + (rot[8] - 1.0f) * rz;
+					p.x += bodies->trans[obj][0]; p.y += bodies->trans[obj][1]; p.z += bodies->trans[obj][2];
+					const float *w = bodies->angularvel[obj], *lv = bodies->linearvel[obj];
+					v.x = lv[0] + (w[1] * rz - w[2] * ry);
+					v.y = lv[1] + (w[2] * rx - w[0] * rz);
+					v.z = lv[2] + (w[0] * ry - w[1] * rx);
+				}
 				if (P->boundarytype == B200SPH_DYN_BOUNDARY) v.w += dt * f.w;
 			}
 		}

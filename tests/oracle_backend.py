@@ -53,7 +53,7 @@ class OracleBackend:
         f[frm:to] = 0
         return int(lib.oracle_forces(C.byref(self.params), p(_np(pos)), p(_np(vel)), p(_np(info, np.uint16)),
                                      p(_np(hashv, np.uint32)), p(_np(cs, np.uint32)), p(_np(nl, np.uint16)), None, None,
-                                     p(f), p(_np(cfl)), None, C.c_uint32(n), C.c_uint32(frm), C.c_uint32(to), C.c_uint32(cfl_offset)))
+                                     p(f), p(_np(cfl)), None, C.c_uint32(n), C.c_uint32(frm), C.c_uint32(to), C.c_uint32(cfl_offset), None, None, None))
 
     def dtreduce(self, cfl, nblocks):
         return ob.dtreduce(self.params, _np(cfl)[:nblocks])
@@ -63,7 +63,7 @@ class OracleBackend:
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         lib.oracle_euler(C.byref(self.params), p(_np(opos)), p(_np(ovel)), p(_np(info, np.uint16)), p(_np(hashv, np.uint32)),
                          p(_np(forces)), p(_np(npos)), p(_np(nvel)), C.c_uint32(n), C.c_uint32(range_end),
-                         C.c_float(dt), C.c_int(step))
+                         C.c_float(dt), C.c_int(step), None)
 
     def fmax_elements(self, n):
         return ((n + 127) // 128 + 3) // 4 * 4

@@ -18,6 +18,16 @@ from gpusph_b200.problems import ParticleArrays, initial_dt  # noqa: E402
 _lib = None
 
 
+MAXB = 16
+
+
+class OracleBodies(C.Structure):
+    """oracle_bodies (oracle/sph_oracle.c): mirror of the reference's per-body __constant__ arrays."""
+    _fields_ = [("cgGridPos", (C.c_int * 3) * MAXB), ("cgPos", (C.c_float * 3) * MAXB), ("startIndex", C.c_int * MAXB),
+                ("trans", (C.c_float * 3) * MAXB), ("steprot", (C.c_float * 9) * MAXB),
+                ("linearvel", (C.c_float * 3) * MAXB), ("angularvel", (C.c_float * 3) * MAXB)]
+
+
 class OracleNeibsInfo(C.Structure):
     _fields_ = [("num_interactions", C.c_int32), ("max_fluid_boundary_neibs", C.c_int32),
                 ("max_vertex_neibs", C.c_int32), ("has_too_many_neibs", C.c_int32),
@@ -82,7 +92,8 @@ def build_neibs(params, pos, info, hashv, cs, ce, range_end=None):
     return nl, out
 
 
-def forces(params, pos, vel, info, hashv, cs, nl, eos_p=None, eos_c=None, from_=0, to=None, want_abssum=False):
+def forces(params, pos, vel, info, hashv, cs, nl, eos_p=None, eos_c=None, from_=0, to=None, want_abssum=False,
+           bodies=None, rb_forces=None, rb_torques=None):
     n = pos.shape[0]
     to = n if to is None else to
     f = np.zeros((n, 4), dtype=np.float32)
@@ -92,7 +103,8 @@ def forces(params, pos, vel, info, hashv, cs, nl, eos_p=None, eos_c=None, from_=
     ab = np.zeros((n, 4), dtype=np.float32) if want_abssum else None
     got = lib().oracle_forces(C.byref(params), _p(pos), _p(vel), _p(info), _p(hashv), _p(cs), _p(nl),
                               _p(eos_p), _p(eos_c), _p(f), _p(cfl), _p(ab),
-                              C.c_uint32(n), C.c_uint32(from_), C.c_uint32(to), C.c_uint32(0))
+                              C.c_uint32(n), C.c_uint32(from_), C.c_uint32(to), C.c_uint32(0),
+                              C.byref(bodies) if bodies is not None else None, _p(rb_forces), _p(rb_torques))
     assert got == nb
     return f, cfl[:nb], ab
 
@@ -109,13 +121,14 @@ def dtreduce(params, cfl):
     return float(lib().oracle_dtreduce(C.byref(params), _p(cfl), C.c_uint32(cfl.shape[0])))
 
 
-def euler(params, old_pos, old_vel, info, hashv, f, dt, step, range_end=None):
+def euler(params, old_pos, old_vel, info, hashv, f, dt, step, range_end=None, bodies=None):
     n = old_pos.shape[0]
     range_end = n if range_end is None else range_end
     npos = old_pos.copy()
     nvel = old_vel.copy()
     lib().oracle_euler(C.byref(params), _p(old_pos), _p(old_vel), _p(info), _p(hashv), _p(f), _p(npos), _p(nvel),
-                       C.c_uint32(n), C.c_uint32(range_end), C.c_float(dt), C.c_int(step))
+                       C.c_uint32(n), C.c_uint32(range_end), C.c_float(dt), C.c_int(step),
+                       C.byref(bodies) if bodies is not None else None)
     return npos, nvel
 
 

@@ -397,3 +397,75 @@ def test_device_resident_dt_matches_host_dt_path_bitwise():
     assert np.array_equal(ga.hash, gb.hash) and np.array_equal(ga.info, gb.info)
     assert np.array_equal(ga.pos.view(np.uint32), gb.pos.view(np.uint32))
     assert np.array_equal(ga.vel.view(np.uint32), gb.vel.view(np.uint32))
+
+
+def test_force_feedback_body_parity():
+    """Row f1: forces with compute_object_forces (force x mass + torque scatter), reduceRbForces (segmented scan) and the
+    rigid motion of moving-body particles in euler, against the oracle."""
+    from test_oracle_cpu import body_setup, prepared
+    from gpusph_b200.engines import BUFFER_RB_FORCES, BUFFER_RB_KEYS, BUFFER_RB_TORQUES
+    from gpusph_b200.problems import ParticleArrays
+    params, parts = dambreak_problem(0.03, obstacle=True, densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
+    rng = np.random.default_rng(3)
+    fl = (parts.info[:, 0] & 7) == 0
+    parts.vel[:, :3] += rng.normal(0, 0.5, size=(parts.n, 3)).astype(np.float32) * fl[:, None]
+    parts.vel[:, 3] += rng.normal(0, 2e-3, size=parts.n).astype(np.float32)
+    spos, svel, info, hashv, pidx, cs, ce, newn = prepared(params, parts)
+    n = parts.n
+    b, isb, cg, nbody, first_id = body_setup(params, ParticleArrays(spos, svel, info, hashv))
+    nl, _ = ob.build_neibs(params, spos, info, hashv, cs, ce)
+    fw = SimFramework(params, 0)
+    cgg = [[b.cgGridPos[o][a] for a in range(3)] for o in range(2)]
+    cgp = [[b.cgPos[o][a] for a in range(3)] for o in range(2)]
+    fw.forcesEngine.setrbcg(cgg, cgp, 2)
+    fw.forcesEngine.setrbstart([0, b.startIndex[1]], 2)
+    g = BufferList({BUFFER_POS: dev(spos), BUFFER_VEL: dev(svel), BUFFER_INFO: dev(info.view(np.int16)),
+                    BUFFER_HASH: dev(hashv.view(np.int32)), BUFFER_CELLSTART: dev(cs.view(np.int32)),
+                    BUFFER_NEIBSLIST: dev(nl.view(np.int16)),
+                    BUFFER_FORCES: torch.zeros((n, 4), dtype=torch.float32, device=DEV),
+                    BUFFER_CFL: torch.zeros(fw.forcesEngine.getFmaxElements(n), dtype=torch.float32, device=DEV),
+                    BUFFER_RB_FORCES: torch.zeros((nbody, 4), dtype=torch.float32, device=DEV),
+                    BUFFER_RB_TORQUES: torch.zeros((nbody, 4), dtype=torch.float32, device=DEV),
+                    BUFFER_RB_KEYS: torch.ones(nbody, dtype=torch.int32, device=DEV)})
+    fw.forcesEngine.basicstep(g, g, n, 0, n, 0, compute_object_forces=True)
+    eos = torch.zeros((n, 2), dtype=torch.float32, device=DEV)
+    fw.forcesEngine.eos_probe(g, eos, n)
+    e = host(eos)
+    rbf = np.zeros((nbody, 4), dtype=np.float32)
+    rbt = np.zeros((nbody, 4), dtype=np.float32)
+    fo, _, ab = ob.forces(params, spos, svel, info, hashv, cs, nl, np.ascontiguousarray(e[:, 0]), np.ascontiguousarray(e[:, 1]),
+                          want_abssum=True, bodies=b, rb_forces=rbf, rb_torques=rbt)
+    ids = (info[:, 3].astype(np.int64) << 16) | info[:, 2]
+    k = ids[isb] - first_id
+    m = spos[isb, 3]
+    scale = (ab[isb, 0] * m)[:, None] + 1e-3 * np.abs(rbf).max() + 1e-12
+    got_f, got_t = host(g[BUFFER_RB_FORCES]), host(g[BUFFER_RB_TORQUES])
+    assert (np.abs(got_f[k, :3] - rbf[k, :3]) < 5e-5 * scale).all()
+    assert np.abs(got_t[k, :3] - rbt[k, :3]).max() < 5e-5 * (np.abs(rbt).max() + 1e-9) + 1e-4 * 0.3 * scale.max()
+    assert np.allclose(host(g[BUFFER_FORCES])[isb, :3], got_f[k, :3])           # FORCES holds the scaled force too
+    # segmented reduction: totals of body 1 (single key) = plain sums
+    tot_f, tot_t = fw.forcesEngine.reduceRbForces(g, [nbody - 1], 1, nbody)
+    assert np.allclose(tot_f[0], got_f[:, :3].astype(np.float64).sum(axis=0), rtol=1e-4, atol=1e-4 * np.abs(got_f).max())
+    assert np.allclose(tot_t[0], got_t[:, :3].astype(np.float64).sum(axis=0), rtol=1e-4, atol=1e-4 * np.abs(got_t).max())
+    # rigid motion in euler
+    th = 0.01
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], dtype=np.float32)
+    tr, lv, om = [1e-3, -2e-3, 5e-4], [0.1, 0.0, -0.05], [0.0, 0.2, 1.0]
+    for i in range(9):
+        b.steprot[1][i] = float(R.ravel()[i])
+    for a in range(3):
+        b.trans[1][a], b.linearvel[1][a], b.angularvel[1][a] = tr[a], lv[a], om[a]
+    ie = fw.integrationEngine
+    ie.setrbcg(cgg, cgp, 2)
+    ie.setrbtrans([[0, 0, 0], tr], 2)
+    ie.setrbsteprot([np.eye(3).ravel(), R.ravel()], 2)
+    ie.setrblinearvel([[0, 0, 0], lv], 2)
+    ie.setrbangularvel([[0, 0, 0], om], 2)
+    po, vo = ob.euler(params, spos, svel, info, hashv, fo, 1e-4, 2, bodies=b)
+    npos = torch.zeros((n, 4), dtype=torch.float32, device=DEV)
+    nvel = torch.zeros((n, 4), dtype=torch.float32, device=DEV)
+    rd = BufferList(g)
+    rd[BUFFER_FORCES] = dev(fo)
+    ie.basicstep(rd, BufferList({BUFFER_POS: npos, BUFFER_VEL: nvel}), n, n, 1e-4, 2)
+    assert np.allclose(host(npos), po, rtol=3e-7, atol=2e-9)
+    assert np.allclose(host(nvel), vo, rtol=3e-7, atol=2e-8)

@@ -318,3 +318,72 @@ def test_oracle_worker_conserves_particles_and_stays_finite():
     assert np.isfinite(out.pos).all() and np.isfinite(out.vel).all()
     assert sorted(((out.info[:, 3].astype(np.int64) << 16) | out.info[:, 2]).tolist()) == list(range(parts.n))
     assert 0 < w.dt < 1e-3
+
+
+def body_setup(params, parts):
+    """Body record for the obstacle of dambreak_problem(obstacle=True): object 1, centre of gravity = mean position."""
+    import oracle_binding as ob
+    flags = parts.info[:, 0]
+    isb = (flags & capi.FG_COMPUTE_FORCE) != 0
+    ids = (parts.info[:, 3].astype(np.int64) << 16) | parts.info[:, 2]
+    gp = global_positions(params, parts.pos, parts.hash)
+    cg = gp[isb].mean(axis=0)
+    cs = np.array([params.cell_size[a] for a in range(3)], dtype=np.float64)
+    org = np.array([params.world_origin[a] for a in range(3)], dtype=np.float64)
+    cgcell = np.floor((cg - org) / cs).astype(np.int32)
+    cgloc = (cg - org - (cgcell + 0.5) * cs).astype(np.float32)
+    b = ob.OracleBodies()
+    for a in range(3):
+        b.cgGridPos[1][a] = int(cgcell[a])
+        b.cgPos[1][a] = float(cgloc[a])
+    first_id = int(ids[isb].min())
+    b.startIndex[1] = -first_id          # rbindex = id + startIndex -> 0 .. nbody-1
+    return b, isb, cg, int(isb.sum()), first_id
+
+
+def test_body_forces_torques_and_rigid_motion():
+    """Force-feedback bodies: finalize scatters force x mass and torque about the centre of gravity
+    (forces_kernel.def:4116-4141); euler moves body particles rigidly (euler_kernel.def:470-503). Checked against
+    float64 numpy from global positions."""
+    params, parts = dambreak_problem(0.04, obstacle=True)
+    rng = np.random.default_rng(3)
+    fl = (parts.info[:, 0] & 7) == 0
+    parts.vel[:, :3] += rng.normal(0, 0.5, size=(parts.n, 3)).astype(np.float32) * fl[:, None]
+    parts.vel[:, 3] += rng.normal(0, 2e-3, size=parts.n).astype(np.float32)
+    # move the column next to the obstacle so that it feels a force
+    spos, svel, info, hashv, pidx, cs, ce, newn = prepared(params, parts)
+    sorted_parts = type(parts)(spos, svel, info, hashv)
+    b, isb, cg, nbody, first_id = body_setup(params, sorted_parts)
+    nl, _ = ob.build_neibs(params, spos, info, hashv, cs, ce)
+    rbf = np.zeros((nbody, 4), dtype=np.float32)
+    rbt = np.zeros((nbody, 4), dtype=np.float32)
+    f, cfl, _ = ob.forces(params, spos, svel, info, hashv, cs, nl, bodies=b, rb_forces=rbf, rb_torques=rbt)
+    f0, _, _ = ob.forces(params, spos, svel, info, hashv, cs, nl)
+    ids = (info[:, 3].astype(np.int64) << 16) | info[:, 2]
+    gp = global_positions(params, spos, hashv)
+    k = ids[isb] - first_id
+    m = spos[isb, 3:4]
+    # force = acceleration x mass, also in the FORCES buffer; non-body particles untouched
+    assert np.allclose(rbf[k, :3], f0[isb, :3] * m, rtol=1e-6, atol=1e-12)
+    assert np.array_equal(f[~isb], f0[~isb]) and np.allclose(f[isb, :3], f0[isb, :3] * m, rtol=1e-6, atol=1e-12)
+    arm = gp[isb] - cg
+    tq = np.cross(arm, rbf[k, :3].astype(np.float64))
+    scale = np.abs(tq).max() + 1e-12
+    assert np.abs(rbt[k, :3] - tq).max() < 1e-4 * scale
+    # rigid motion: rotate by 0.01 rad about z through the centre of gravity, translate, spin
+    th = 0.01
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    tr = np.array([1e-3, -2e-3, 5e-4])
+    lv, om = np.array([0.1, 0.0, -0.05]), np.array([0.0, 0.2, 1.0])
+    for i in range(9):
+        b.steprot[1][i] = float(R.ravel()[i])
+    for a in range(3):
+        b.trans[1][a], b.linearvel[1][a], b.angularvel[1][a] = float(tr[a]), float(lv[a]), float(om[a])
+    npos, nvel = ob.euler(params, spos, svel, info, hashv, f, 1e-4, 2, bodies=b)
+    g1 = global_positions(params, npos, hashv)
+    expect = cg + (R @ (gp[isb] - cg).T).T + tr
+    assert np.abs(g1[isb] - expect).max() < 2e-7
+    assert np.allclose(nvel[isb, :3], lv + np.cross(om, gp[isb] - cg), rtol=0, atol=2e-6)
+    # walls (not moving) stay put
+    wall = ((info[:, 0] & 7) == 1) & ~isb
+    assert np.array_equal(npos[wall], spos[wall])

@@ -18,9 +18,9 @@ sys.path.insert(0, ROOT)
 from hotfile import particle_arrays, read_hotfile  # noqa: E402
 
 
-def run(binp, dp, maxiter, rhodiff, save):
+def run(binp, dp, maxiter, rhodiff, save, obstacles=0):
     d = tempfile.mkdtemp(prefix="dropin_")
-    cmd = [binp, "--deltap", str(dp), "--maxiter", str(maxiter), "--dir", d, "--num_obstacles", "0",
+    cmd = [binp, "--deltap", str(dp), "--maxiter", str(maxiter), "--dir", d, "--num_obstacles", str(obstacles),
            "--density-diffusion", str(rhodiff), "--debug", "benchmark_command_runtimes"]
     cmd += ["--checkpoint-every", "1000", "--checkpoints", "0"] if save else ["--nosave"]
     p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
@@ -50,9 +50,10 @@ def main():
     ours = os.path.join(ROOT, "build", "dropin", "DamBreak3D_b200")
     report = {}
     # 1. parity: 100 iterations of a small case, final states compared particle by particle
-    for name, dp, rhodiff in (("dp0.02_colagrossi", 0.02, 2), ("dp0.02_ferrari", 0.02, 1)):
-        rc_r, out_r, _, st_r, n = run(ref, dp, 100, rhodiff, True)
-        rc_o, out_o, _, st_o, _ = run(ours, dp, 100, rhodiff, True)
+    for name, dp, rhodiff, obst in (("dp0.02_colagrossi", 0.02, 2, 0), ("dp0.02_ferrari", 0.02, 1, 0),
+                                    ("dp0.02_default_obstacle_colagrossi", 0.02, 2, 1)):
+        rc_r, out_r, _, st_r, n = run(ref, dp, 100, rhodiff, True, obst)
+        rc_o, out_o, _, st_o, _ = run(ours, dp, 100, rhodiff, True, obst)
         if rc_r or rc_o or st_r is None or st_o is None:
             report[name] = {"error": f"rc {rc_r}/{rc_o}", "ours_tail": out_o[-600:], "ref_tail": out_r[-300:]}
             continue
@@ -68,16 +69,16 @@ def main():
             "max_rho_err": float(np.abs(vr[a][live, 3] - vo[b][live, 3]).max()),
             "max_localpos_err_same_cell": float(np.abs(pr[a][hr[a] == ho[b]] - po[b][hr[a] == ho[b]])[:, :3].max()),
         }
-    # 2. timing: ~2M particles, the reference's own per-command timers, K = 30 steps after 10 of warm-up
+    # 2. timing: ~2M particles, the reference's own per-command timers, K = 100 steps after 10 of warm-up
     for name, dp in (("timing_dp0.0043_ferrari", 0.0043),):
         res = {}
         for tag, binp in (("reference", ref), ("dropin", ours)):
             _, _, t_w, _, n = run(binp, dp, 10, 1, False)
-            rc, out, t_k, _, n = run(binp, dp, 40, 1, False)
+            rc, out, t_k, _, n = run(binp, dp, 110, 1, False)
             if rc or not t_k:
                 res[tag] = {"error": out[-500:]}
                 continue
-            ph = {k: (t_k[k] - t_w.get(k, 0.0)) / 30 for k in t_k}
+            ph = {k: (t_k[k] - t_w.get(k, 0.0)) / 100 for k in t_k}
             res[tag] = {"particles": n, "ms_per_step": sum(ph.values()),
                         "phases_ms_per_step": dict(sorted(ph.items(), key=lambda kv: -kv[1])[:8])}
         if "ms_per_step" in res.get("reference", {}) and "ms_per_step" in res.get("dropin", {}):

@@ -49,7 +49,7 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
                 density_diff_coeff: float | None = None,
                 rheology: int = capi.RHEOLOGY_INVISCID, turbmodel: int = capi.TURB_ARTIFICIAL,
                 kinvisc: float = 0.0, viscavgop: int = capi.AVG_ARITHMETIC,
-                artvisccoeff: float = 0.3, dtadaptfactor: float = 0.3) -> capi.Params:
+                artvisccoeff: float = 0.3, dtadaptfactor: float = 0.3, fluids=None) -> capi.Params:
     """Build b200sph_params the way ProblemCore + the engines' setconstants derive them."""
     p = capi.Params()
     p.abi_version = capi.ABI_VERSION
@@ -97,6 +97,19 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
     p.sscoeff[0] = c0
     p.sspowercoeff[0] = np.float32((gamma - 1.0) / 2.0)
     p.visccoeff[0] = kinvisc
+    # additional fluids (multi-fluid runs): list of dicts with rho0, gamma, c0, kinvisc (physparams.h add_fluid)
+    for f, fl in enumerate(fluids or [], start=1):
+        p.num_fluids = f + 1
+        p.rho0[f] = fl["rho0"]
+        p.bcoeff[f] = np.float32(fl["rho0"] * fl["c0"] ** 2 / fl["gamma"])
+        p.gammacoeff[f] = fl["gamma"]
+        p.sscoeff[f] = fl["c0"]
+        p.sspowercoeff[f] = np.float32((fl["gamma"] - 1.0) / 2.0)
+        p.visccoeff[f] = fl.get("kinvisc", 0.0)
+        c0 = max(c0, fl["c0"])
+        kinvisc = max(kinvisc, fl.get("kinvisc", 0.0))
+    if fluids:
+        p.is_const_visc = 0                                     # IS_SINGLEFLUID is false (visc_spec.h:262)
     p.artvisccoeff = artvisccoeff
     p.epsartvisc = np.float32(0.01 * float(slength) * float(slength))   # ProblemCore.cc:160-161
     p.max_sound_speed_cfl = np.float32(np.float32(c0) * 1.1)     # GPUWorker.cc:3010-3011

@@ -43,6 +43,16 @@ def problems():
     out["poiseuille_geo"] = poiseuille_problem(10, viscavgop=capi.AVG_GEOMETRIC)
     out["laminar_artvisc"] = lattice_problem(12, jitter=0.3, rheology=capi.RHEOLOGY_NEWTONIAN, kinvisc=5e-3,
                                              densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
+    # two fluids (different rest density, EOS and viscosity) in one lattice: the MULTIFLUID kernel variants
+    two = [dict(rho0=800.0, gamma=5.0, c0=25.0, kinvisc=2e-3)]
+    for nm, kw in (("twofluid", dict(densitydiffusion=capi.RHODIFF_COLAGROSSI)),
+                   ("twofluid_laminar", dict(rheology=capi.RHEOLOGY_NEWTONIAN, kinvisc=5e-3, viscavgop=capi.AVG_HARMONIC,
+                                             densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1))):
+        p2, q2 = lattice_problem(12, jitter=0.3, fluids=two, **kw)
+        upper = global_positions(p2, q2.pos, q2.hash)[:, 2] > 0.06
+        q2.info[upper, 1] = np.uint16(1 << 12)                       # fluid number 1 (src/particleinfo.h:135-160)
+        q2.pos[upper, 3] *= np.float32(0.8)
+        out[nm] = (p2, q2)
     for params, parts in out.values():
         fl = (parts.info[:, 0] & 7) == 0
         parts.vel[:, :3] += rng.normal(0, 0.3, size=(parts.n, 3)).astype(np.float32) * fl[:, None]
@@ -61,7 +71,8 @@ def get(name):
     return params, parts
 
 
-NAMES = ["lattice", "dambreak", "dambreak_ferrari", "periodic", "ragged", "poiseuille", "poiseuille_geo", "laminar_artvisc"]
+NAMES = ["lattice", "dambreak", "dambreak_ferrari", "periodic", "ragged", "poiseuille", "poiseuille_geo", "laminar_artvisc",
+         "twofluid", "twofluid_laminar"]
 
 
 class Pipeline:
@@ -469,3 +480,30 @@ def test_force_feedback_body_parity():
     ie.basicstep(rd, BufferList({BUFFER_POS: npos, BUFFER_VEL: nvel}), n, n, 1e-4, 2)
     assert np.allclose(host(npos), po, rtol=3e-7, atol=2e-9)
     assert np.allclose(host(nvel), vo, rtol=3e-7, atol=2e-8)
+
+
+def test_empty_and_single_particle_inputs():
+    """Edge cases: zero particles is a no-op for every entry point; a single particle gets an empty neighbour list,
+    only gravity as acceleration and moves ballistically."""
+    params, parts = lattice_problem(1, jitter=0.0)
+    fw = SimFramework(params, 0)
+    e = BufferList({k: torch.zeros((1, 4), dtype=torch.float32, device=DEV) for k in (BUFFER_POS, BUFFER_VEL, BUFFER_FORCES)})
+    e.update({BUFFER_INFO: torch.zeros((1, 4), dtype=torch.int16, device=DEV), BUFFER_HASH: torch.zeros(1, dtype=torch.int32, device=DEV),
+              BUFFER_PARTINDEX: torch.zeros(1, dtype=torch.int32, device=DEV),
+              BUFFER_CELLSTART: torch.full((params.num_cells,), -1, dtype=torch.int32, device=DEV),
+              BUFFER_CELLEND: torch.full((params.num_cells,), -1, dtype=torch.int32, device=DEV),
+              BUFFER_NEIBSLIST: torch.full((int(params.neiblistsize), 1), -1, dtype=torch.int16, device=DEV),
+              BUFFER_CFL: torch.zeros(8, dtype=torch.float32, device=DEV)})
+    fw.neibsEngine.calcHash(e, e, 0)
+    fw.neibsEngine.sort(e, e, 0)
+    fw.neibsEngine.buildNeibsList(e, e, 0, 0)
+    assert fw.forcesEngine.basicstep(e, e, 0, 0, 0, 0) == 0
+    fw.integrationEngine.basicstep(e, e, 0, 0, 1e-4, 1)
+    w = Worker(params, parts, 0, clobber=True)
+    w.step()
+    assert w.last_neibs_info.num_interactions == 0
+    f = w.forces_buf[:1].cpu().numpy()
+    assert np.allclose(f[0, :3], [0, 0, -9.81]) and f[0, 3] == 0
+    out = w.download()
+    assert out.n == 1 and np.isfinite(out.pos).all()
+    assert out.vel[0, 2] == pytest.approx(parts.vel[0, 2] - 9.81 * w.t, rel=1e-5)

@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sph.so")
+# B200SPH_LIB: alternative build of the same library (kernel tuning experiments, tools/build_variants.sh)
+LIB_PATH = os.environ.get("B200SPH_LIB") or os.path.join(_HERE, "libb200sph.so")
 
 ABI_VERSION = 1
 MAX_FLUIDS = 4

@@ -103,6 +103,7 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	fill_devparams(p, &ctx->dp);
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
+	{ const char *e = getenv("B200SPH_FORCES_COOP"); ctx->use_coop = e ? atoi(e) : 1; }
 	{ const char *e = getenv("B200SPH_FORCES_TILES"); ctx->use_tiles = e ? atoi(e) : 0; }   // staged kernel is opt-in: measured slower than the gather kernel
 	ctx->tile_cfg = 0; ctx->tile_p = TILE_P; ctx->tile_s = TILE_S;
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
@@ -130,7 +131,7 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 	if (!ctx) return B200SPH_OK;
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
-	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->plist); cudaFree(ctx->pcount); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);
 	free(ctx);
 	return B200SPH_OK;

@@ -111,6 +111,11 @@ struct b200sph_ctx {
 	cudaEvent_t tiles_event; int tiles_state;   // 0 none, 1 copy in flight, 2 valid
 	uint num_tiles; uint tiles_range_end; const uint32_t *tiles_cellstart;
 	int use_tiles;                          // env B200SPH_FORCES_TILES (default 0)
+	// cooperative forces kernel: private transposed copy of the neighbour list (forces.cu, b200_coop_list)
+	uint *plist; size_t plist_cap;          // entries, see coop_slot()
+	ushort2 *pcount; size_t pcount_cap;     // per particle {fluid neighbours, boundary neighbours}
+	const void *coop_src; uint coop_n;      // list buffer / particle count the copy was made from (NULL: none)
+	int use_coop;                           // env B200SPH_FORCES_COOP (default 1)
 	int tile_cfg, tile_p, tile_s;           // tile shape handed to the tile builder
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions
@@ -165,4 +170,7 @@ __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
 
 // ---- internal launchers implemented in the .cu files ----
 int b200_build_tiles(b200sph_ctx *ctx, const uint32_t *cell_start, const uint32_t *cell_end, uint range_end);
+int b200_coop_list(b200sph_ctx *ctx, const void *info, const void *pos, const uint32_t *hash, const uint32_t *cell_start,
+	const uint16_t *neibs_list, uint n);
+void b200_invalidate_coop(b200sph_ctx *ctx);
 void b200_invalidate_tiles(b200sph_ctx *ctx);

@@ -102,39 +102,48 @@ __device__ __forceinline__ float4 cell_offset(const DevParams &P, const int c)
 
 // Walk one section of a particle's neighbour-list column. fetch(slot, np, nv, ne) loads the neighbour record
 // `slot` = base-of-its-cell + offset-in-cell (global index for the gather kernel, shared-memory slot for the
-// staged kernel). PF list rows are read ahead of use (row indices clamped to the list).
+// staged kernel); lut(cell, base, ox, oy, oz) returns the first slot of neighbour cell `cell` and its offset times
+// the cell size. PF list rows are read ahead of use; the read-ahead offset is clamped to the list.
+// WIDE: 64-bit list offsets (lists of 2^31 entries or more), else 32-bit (one VIADDMNMX per row).
 // Accumulation order = list order, as in the reference (neibs_iteration.cuh:56-200).
-template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int BASE_STRIDE, int PF, typename Fetch>
+struct ListGeom { const ushort *list; uint stride, rows, boundpos; };      // neighbour list + its shape (DevParams copies)
+template<bool WIDE> struct ListOff { typedef uint type; typedef int stype; };
+template<> struct ListOff<true> { typedef unsigned long long type; typedef long long stype; };
+
+template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch>
 __device__ __forceinline__ void
-walk_section(const DevParams &P, const PairConsts &k, const Central &c, const uint index,
-	const uint *s_base /* [27][BASE_STRIDE] + tid */, const float4 *s_off /* [27] */,
-	const ushort *__restrict__ neibsList, Fetch fetch, float4 &acc)
+walk_section(const DevParams &P, const PairConsts &k, const Central &c, const uint index, Lut lut,
+	const ListGeom &L, Fetch fetch, float4 &acc)
 {
-	const size_t stride = P.stride;
-	// list column of this particle; fluid section grows up from row 0, boundary section down from neibboundpos
-	const ushort *col = neibsList + index;
-	const int rstep = NFLUID ? 1 : -1;
-	const int last_row = (int)P.neiblistsize - 1;
-	int slot = NFLUID ? 0 : (int)P.neibboundpos;
+	typedef typename ListOff<WIDE>::type off_t;
+	typedef typename ListOff<WIDE>::stype soff_t;
+	const ushort *__restrict__ neibsList = L.list;
+	const off_t stride = (off_t)L.stride;
+	// element offset of the next row to read ahead: the fluid section grows up from row 0, the boundary section
+	// down from neibboundpos; the last (first) row of the list is re-read instead of running off the buffer
+	const off_t lo = index, hi = lo + (off_t)(L.rows - 1) * stride;
+	off_t off = NFLUID ? lo : lo + (off_t)L.boundpos * stride;
+	auto advance = [&](off_t o) -> off_t {
+		return NFLUID ? min(o + stride, hi) : (off_t)max((soff_t)(o - stride), (soff_t)lo);
+	};
 	uint base = 0;
 	float pcx = 0.f, pcy = 0.f, pcz = 0.f;
-	// PF list rows are kept in flight: the column is a stride-N walk through HBM/L2 (one row = one sector per warp),
-	// and there are only a few warps per SM to hide that latency when the neighbourhood is staged in shared memory
+	// PF list rows are kept in flight: the column is a stride-N walk through HBM/L2 (one row = one sector per warp)
 	uint q[PF];
 #pragma unroll
-	for (int i = 0; i < PF; ++i) q[i] = ld_neib(col + (size_t)min(max(slot + i * rstep, 0), last_row) * stride);
+	for (int i = 0; i < PF; ++i) { q[i] = ld_neib(neibsList + off); off = advance(off); }
 	while (q[0] != NEIBS_END) {
 		uint nd = q[0];
 #pragma unroll
 		for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
-		q[PF - 1] = ld_neib(col + (size_t)min(max(slot + PF * rstep, 0), last_row) * stride);   // clamped: rows past the marker are never used
-		slot += rstep;
+		q[PF - 1] = ld_neib(neibsList + off);        // rows past the end marker are never used
+		off = advance(off);
 		if (nd >= CELLNUM_ENCODED) {                                    // getNeibIndex, cellgrid.cuh:198-226
 			const uint cell = (nd >> CELLNUM_SHIFT) - 1;
 			nd &= NEIBINDEX_MASK;
-			base = s_base[cell * BASE_STRIDE];
-			const float4 o = s_off[cell];
-			pcx = c.pos.x - o.x; pcy = c.pos.y - o.y; pcz = c.pos.z - o.z;
+			float ox, oy, oz;
+			lut(cell, base, ox, oy, oz);
+			pcx = c.pos.x - ox; pcy = c.pos.y - oy; pcz = c.pos.z - oz;
 		}
 		float4 np, nv, ne;
 		fetch(base + nd, np, nv, ne);
@@ -142,17 +151,16 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
 		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
-		pair_interaction<NFLUID, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, acc);
+		pair_interaction<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, NFLUID, acc);
 	}
 }
 
 // all sections of one particle (forces.cu:759,782,792 in the reference) + finalize; returns the CFL term
-template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int BASE_STRIDE, int PF, typename Fetch>
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch>
 __device__ __forceinline__ float
 particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
-	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo,
-	const uint *s_base, const float4 *s_off,
-	const ushort *__restrict__ neibsList, Fetch fetch, float4 *__restrict__ forces)
+	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo, Lut lut,
+	const ListGeom &L, Fetch fetch, float4 *__restrict__ forces)
 {
 	Central c;
 	c.pos = pos; c.vel = vel;
@@ -162,12 +170,12 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 	if (type == PT_FLUID) {
 		// fluid<-fluid then fluid<-boundary; DYN boundary neighbours interact like fluid ones (forces_kernel.def:3717-3726)
 		c.momentum = true;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
-		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc);
+		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc);
 	} else {
 		// boundary<-fluid: density always, momentum only with force feedback (forces_kernel.def:3634-3667)
 		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BASE_STRIDE, PF>(P, k, c, index, s_base, s_off, neibsList, fetch, acc);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc);
 	}
 	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, cellHash, bo, acc);
 	forces[index] = acc;
@@ -175,10 +183,26 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 }
 
 // ---------------------------------------------------------------------------
-// gather kernel (fallback): neighbours through L1/L2
+// gather kernel: neighbours through L1/L2
 // ---------------------------------------------------------------------------
-template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
-__global__ void __launch_bounds__(BLOCK_FORCES)
+__device__ __forceinline__ uint smem_u32(const void *p) { return (uint)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint lds_u32(uint a) { uint v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f4(uint a)
+{ float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+// Loop-invariant kernel parameters live in the constant bank; on sm_100 every use inside the pair loop costs an
+// LDCU issue slot (ALU instructions no longer take constant-bank operands). B200_HOIST=1 pins the ones the pair
+// loop needs in vector registers by passing them through a warp shuffle, which ptxas will not rematerialise.
+#ifndef B200_HOIST
+#define B200_HOIST 1
+#endif
+#ifndef B200_MIN_BLOCKS
+#define B200_MIN_BLOCKS 7
+#endif
+// (the detour through shared memory is what stops ptxas from re-deriving the value from the constant bank)
+struct Pinned { float v[20]; };
+
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, bool WIDE>
+__global__ void __launch_bounds__(BLOCK_FORCES, B200_MIN_BLOCKS)
 forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
@@ -190,25 +214,58 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x + fromParticle;
 	float cfl_term = 0.0f;
 	if (threadIdx.x < 27) s_celloff[threadIdx.x] = cell_offset(P, threadIdx.x);
+	PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
+	EosConsts E;
+	E.gamma = P.gammacoeff[0]; E.sspow = P.sspowercoeff[0]; E.b = P.bcoeff[0]; E.ss = P.sscoeff[0]; E.rho0 = P.rho0[0];
+	uint a_off = smem_u32(s_celloff);
+	ListGeom L;
+	L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos;
+#if B200_HOIST
+	__shared__ Pinned s_pin;
+	if (threadIdx.x == 0) {
+		float *v = s_pin.v;
+		v[0] = k.inv_h; v[1] = k.fc; v[2] = k.R2; v[3] = k.h_alpha; v[4] = k.eps; v[5] = k.g0; v[6] = k.g1; v[7] = k.g2;
+		v[8] = k.diff; v[9] = k.grav_scale; v[10] = E.gamma; v[11] = E.sspow; v[12] = E.b; v[13] = E.ss; v[14] = E.rho0;
+		v[15] = __uint_as_float(a_off); v[16] = k.h; v[17] = __uint_as_float(L.stride);
+		v[18] = __uint_as_float((uint)(uintptr_t)neibsList); v[19] = __uint_as_float((uint)((uintptr_t)neibsList >> 32));
+	}
 	__syncthreads();
+	{
+		const uint a = smem_u32(s_pin.v);
+		auto ld = [&](int i) { float x; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a + 4u * i)); return x; };
+		k.inv_h = ld(0); k.fc = ld(1); k.R2 = ld(2); k.h_alpha = ld(3); k.eps = ld(4); k.g0 = ld(5); k.g1 = ld(6); k.g2 = ld(7);
+		k.diff = ld(8); k.grav_scale = ld(9); E.gamma = ld(10); E.sspow = ld(11); E.b = ld(12); E.ss = ld(13); E.rho0 = ld(14);
+		a_off = __float_as_uint(ld(15)); k.h = ld(16); L.stride = __float_as_uint(ld(17));
+		L.list = (const ushort *)((uintptr_t)__float_as_uint(ld(18)) | ((uintptr_t)__float_as_uint(ld(19)) << 32));
+	}
+#else
+	__syncthreads();
+#endif
 
 	if (index < toParticle) {
 		const ushort4 info = infoArray[index];
 		const int type = ptype_of(info);
 		const float4 pos = posArray[index];
 		if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000)) {
-			const PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
 			uint *my_base = s_cellbase + threadIdx.x;
 			const uint cellHash = particleHash[index] & CELLTYPE_BITMASK;
 			load_cell_starts(P, (int)cellHash, cellStart, my_base, BLOCK_FORCES);
-			// two gathers per pair straight from the reference's own pos / vel buffers; EOS terms from rho~ on the fly
+			// 32-bit shared-memory addresses computed once (the generic-pointer form is re-derived per use)
+			const uint a_base = smem_u32(my_base);
+			auto lut = [=](const uint cell, uint &base, float &ox, float &oy, float &oz) {
+				base = lds_u32(a_base + cell * (BLOCK_FORCES * 4u));
+				const float4 o = lds_f4(a_off + cell * 16u);
+				ox = o.x; oy = o.y; oz = o.z;
+			};
+			// neighbour data straight from the reference's own pos / vel buffers (two 128-bit gathers); EOS terms from
+			// rho~ on the fly
 			auto fetch = [&](const uint j, float4 &np, float4 &nv, float4 &ne) {
 				np = __ldg(posArray + j); nv = __ldg(velArray + j);
-				ne = eos_from_density(P, nv.w, MULTIFLUID ? fluid_num_of(__ldg(infoArray + j)) : 0);
+				ne = MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
 			};
 			const float4 vel = velArray[index];
-			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, BLOCK_FORCES, GATHER_PF>(P, k, index, info, type, pos,
-				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, my_base, s_celloff, neibsList, fetch, forces);
+			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE>(P, k, index, info, type, pos,
+				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, forces);
 		}
 	}
 
@@ -229,9 +286,216 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 }
 
 // ---------------------------------------------------------------------------
+// cooperative kernel: COOP_LPP lanes per particle
+// ---------------------------------------------------------------------------
+// The gather kernel above gives every thread its own list column: at a given row the 8 threads of a quarter-warp
+// fetch the k-th neighbours of 8 different particles, which on a dam break fall on ~5.6 different 128-byte lines —
+// and the L1 data pipe, at one line per quarter-warp per cycle, is what bounds that kernel (ncu: lsu wavefronts 87 %).
+// Here COOP_LPP (8) lanes share ONE particle and fetch COOP_LPP *consecutive* entries of its list. The list is
+// ordered by cell and, inside a cell, by particle index, so those entries are neighbours in memory too: ~3.2 lines
+// per quarter-warp on the same data (counted on the host from a dam-break list). The price is a transposed private
+// copy of the list (b200_coop_list, made once per neighbour-list build) with absolute particle indices, a shuffle
+// reduction per particle, and the central-particle work being done by every lane of the group.
+// Summation order: lane-strided partial sums combined by a butterfly (the reference sums in list order); the
+// difference is rounding-level and covered by the parity tolerance.
+#ifndef COOP_LPP
+#define COOP_LPP 8
+#endif
+#define COOP_PPW (32 / COOP_LPP)             // particles per warp
+#define COOP_BLOCK 128
+#define COOP_INDEX_BITS 27                   // entry = cell code (5 bits) << 27 | absolute particle index
+#define COOP_INDEX_MASK ((1u << COOP_INDEX_BITS) - 1u)
+#ifndef COOP_MIN_BLOCKS
+#define COOP_MIN_BLOCKS 7
+#endif
+
+// slot of entry k of particle i: the COOP_LPP entries a lane group reads in one step are contiguous, and so are the
+// groups of one warp (one 128-byte line per warp per step)
+__host__ __device__ __forceinline__ size_t coop_slot(const uint i, const uint k, const uint nchunks)
+{
+	return ((size_t)(i / COOP_PPW) * nchunks + k / COOP_LPP) * 32u + (i % COOP_PPW) * COOP_LPP + k % COOP_LPP;
+}
+
+// reference-format list -> private list. One thread per particle walks its column like forcesDevice would
+// (neibs_iteration.cuh:56-200, getNeibIndex cellgrid.cuh:198-226): fluid section up from row 0, boundary section down
+// from neibboundpos (only fluid particles use it, forces_kernel.def:3634-3726).
+__global__ void __launch_bounds__(BLOCK_STREAM)
+coop_list_kernel(const __grid_constant__ DevParams P, const ushort4 *__restrict__ infoArray, const float4 *__restrict__ posArray,
+	const uint *__restrict__ particleHash, const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
+	uint *__restrict__ plist, ushort2 *__restrict__ pcount, const uint n, const uint nchunks)
+{
+	const uint i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const ushort4 info = infoArray[i];
+	const int type = ptype_of(info);
+	uint cf = 0, cb = 0;
+	if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(posArray[i].w) < __int_as_float(0x7f800000)) {
+		const int h0 = (int)(particleHash[i] & CELLTYPE_BITMASK);
+		const int3 gp = grid_pos(P, (uint)h0);
+		const int sx = P.hstride[0], sy = P.hstride[1], sz = P.hstride[2];
+		const int Gx = P.gridSize[0], Gy = P.gridSize[1], Gz = P.gridSize[2];
+		const int dx[3] = { gp.x == 0 ? (Gx - 1) * sx : -sx, 0, gp.x == Gx - 1 ? -(Gx - 1) * sx : sx };
+		const int dy[3] = { gp.y == 0 ? (Gy - 1) * sy : -sy, 0, gp.y == Gy - 1 ? -(Gy - 1) * sy : sy };
+		const int dz[3] = { gp.z == 0 ? (Gz - 1) * sz : -sz, 0, gp.z == Gz - 1 ? -(Gz - 1) * sz : sz };
+		const size_t stride = P.stride;
+		const ushort *col = neibsList + i;
+		uint k = 0;
+		for (int section = 0; section < (type == PT_FLUID ? 2 : 1); ++section) {
+			uint base = 0, code = 0;
+			int row = section == 0 ? 0 : (int)P.neibboundpos;
+			const int step = section == 0 ? 1 : -1;
+			while (row >= 0 && row < (int)P.neiblistsize && k < nchunks * COOP_LPP) {
+				uint nd = ld_neib(col + (size_t)row * stride);
+				if (nd == NEIBS_END) break;
+				if (nd >= CELLNUM_ENCODED) {
+					code = (nd >> CELLNUM_SHIFT) - 1;
+					if (code >= 27) break;                       // not a list column (never built for this particle)
+					nd &= NEIBINDEX_MASK;
+					base = __ldg(cellStart + (h0 + dx[code % 3] + dy[(code / 3) % 3] + dz[code / 9]));
+				}
+				plist[coop_slot(i, k, nchunks)] = (code << COOP_INDEX_BITS) | ((base + nd) & COOP_INDEX_MASK);
+				++k; row += step;
+			}
+			if (section == 0) cf = k; else cb = k - cf;
+		}
+	}
+	pcount[i] = make_ushort2((ushort)cf, (ushort)cb);
+}
+
+void b200_invalidate_coop(b200sph_ctx *ctx) { ctx->coop_src = NULL; ctx->coop_n = 0; }
+
+int b200_coop_list(b200sph_ctx *ctx, const void *info, const void *pos, const uint32_t *hash, const uint32_t *cell_start,
+	const uint16_t *neibs_list, uint n)
+{
+	b200_invalidate_coop(ctx);
+	if (!ctx->use_coop || n == 0 || n > COOP_INDEX_MASK) return B200SPH_OK;
+	const uint nchunks = div_up(ctx->dp.neiblistsize, COOP_LPP);
+	const size_t groups = div_up(n, COOP_PPW);
+	const size_t need = groups * nchunks * 32;
+	if (ctx->plist_cap < need) {
+		cudaFree(ctx->plist); ctx->plist = NULL; ctx->plist_cap = 0;
+		const size_t cap = need + need / 8 + 4096;
+		CUDA_TRY(cudaMalloc(&ctx->plist, cap * sizeof(uint)));
+		ctx->plist_cap = cap;
+	}
+	if (ctx->pcount_cap < n) {
+		cudaFree(ctx->pcount); ctx->pcount = NULL; ctx->pcount_cap = 0;
+		const size_t cap = (size_t)n + n / 8 + 4096;
+		CUDA_TRY(cudaMalloc(&ctx->pcount, cap * sizeof(ushort2)));
+		ctx->pcount_cap = cap;
+	}
+	coop_list_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const ushort4 *)info, (const float4 *)pos,
+		hash, cell_start, neibs_list, ctx->plist, ctx->pcount, n, nchunks);
+	KERNEL_TRY();
+	ctx->coop_src = neibs_list; ctx->coop_n = n;
+	return B200SPH_OK;
+}
+
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
+__global__ void __launch_bounds__(COOP_BLOCK, COOP_MIN_BLOCKS)
+forces_coop_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
+	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
+	const uint *__restrict__ plist, const ushort2 *__restrict__ pcount, const uint nchunks,
+	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
+	const uint fromParticle, const uint toParticle, const uint cflOffset)
+{
+	__shared__ float4 s_celloff[32];
+	if (threadIdx.x < 27) s_celloff[threadIdx.x] = cell_offset(P, threadIdx.x);
+	PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
+	EosConsts E;
+	E.gamma = P.gammacoeff[0]; E.sspow = P.sspowercoeff[0]; E.b = P.bcoeff[0]; E.ss = P.sscoeff[0]; E.rho0 = P.rho0[0];
+	uint a_off = smem_u32(s_celloff);
+#if B200_HOIST
+	__shared__ Pinned s_pin;
+	if (threadIdx.x == 0) {
+		float *v = s_pin.v;
+		v[0] = k.inv_h; v[1] = k.fc; v[2] = k.R2; v[3] = k.h_alpha; v[4] = k.eps; v[5] = k.g0; v[6] = k.g1; v[7] = k.g2;
+		v[8] = k.diff; v[9] = k.grav_scale; v[10] = E.gamma; v[11] = E.sspow; v[12] = E.b; v[13] = E.ss; v[14] = E.rho0;
+		v[15] = __uint_as_float(a_off); v[16] = k.h;
+	}
+	__syncthreads();
+	{
+		const uint a = smem_u32(s_pin.v);
+		auto ld = [&](int i) { float x; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a + 4u * i)); return x; };
+		k.inv_h = ld(0); k.fc = ld(1); k.R2 = ld(2); k.h_alpha = ld(3); k.eps = ld(4); k.g0 = ld(5); k.g1 = ld(6); k.g2 = ld(7);
+		k.diff = ld(8); k.grav_scale = ld(9); E.gamma = ld(10); E.sspow = ld(11); E.b = ld(12); E.ss = ld(13); E.rho0 = ld(14);
+		a_off = __float_as_uint(ld(15)); k.h = ld(16);
+	}
+#else
+	__syncthreads();
+#endif
+
+	const uint lane = threadIdx.x & 31u, sub = lane % COOP_LPP;
+	// warp w handles particles [COOP_PPW*w, COOP_PPW*(w+1)) so that its list lines are the ones coop_slot laid out
+	const uint warp = fromParticle / COOP_PPW + blockIdx.x * (COOP_BLOCK / 32) + (threadIdx.x >> 5);
+	const uint index = warp * COOP_PPW + lane / COOP_LPP;
+	bool active = index >= fromParticle && index < toParticle;
+	ushort4 info = make_ushort4(0, 0, 0, 0);
+	float4 pos = make_float4(0.f, 0.f, 0.f, 0.f), vel = pos;
+	int type = -1;
+	uint cf = 0, ntot = 0;
+	if (active) {
+		info = infoArray[index];
+		type = ptype_of(info);
+		pos = posArray[index];
+		active = (type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000);
+	}
+	Central c;
+	c.pos = pos; c.vel = vel; c.rho = 1.f; c.p_precalc = 0.f; c.sspeed = 0.f; c.fnum = 0; c.momentum = false;
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (active) {
+		vel = velArray[index];
+		const ushort2 cnt = pcount[index];
+		cf = cnt.x;
+		// fluid<-fluid, fluid<-boundary (DYN boundary neighbours interact like fluid ones, forces_kernel.def:3717-3726);
+		// boundary<-fluid: density always, momentum only with force feedback (:3634-3667)
+		ntot = type == PT_FLUID ? (uint)cnt.x + cnt.y : (uint)cnt.x;
+		const float4 e = MULTIFLUID ? eos_from_density(P, vel.w, fluid_num_of(info)) : eos_from_density(E, vel.w);
+		c.pos = pos; c.vel = vel;
+		c.p_precalc = e.x; c.sspeed = e.y; c.rho = e.z;
+		c.fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
+		c.momentum = type == PT_FLUID || (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
+	}
+
+	// lane `sub` takes entries sub, sub + LPP, ...; the next chunk's entry is loaded one step ahead
+	const uint *pl = plist + (size_t)warp * nchunks * 32u + lane;
+	const uint steps = (ntot + COOP_LPP - 1) / COOP_LPP;
+	uint e_next = steps ? __ldg(pl) : 0u;
+	for (uint s = 0; s < steps; ++s) {
+		const uint e = e_next;
+		if (s + 1 < steps) e_next = __ldg(pl + (size_t)(s + 1) * 32u);
+		const uint kk = s * COOP_LPP + sub;
+		if (kk >= ntot) continue;
+		const uint j = e & COOP_INDEX_MASK;
+		const float4 o = lds_f4(a_off + (e >> COOP_INDEX_BITS) * 16u);
+		const float4 np = __ldg(posArray + j), nv = __ldg(velArray + j);
+		const float4 ne = MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
+		const float rx = (c.pos.x - o.x) - np.x, ry = (c.pos.y - o.y) - np.y, rz = (c.pos.z - o.z) - np.z;
+		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
+		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
+		pair_interaction<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, kk < cf, acc);
+	}
+	// combine the partial sums of the lane group
+#pragma unroll
+	for (int o = COOP_LPP / 2; o > 0; o >>= 1) {
+		acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+		acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+	}
+	if (active && sub == 0) {
+		const uint cellHash = bo.bodies ? particleHash[index] & CELLTYPE_BITMASK : 0u;
+		const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, cellHash, bo, acc);
+		forces[index] = acc;
+		// one CFL slot per 128 particles like the reference's per-block maxima (slots are zeroed by the launcher;
+		// non-negative floats order like their bit patterns)
+		if (cfl && cfl_term > 0.0f)
+			atomicMax(reinterpret_cast<unsigned int *>(cfl + cflOffset + (index - fromParticle) / BLOCK_FORCES), __float_as_uint(cfl_term));
+	}
+}
+
+// ---------------------------------------------------------------------------
 // staged kernel: one CTA per tile, neighbourhood in shared memory via TMA bulk copies
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint smem_u32(const void *p) { return (uint)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint count)
 { asm volatile("mbarrier.init.shared.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint bytes)
@@ -338,8 +602,15 @@ forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__
 			my_base[cell * TP] = cs - S.row_start[r] + S.row_off[r];   // meaningless (and unused) for empty cells
 		}
 		if (!staged) { while (!mbar_try_wait(bar, 0)) { } staged = true; }
-		const float t = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, TP, PF>(P, k, index, info, type, pos, vel, e,
-			cellHash, bo, my_base, S.celloff, neibsList, fetch, forces);
+		auto lut = [&](const uint cell, uint &base, float &ox, float &oy, float &oz) {
+			base = my_base[cell * TP];
+			const float4 o = S.celloff[cell];
+			ox = o.x; oy = o.y; oz = o.z;
+		};
+		ListGeom L;
+		L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos;
+		const float t = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, true>(P, k, index, info, type, pos, vel, e,
+			cellHash, bo, lut, L, fetch, forces);
 		cfl_term = fmaxf(cfl_term, t);
 		cfl_slot = (index - fromParticle) / BLOCK_FORCES;
 	}
@@ -357,14 +628,17 @@ forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__
 // ---------------------------------------------------------------------------
 typedef void (*gather_kernel_t)(const DevParams, const float4 *, const float4 *, const ushort4 *, const uint *,
 	const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
+typedef void (*coop_kernel_t)(const DevParams, const float4 *, const float4 *, const ushort4 *, const uint *,
+	const uint *, const ushort2 *, const uint, float4 *, float *, const BodyOut, const uint, const uint, const uint);
 typedef void (*tile_kernel_t)(const DevParams, const Tile *, const float4 *, const float4 *, const float4 *, const ushort4 *,
 	const uint *, const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
 
 template<int RHODIFF>
-static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather_kernel_t *g, tile_kernel_t *t, size_t *smem)
+static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather_kernel_t *g /* [wide] */, coop_kernel_t *cpk, tile_kernel_t *t, size_t *smem)
 {
 	// the staged kernel's tile shape (TILE_P threads, TILE_S staged slots: common.cuh) is the best of the five measured
-#define PICK(A, L, M) do { *g = forces_gather_kernel<RHODIFF, A, L, M>; \
+#define PICK(A, L, M) do { g[0] = forces_gather_kernel<RHODIFF, A, L, M, false>; g[1] = forces_gather_kernel<RHODIFF, A, L, M, true>; \
+	*cpk = forces_coop_kernel<RHODIFF, A, L, M>; \
 	(void)cfg; *t = forces_tile_kernel<RHODIFF, A, L, M, TILE_P, TILE_S, 4>; *smem = sizeof(TileSmem<TILE_P, TILE_S>); \
 } while (0)
 	if (multi) {
@@ -375,6 +649,30 @@ static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather
 		else { if (laminar) PICK(false, true, false); else PICK(false, false, false); }
 	}
 #undef PICK
+}
+
+// Shared-memory carve-out of the gather kernel = what the CTAs its register count allows per SM actually need (the
+// rest of the 228 KB stays L1 for the neighbour gathers). Said explicitly because a host application may have set
+// a device-wide cache preference (GPUSPH sets cudaFuncCachePreferL1, src/cuda/cudautil.cc:71-79), which would
+// otherwise shrink the carve-out and cut the occupancy of this kernel several times over.
+static int gather_carveout(const void *kernel)
+{
+	static const void *known[128]; static int pct[128]; static int nknown = 0;
+	for (int i = 0; i < nknown; ++i) if (known[i] == kernel) return pct[i];
+	int result = 66;
+	cudaFuncAttributes fa;
+	if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.numRegs > 0) {
+		const int regs = (fa.numRegs + 7) / 8 * 8;
+		int blocks = 65536 / (regs * BLOCK_FORCES);
+		if (blocks > 2048 / BLOCK_FORCES) blocks = 2048 / BLOCK_FORCES;
+		const size_t per_block = fa.sharedSizeBytes + 1024;           // + the per-CTA reservation
+		while (blocks > 1 && blocks * per_block > 227 * 1024) --blocks;
+		if (const char *e = getenv("B200SPH_FORCES_BLOCKS")) { const int b = atoi(e); if (b > 0 && b < blocks) blocks = b; }
+		result = (int)((blocks * per_block * 100 + 228 * 1024 - 1) / (228 * 1024));
+		if (result > 100) result = 100;
+	}
+	if (nknown < 128) { known[nknown] = kernel; pct[nknown] = result; ++nknown; }
+	return result;
 }
 
 extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel, const void *info,
@@ -409,12 +707,12 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 	nblocks = (nblocks + 3) / 4 * 4;
 	const DevParams &d = ctx->dp;
 	const bool artvisc = d.turbmodel == B200SPH_TURB_ARTIFICIAL, laminar = !d.inviscid, multi = d.numFluids > 1;
-	gather_kernel_t gk; tile_kernel_t tk; size_t smem = 0;
+	gather_kernel_t gks[2]; coop_kernel_t ck; tile_kernel_t tk; size_t smem = 0;
 	const int cfg = ctx->tile_cfg;
 	switch (d.densitydiffusiontype) {
-	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, cfg, &gk, &tk, &smem); break;
-	case B200SPH_RHODIFF_COLAGROSSI: pick_kernels<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi, cfg, &gk, &tk, &smem); break;
-	default: pick_kernels<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi, cfg, &gk, &tk, &smem); break;
+	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
+	case B200SPH_RHODIFF_COLAGROSSI: pick_kernels<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
+	default: pick_kernels<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
 	}
 	// tiles built by the last buildNeibsList for these cell ranges?
 	if (ctx->tiles_state == 1) {
@@ -431,11 +729,23 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		tk<<<ctx->num_tiles, ctx->tile_p, smem, ctx->stream>>>(ctx->dp, ctx->tiles, (const float4 *)pos, (const float4 *)vel, ctx->aux,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
+	} else if (ctx->use_coop && num_particles <= COOP_INDEX_MASK) {
+		// private copy of the list: made by buildNeibsList for the list it wrote; a list from elsewhere is converted here
+		if (ctx->coop_src != (const void *)neibs_list || ctx->coop_n < to) {
+			int rc = b200_coop_list(ctx, info, pos, hash, cell_start, neibs_list, num_particles);
+			if (rc) return rc;
+		}
+		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
+		const uint first_warp = from / COOP_PPW, end_warp = div_up(to, COOP_PPW);
+		const uint grid = div_up(end_warp - first_warp, COOP_BLOCK / 32);
+		CUDA_TRY(cudaFuncSetAttribute((const void *)ck, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout((const void *)ck)));
+		ck<<<grid, COOP_BLOCK, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel, (const ushort4 *)info, hash,
+			ctx->plist, ctx->pcount, div_up(d.neiblistsize, COOP_LPP), (float4 *)forces, cfl, bo, from, to, cfl_offset);
 	} else {
-		// The kernel wants ~9 resident CTAs x 15 KB of shared memory per SM. Say so explicitly: a host application may
-		// have set a device-wide cache preference (GPUSPH sets cudaFuncCachePreferL1, src/cuda/cudautil.cc:71-79),
-		// which would otherwise shrink the carve-out and cut the occupancy of this kernel by 5x.
-		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, 66));
+		// 32-bit list offsets unless the list has 2^31 entries or more
+		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
+		gather_kernel_t gk = gks[wide ? 1 : 0];
+		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout((const void *)gk)));
 		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
 	}

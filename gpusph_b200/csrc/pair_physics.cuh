@@ -73,16 +73,25 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 // reference does (P() and soundSpeed() with __powf = ex2(y*lg2(x)), phys_core.cu:99-136; precalc_pressure
 // forces_kernel.def:419-429) but sharing the logarithm between the two powers. Trading ~12 ALU/MUFU instructions
 // for one scattered 128-bit gather is a win because the pair kernel is L1-wavefront bound, not issue bound.
-__device__ __forceinline__ float4 eos_from_density(const DevParams &P, const float rho_tilde, const int f)
+struct EosConsts { float gamma, sspow, b, ss, rho0; };      // of fluid 0, kept in registers by the single-fluid kernels
+__device__ __forceinline__ float4 eos_from_density(const EosConsts &E, const float rho_tilde)
 {
 	const float ratio = rho_tilde + 1.0f;
 	const float lg = lg2_approx(ratio);
-	const float pw = ex2_approx(P.gammacoeff[f] * lg);
-	const float rho = ratio * P.rho0[f];
+	const float pw = ex2_approx(E.gamma * lg);
+	const float rho = ratio * E.rho0;
 	float4 e;
-	e.x = P.bcoeff[f] * (pw - 1.0f) * rcp_approx(rho * rho);
-	e.y = P.sscoeff[f] * ex2_approx(P.sspowercoeff[f] * lg);
+	e.x = E.b * (pw - 1.0f) * rcp_approx(rho * rho);
+	e.y = E.ss * ex2_approx(E.sspow * lg);
 	e.z = rho;
+	e.w = __int_as_float(0);
+	return e;
+}
+__device__ __forceinline__ float4 eos_from_density(const DevParams &P, const float rho_tilde, const int f)
+{
+	EosConsts E;
+	E.gamma = P.gammacoeff[f]; E.sspow = P.sspowercoeff[f]; E.b = P.bcoeff[f]; E.ss = P.sscoeff[f]; E.rho0 = P.rho0[f];
+	float4 e = eos_from_density(E, rho_tilde);
 	e.w = __int_as_float(f);
 	return e;
 }
@@ -97,12 +106,12 @@ struct Central {
 
 // One pair interaction. (rx,ry,rz) = relPos, r2 its squared length (already known to be inside the support),
 // np/nv = neighbour position|mass and velocity|rho~, ne = neighbour {P/rho^2, sound speed, density, fluid#}.
-// NFLUID: the neighbour is a fluid particle (density diffusion applies), else a DYN boundary particle
+// nfluid: the neighbour is a fluid particle (density diffusion applies), else a DYN boundary particle
 // (forces_kernel.def:1594-1606, 3717-3726).
-template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
 __device__ __forceinline__ void
 pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
-	const float r2, const float nmass, const float4 nv, const float4 ne, float4 &acc)
+	const float r2, const float nmass, const float4 nv, const float4 ne, const bool nfluid, float4 &acc)
 {
 	const int nfnum = MULTIFLUID ? __float_as_int(ne.w) : 0;
 	const float r = r2 * rsqrt_approx(r2 + 1e-30f);
@@ -117,7 +126,7 @@ pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, cons
 
 	// --- continuity: mass_continuity_div_vel_term :2140-2150 ---
 	float DrDt = mf * vel_dot_pos;
-	if (NFLUID) {
+	if (nfluid) {
 		if (RHODIFF == B200SPH_RHODIFF_FERRARI) {                   // :1614-1636
 			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
 			const float grav_corr = -gdot * (MULTIFLUID ? P.rho0[c.fnum] / P.sqC0[c.fnum] : k.grav_scale);

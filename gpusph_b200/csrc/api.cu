@@ -103,7 +103,7 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	fill_devparams(p, &ctx->dp);
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
-	{ const char *e = getenv("B200SPH_FORCES_COOP"); ctx->use_coop = e ? atoi(e) : 1; }
+	{ const char *e = getenv("B200SPH_FORCES_COOP"); ctx->use_coop = e ? atoi(e) : 0; }     // cooperative kernel is opt-in: measured slower (788 vs 553 us, profiles/r01_forces_coop_experiment_ncu.txt)
 	{ const char *e = getenv("B200SPH_FORCES_TILES"); ctx->use_tiles = e ? atoi(e) : 0; }   // staged kernel is opt-in: measured slower than the gather kernel
 	ctx->tile_cfg = 0; ctx->tile_p = TILE_P; ctx->tile_s = TILE_S;
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));

@@ -115,7 +115,7 @@ struct b200sph_ctx {
 	uint *plist; size_t plist_cap;          // entries, see coop_slot()
 	ushort2 *pcount; size_t pcount_cap;     // per particle {fluid neighbours, boundary neighbours}
 	const void *coop_src; uint coop_n;      // list buffer / particle count the copy was made from (NULL: none)
-	int use_coop;                           // env B200SPH_FORCES_COOP (default 1)
+	int use_coop;                           // env B200SPH_FORCES_COOP (default 0)
 	int tile_cfg, tile_p, tile_s;           // tile shape handed to the tile builder
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions

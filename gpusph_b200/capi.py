@@ -15,8 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SPH_LIB: alternative build of the same library (kernel tuning experiments, tools/build_variants.sh)
 LIB_PATH = os.environ.get("B200SPH_LIB") or os.path.join(_HERE, "libb200sph.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_FLUIDS = 4
+MAX_PLANES = 8
 
 # enums (values are the reference's, src/particledefine.h:79-224, src/visc_spec.h)
 KERNEL_WENDLAND = 3
@@ -27,7 +28,9 @@ PERIODIC_X, PERIODIC_Y, PERIODIC_Z = 1, 2, 4
 RHEOLOGY_INVISCID, RHEOLOGY_NEWTONIAN = 0, 1
 TURB_LAMINAR, TURB_ARTIFICIAL = 0, 1
 COMPVISC_KINEMATIC, COMPVISC_DYNAMIC = 0, 1
-VISCMODEL_MORRIS = 0
+VISCMODEL_MORRIS, VISCMODEL_MONAGHAN, VISCMODEL_ESPANOL_REVENGA = 0, 1, 2
+# simulation flags (src/simflags.h:71-86)
+ENABLE_DTADAPT, ENABLE_XSPH, ENABLE_PLANES, ENABLE_DEM = 1, 2, 4, 8
 AVG_ARITHMETIC, AVG_HARMONIC, AVG_GEOMETRIC = 0, 1, 2
 
 PT_FLUID, PT_BOUNDARY, PT_VERTEX, PT_TESTPOINT = 0, 1, 2, 3
@@ -69,6 +72,11 @@ class Params(C.Structure):
         ("artvisccoeff", C.c_float), ("epsartvisc", C.c_float),
         ("max_sound_speed_cfl", C.c_float), ("max_kinvisc", C.c_float),
         ("dtadapt", C.c_uint32),
+        # ABI version 2
+        ("simflags", C.c_uint32),
+        ("epsxsph", C.c_float), ("monaghan_visc_coeff", C.c_float),
+        ("visc2coeff", C.c_float * MAX_FLUIDS),
+        ("r0", C.c_float), ("dcoeff", C.c_float), ("p1coeff", C.c_float), ("p2coeff", C.c_float), ("partsurf", C.c_float),
     ]
 
     def copy(self) -> "Params":
@@ -91,6 +99,18 @@ class NeibsInfo(C.Structure):
     ]
 
 
+class ForcesArgs(C.Structure):
+    """struct b200sph_forces_args (include/b200sph.h): the complete argument set of AbstractForcesEngine::basicstep."""
+    _fields_ = [
+        ("pos", C.c_void_p), ("vel", C.c_void_p), ("info", C.c_void_p),
+        ("hash", C.c_void_p), ("cell_start", C.c_void_p), ("neibs_list", C.c_void_p),
+        ("forces", C.c_void_p), ("cfl", C.c_void_p),
+        ("rb_forces", C.c_void_p), ("rb_torques", C.c_void_p), ("xsph", C.c_void_p),
+        ("num_particles", C.c_uint32), ("from_particle", C.c_uint32), ("to_particle", C.c_uint32), ("cfl_offset", C.c_uint32),
+        ("dt", C.c_float), ("step", C.c_int), ("dt_from_device", C.c_int),
+    ]
+
+
 class ReorderExtra(C.Structure):
     _fields_ = [("unsorted", C.c_void_p), ("sorted", C.c_void_p), ("elem_size", C.c_uint32)]
 
@@ -108,6 +128,12 @@ PROTOTYPES = {
     "b200sph_set_stream": (C.c_int, [_P, _P]),
     "b200sph_set_gravity": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "b200sph_get_neibboundpos": (C.c_int, [_P, C.POINTER(_U)]),
+    "b200sph_set_planes": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
+    "b200sph_forces_ex": (C.c_int, [_P, C.POINTER(ForcesArgs), C.POINTER(_U)]),
+    "b200sph_euler_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_float, C.c_int, C.c_int]),
+    "b200sph_filter_shepard": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U]),
+    "b200sph_filter_mls": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U]),
+    "b200sph_testpoints": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U]),
     "b200sph_calc_hash": (C.c_int, [_P, _P, _P, _P, _P, _P, _U]),
     "b200sph_fix_hash": (C.c_int, [_P, _P, _P, _P, _P, _U]),
     "b200sph_sort": (C.c_int, [_P, _P, _P, _P, _U]),

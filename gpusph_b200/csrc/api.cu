@@ -46,10 +46,12 @@ extern "C" int b200sph_validate(const b200sph_params *p)
 	if (p->kerneltype != B200SPH_KERNEL_WENDLAND) { b200_set_error("unsupported SPH kernel %u: only WENDLAND is implemented", p->kerneltype); return B200SPH_EUNSUP; }
 	if (p->sph_formulation != B200SPH_SPH_F1) { b200_set_error("unsupported SPH formulation %u: only SPH_F1 is implemented", p->sph_formulation); return B200SPH_EUNSUP; }
 	if (p->boundarytype != B200SPH_DYN_BOUNDARY) { b200_set_error("unsupported boundary type %u: only DYN_BOUNDARY is implemented", p->boundarytype); return B200SPH_EUNSUP; }
-	if (p->densitydiffusiontype > B200SPH_RHODIFF_COLAGROSSI) { b200_set_error("unsupported density diffusion %u (BREZZI not implemented)", p->densitydiffusiontype); return B200SPH_EUNSUP; }
+	if (p->densitydiffusiontype > B200SPH_RHODIFF_BREZZI) { b200_set_error("unknown density diffusion %u", p->densitydiffusiontype); return B200SPH_EINVAL; }
 	if (p->rheologytype > B200SPH_RHEOLOGY_NEWTONIAN) { b200_set_error("unsupported rheology %u", p->rheologytype); return B200SPH_EUNSUP; }
 	if (p->turbmodel > B200SPH_TURB_ARTIFICIAL) { b200_set_error("unsupported turbulence model %u", p->turbmodel); return B200SPH_EUNSUP; }
-	if (p->rheologytype == B200SPH_RHEOLOGY_NEWTONIAN && p->viscmodel != B200SPH_VISCMODEL_MORRIS) { b200_set_error("unsupported viscous model %u: only MORRIS", p->viscmodel); return B200SPH_EUNSUP; }
+	if (p->rheologytype == B200SPH_RHEOLOGY_NEWTONIAN && p->viscmodel > B200SPH_VISCMODEL_ESPANOL_REVENGA) { b200_set_error("unknown viscous model %u", p->viscmodel); return B200SPH_EINVAL; }
+	if (p->simflags & B200SPH_ENABLE_DEM) { b200_set_error("unsupported simulation flag ENABLE_DEM (out of scope, SURVEY.md section 8)"); return B200SPH_EUNSUP; }
+	if ((p->simflags & B200SPH_ENABLE_PLANES) && !(p->r0 > 0)) { b200_set_error("ENABLE_PLANES needs the Lennard-Jones radius r0 > 0"); return B200SPH_EINVAL; }
 	if (p->viscavgop > B200SPH_AVG_GEOMETRIC || p->compvisc > B200SPH_COMPVISC_DYNAMIC) { b200_set_error("bad viscous averaging / computational viscosity"); return B200SPH_EINVAL; }
 	if (!(p->slength > 0) || !(p->influenceradius > 0)) { b200_set_error("non-positive smoothing length"); return B200SPH_EINVAL; }
 	return B200SPH_OK;
@@ -84,7 +86,16 @@ static void fill_devparams(const b200sph_params *p, DevParams *d)
 		d->rho0[f] = p->rho0[f]; d->bcoeff[f] = p->bcoeff[f]; d->gammacoeff[f] = p->gammacoeff[f];
 		d->sscoeff[f] = p->sscoeff[f]; d->sspowercoeff[f] = p->sspowercoeff[f]; d->visccoeff[f] = p->visccoeff[f];
 		d->sqC0[f] = p->sscoeff[f] * p->sscoeff[f];   // src/cuda/forces.cu:318-323
+		d->visc2coeff[f] = p->visc2coeff[f];
 	}
+	const float h3 = h2 * h;
+	d->wcoeff_wendland = (float)(21.0f / (16.0f * M_PI * h3));      // src/cuda/forces.cu:283
+	d->viscmodel = p->viscmodel; d->simflags = p->simflags;
+	d->epsxsph = p->epsxsph; d->monaghanViscCoeff = p->monaghan_visc_coeff;
+	d->r0 = p->r0; d->dcoeff = p->dcoeff; d->p1coeff = p->p1coeff; d->p2coeff = p->p2coeff;
+	d->partsurf = p->partsurf == 0.0f ? p->r0 * p->r0 : p->partsurf;   // src/cuda/forces.cu:364-368
+	d->numplanes = 0;
+	d->cmd_dt = 0.0f; d->cmd_step = 0; d->dev_state = NULL;
 }
 
 extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
@@ -148,6 +159,22 @@ extern "C" int b200sph_set_gravity(b200sph_ctx *ctx, const float g[3])
 {
 	if (!ctx || !g) { b200_set_error("null argument"); return B200SPH_EINVAL; }
 	for (int a = 0; a < 3; ++a) { ctx->hp.gravity[a] = g[a]; ctx->dp.gravity[a] = g[a]; }
+	return B200SPH_OK;
+}
+
+// AbstractForcesEngine::setplanes, src/cuda/forces.cu:443-447
+extern "C" int b200sph_set_planes(b200sph_ctx *ctx, const float *normals, const int *grid_pos, const float *pos, int n)
+{
+	if (!ctx) { b200_set_error("null context"); return B200SPH_EINVAL; }
+	if (n < 0 || n > B200SPH_MAX_PLANES) { b200_set_error("too many planes (%d > %d)", n, B200SPH_MAX_PLANES); return B200SPH_EINVAL; }
+	if (n && (!normals || !grid_pos || !pos)) { b200_set_error("null plane array"); return B200SPH_EINVAL; }
+	if (n && !(ctx->hp.simflags & B200SPH_ENABLE_PLANES)) { b200_set_error("planes given but ENABLE_PLANES is not set in simflags"); return B200SPH_EINVAL; }
+	for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) {
+		ctx->dp.planeNormal[i][a] = normals[3 * i + a];
+		ctx->dp.planeGridPos[i][a] = grid_pos[3 * i + a];
+		ctx->dp.planePos[i][a] = pos[3 * i + a];
+	}
+	ctx->dp.numplanes = (uint)n;
 	return B200SPH_OK;
 }
 

@@ -53,6 +53,21 @@ struct DevParams {
 	float sscoeff[B200SPH_MAX_FLUIDS], sspowercoeff[B200SPH_MAX_FLUIDS], visccoeff[B200SPH_MAX_FLUIDS];
 	float sqC0[B200SPH_MAX_FLUIDS];
 	float gravity[3];
+	// options only the general forces kernel / the filters read
+	uint viscmodel, simflags;
+	float wcoeff_wendland;  // 21/(16 pi h^3), src/cuda/forces.cu:283
+	float epsxsph, monaghanViscCoeff;
+	float visc2coeff[B200SPH_MAX_FLUIDS];
+	// geometric planes (src/planes.h:42-46, src/cuda/geom_core.cu:52-53) and their Lennard-Jones repulsion
+	uint numplanes;
+	float r0, dcoeff, p1coeff, p2coeff, partsurf;
+	float planeNormal[B200SPH_MAX_PLANES][3];
+	int planeGridPos[B200SPH_MAX_PLANES][3];
+	float planePos[B200SPH_MAX_PLANES][3];
+	// per launch (filled by the launcher on its by-value copy): dt of the command, read by BREZZI diffusion only
+	float cmd_dt;
+	int cmd_step;                        // 1 / 2
+	const struct StepState *dev_state;   // non-NULL: dt from the device-resident record (dt/2 for step 1)
 };
 
 // One CTA of the staged forces kernel: a run of consecutive non-empty cells along COORD1 inside one

@@ -8,7 +8,7 @@ __global__ void __launch_bounds__(BLOCK_STREAM)
 euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ oldPos, const float4 *__restrict__ oldVel,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash, const float4 *__restrict__ forces,
 	float4 *__restrict__ newPos, float4 *__restrict__ newVel, const uint numParticles, const float dt_arg,
-	const StepState *__restrict__ dev_state, const BodyData *__restrict__ bodies)
+	const StepState *__restrict__ dev_state, const BodyData *__restrict__ bodies, const float4 *__restrict__ xsph)
 {
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
 	if (index >= numParticles) return;
@@ -27,6 +27,10 @@ euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ old
 		if (STEP == 2) {
 			const float hdt = dt / 2;
 			vcx += force.x * hdt; vcy += force.y * hdt; vcz += force.z * hdt;
+		}
+		if (xsph) {                                               // XSPH correction, :165-180
+			const float4 mv = xsph[index];
+			vcx += P.epsxsph * mv.x; vcy += P.epsxsph * mv.y; vcz += P.epsxsph * mv.z;
 		}
 		if (type == PT_FLUID) {                                   // :441-462
 			pos.x += vcx * dt; pos.y += vcy * dt; pos.z += vcz * dt;
@@ -60,45 +64,50 @@ euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ old
 	newVel[index] = vel;
 }
 
-extern "C" int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
-	const uint32_t *hash, const void *forces, void *new_pos, void *new_vel,
-	uint32_t num_particles, uint32_t particle_range_end, float dt, int step)
+static int launch_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
+	const uint32_t *hash, const void *forces, const void *xsph, void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step, int dt_from_device)
 {
 	CHECK_CTX(ctx);
 	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }   // euler.cu:361-362
 	const BodyData *bodies = (ctx->have_bodies && hash) ? ctx->d_bodies : NULL;
 	if (particle_range_end == 0) return B200SPH_OK;
 	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
+	if ((ctx->hp.simflags & B200SPH_ENABLE_XSPH) && !xsph) { b200_set_error("euler: ENABLE_XSPH needs the xsph buffer"); return B200SPH_EINVAL; }
+	if (!(ctx->hp.simflags & B200SPH_ENABLE_XSPH)) xsph = NULL;
 	const uint nb = div_up(particle_range_end, BLOCK_STREAM);
 	// NOTE the reference passes numParticles (not the range end) as the kernel bound, euler.cu:352
 	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
+	const StepState *st = dt_from_device ? ctx->d_step : NULL;
 	if (step == 1)
 		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL, bodies);
+			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, st, bodies, (const float4 *)xsph);
 	else
 		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, NULL, bodies);
+			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, dt, st, bodies, (const float4 *)xsph);
 	KERNEL_TRY();
 	return B200SPH_OK;
+}
+
+extern "C" int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
+	const uint32_t *hash, const void *forces, void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step)
+{
+	if (ctx && (ctx->hp.simflags & B200SPH_ENABLE_XSPH)) { b200_set_error("euler: ENABLE_XSPH needs b200sph_euler_ex with the xsph buffer"); return B200SPH_EINVAL; }
+	return launch_euler(ctx, old_pos, old_vel, info, hash, forces, NULL, new_pos, new_vel, num_particles, particle_range_end, dt, step, 0);
 }
 
 extern "C" int b200sph_euler_async(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
 	const uint32_t *hash, const void *forces, void *new_pos, void *new_vel,
 	uint32_t num_particles, uint32_t particle_range_end, int step)
 {
-	CHECK_CTX(ctx);
-	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }
-	const BodyData *bodies = (ctx->have_bodies && hash) ? ctx->d_bodies : NULL;
-	if (particle_range_end == 0) return B200SPH_OK;
-	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
-	const uint nb = div_up(particle_range_end, BLOCK_STREAM);
-	const uint bound = num_particles < particle_range_end ? num_particles : particle_range_end;
-	if (step == 1)
-		euler_kernel<1><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step, bodies);
-	else
-		euler_kernel<2><<<nb, BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const float4 *)old_pos, (const float4 *)old_vel,
-			(const ushort4 *)info, hash, (const float4 *)forces, (float4 *)new_pos, (float4 *)new_vel, bound, 0.0f, ctx->d_step, bodies);
-	KERNEL_TRY();
-	return B200SPH_OK;
+	if (ctx && (ctx->hp.simflags & B200SPH_ENABLE_XSPH)) { b200_set_error("euler: ENABLE_XSPH needs b200sph_euler_ex with the xsph buffer"); return B200SPH_EINVAL; }
+	return launch_euler(ctx, old_pos, old_vel, info, hash, forces, NULL, new_pos, new_vel, num_particles, particle_range_end, 0.0f, step, 1);
+}
+
+extern "C" int b200sph_euler_ex(b200sph_ctx *ctx, const void *old_pos, const void *old_vel, const void *info,
+	const uint32_t *hash, const void *forces, const void *xsph, void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step, int dt_from_device)
+{
+	return launch_euler(ctx, old_pos, old_vel, info, hash, forces, xsph, new_pos, new_vel, num_particles, particle_range_end, dt, step, dt_from_device);
 }

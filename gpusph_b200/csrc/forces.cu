@@ -113,7 +113,7 @@ template<> struct ListOff<true> { typedef unsigned long long type; typedef long 
 template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch>
 __device__ __forceinline__ void
 walk_section(const DevParams &P, const PairConsts &k, const Central &c, const uint index, Lut lut,
-	const ListGeom &L, Fetch fetch, float4 &acc)
+	const ListGeom &L, Fetch fetch, float4 &acc, float3 &xs)
 {
 	typedef typename ListOff<WIDE>::type off_t;
 	typedef typename ListOff<WIDE>::stype soff_t;
@@ -151,7 +151,7 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
 		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
-		pair_interaction<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, NFLUID, acc);
+		pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, NFLUID, acc, xs);
 	}
 }
 
@@ -160,24 +160,29 @@ template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool 
 __device__ __forceinline__ float
 particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
 	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo, Lut lut,
-	const ListGeom &L, Fetch fetch, float4 *__restrict__ forces)
+	const ListGeom &L, Fetch fetch, float4 *__restrict__ forces, float4 *__restrict__ xsph = NULL)
 {
 	Central c;
 	c.pos = pos; c.vel = vel;
 	c.p_precalc = e.x; c.sspeed = e.y; c.rho = e.z;
 	c.fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
+	c.xsph = false;
 	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	float3 xs = make_float3(0.f, 0.f, 0.f);
 	if (type == PT_FLUID) {
 		// fluid<-fluid then fluid<-boundary; DYN boundary neighbours interact like fluid ones (forces_kernel.def:3717-3726)
 		c.momentum = true;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc);
-		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc);
+		c.xsph = RHODIFF == RHODIFF_RUNTIME && xsph != NULL;
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc, xs);
+		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc, xs);
+		// write_xsph :3366-3368
+		if (c.xsph) xsph[index] = make_float4(2.0f * xs.x, 2.0f * xs.y, 2.0f * xs.z, 0.0f);
 	} else {
 		// boundary<-fluid: density always, momentum only with force feedback (forces_kernel.def:3634-3667)
 		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc, xs);
 	}
-	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, cellHash, bo, acc);
+	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
 	forces[index] = acc;
 	return cfl_term;
 }
@@ -209,6 +214,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
 	const uint fromParticle, const uint toParticle, const uint cflOffset)
 {
+	constexpr bool GEN = RHODIFF == RHODIFF_RUNTIME;
 	__shared__ uint s_cellbase[27 * BLOCK_FORCES];
 	__shared__ float4 s_celloff[27];
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x + fromParticle;
@@ -441,7 +447,7 @@ forces_coop_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 		active = (type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000);
 	}
 	Central c;
-	c.pos = pos; c.vel = vel; c.rho = 1.f; c.p_precalc = 0.f; c.sspeed = 0.f; c.fnum = 0; c.momentum = false;
+	c.pos = pos; c.vel = vel; c.rho = 1.f; c.p_precalc = 0.f; c.sspeed = 0.f; c.fnum = 0; c.momentum = false; c.xsph = false;
 	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (active) {
 		vel = velArray[index];
@@ -483,8 +489,8 @@ forces_coop_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 		acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
 	}
 	if (active && sub == 0) {
-		const uint cellHash = bo.bodies ? particleHash[index] & CELLTYPE_BITMASK : 0u;
-		const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, cellHash, bo, acc);
+		const uint cellHash = (bo.bodies || P.numplanes) ? particleHash[index] & CELLTYPE_BITMASK : 0u;
+		const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
 		forces[index] = acc;
 		// one CFL slot per 128 particles like the reference's per-block maxima (slots are zeroed by the launcher;
 		// non-negative floats order like their bit patterns)
@@ -689,14 +695,37 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 	void *forces, float *cfl, void *rb_forces, void *rb_torques, uint32_t num_particles, uint32_t from, uint32_t to,
 	uint32_t cfl_offset, uint32_t *num_cfl_blocks)
 {
+	b200sph_forces_args a;
+	memset(&a, 0, sizeof(a));
+	a.pos = pos; a.vel = vel; a.info = info; a.hash = hash; a.cell_start = cell_start; a.neibs_list = neibs_list;
+	a.forces = forces; a.cfl = cfl; a.rb_forces = rb_forces; a.rb_torques = rb_torques;
+	a.num_particles = num_particles; a.from_particle = from; a.to_particle = to; a.cfl_offset = cfl_offset;
+	return b200sph_forces_ex(ctx, &a, num_cfl_blocks);
+}
+
+extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks)
+{
 	CHECK_CTX(ctx);
+	if (!args) { b200_set_error("forces: null argument block"); return B200SPH_EINVAL; }
+	const void *pos = args->pos, *vel = args->vel, *info = args->info;
+	const uint32_t *hash = args->hash, *cell_start = args->cell_start;
+	const uint16_t *neibs_list = args->neibs_list;
+	void *forces = args->forces; float *cfl = args->cfl;
+	void *rb_forces = args->rb_forces, *rb_torques = args->rb_torques;
+	const uint32_t num_particles = args->num_particles, from = args->from_particle, to = args->to_particle, cfl_offset = args->cfl_offset;
 	BodyOut bo;
-	bo.bodies = NULL; bo.rb_forces = (float4 *)rb_forces; bo.rb_torques = (float4 *)rb_torques;
+	bo.bodies = NULL; bo.rb_forces = (float4 *)rb_forces; bo.rb_torques = (float4 *)rb_torques; bo.xsph = NULL;
 	if (rb_forces) {
 		if (!rb_torques) { b200_set_error("forces: rb_forces without rb_torques"); return B200SPH_EINVAL; }
 		if (!ctx->have_bodies) { b200_set_error("forces: body output requested before setrbcg/setrbstart"); return B200SPH_EINVAL; }
 		bo.bodies = ctx->d_bodies;
 	}
+	const bool xsph = (ctx->hp.simflags & B200SPH_ENABLE_XSPH) != 0;
+	if (xsph && !args->xsph && to > from) { b200_set_error("forces: ENABLE_XSPH needs the xsph buffer"); return B200SPH_EINVAL; }
+	if (xsph) bo.xsph = (float4 *)args->xsph;
+	const bool brezzi = ctx->dp.densitydiffusiontype == B200SPH_RHODIFF_BREZZI;
+	if (brezzi && !args->dt_from_device && !(args->dt > 0) && to > from) { b200_set_error("forces: BREZZI density diffusion needs the command's dt"); return B200SPH_EINVAL; }
+	if (brezzi && args->dt_from_device && args->step != 1 && args->step != 2) { b200_set_error("forces: bad integrator step %d", args->step); return B200SPH_EINVAL; }
 	if (num_cfl_blocks) *num_cfl_blocks = 0;
 	if (to <= from) return B200SPH_OK;
 	if (!pos || !vel || !info || !hash || !cell_start || !neibs_list || !forces) { b200_set_error("forces: null buffer"); return B200SPH_EINVAL; }
@@ -709,6 +738,22 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 	const bool artvisc = d.turbmodel == B200SPH_TURB_ARTIFICIAL, laminar = !d.inviscid, multi = d.numFluids > 1;
 	gather_kernel_t gks[2]; coop_kernel_t ck; tile_kernel_t tk; size_t smem = 0;
 	const int cfg = ctx->tile_cfg;
+	// options served by the general (run-time switched) variant of the gather kernel only
+	const bool general = brezzi || xsph || (laminar && d.viscmodel != B200SPH_VISCMODEL_MORRIS);
+	DevParams dp_launch = ctx->dp;
+	dp_launch.cmd_dt = args->dt; dp_launch.cmd_step = args->step;
+	dp_launch.dev_state = args->dt_from_device ? ctx->d_step : NULL;
+	if (general) {
+		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
+		gather_kernel_t gk = wide ? forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, true>
+		                          : forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, false>;
+		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout((const void *)gk)));
+		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(dp_launch, (const float4 *)pos, (const float4 *)vel,
+			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
+		KERNEL_TRY();
+		if (num_cfl_blocks) *num_cfl_blocks = nblocks;
+		return B200SPH_OK;
+	}
 	switch (d.densitydiffusiontype) {
 	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
 	case B200SPH_RHODIFF_COLAGROSSI: pick_kernels<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;

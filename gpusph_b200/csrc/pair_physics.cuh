@@ -102,17 +102,38 @@ struct Central {
 	float rho, p_precalc, sspeed;
 	int fnum;
 	bool momentum;    // accumulate the momentum equation (false for DYN boundary particles without force feedback)
+	bool xsph;        // accumulate the XSPH mean velocity (fluid particle and ENABLE_XSPH; general variant only)
 };
+
+// RHODIFF template value of the GENERAL kernel variant: every physics option is read from DevParams at run time
+// (uniform branches). It serves the options that are not worth a specialised instantiation each — BREZZI diffusion,
+// the MONAGHAN / ESPANOL_REVENGA viscous models, XSPH — while the specialised variants stay lean for the
+// benchmarked configurations.
+#define RHODIFF_RUNTIME (-1)
+
+// average<avgop>, src/average.h:75-100
+__device__ __forceinline__ float average_op(const uint op, const float a, const float b)
+{
+	switch (op) {
+	case B200SPH_AVG_ARITHMETIC: return (a + b) * 0.5f;
+	case B200SPH_AVG_HARMONIC: return 2.0f * a * b / (a + b);
+	default: return sqrtf(a * b);
+	}
+}
 
 // One pair interaction. (rx,ry,rz) = relPos, r2 its squared length (already known to be inside the support),
 // np/nv = neighbour position|mass and velocity|rho~, ne = neighbour {P/rho^2, sound speed, density, fluid#}.
 // nfluid: the neighbour is a fluid particle (density diffusion applies), else a DYN boundary particle
-// (forces_kernel.def:1594-1606, 3717-3726).
+// (forces_kernel.def:1594-1606, 3717-3726). xs accumulates the XSPH mean velocity (general variant only).
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
 __device__ __forceinline__ void
-pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
-	const float r2, const float nmass, const float4 nv, const float4 ne, const bool nfluid, float4 &acc)
+pair_interaction_x(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
+	const float r2, const float nmass, const float4 nv, const float4 ne, const bool nfluid, float4 &acc, float3 &xs)
 {
+	constexpr bool GEN = RHODIFF == RHODIFF_RUNTIME;
+	const int rhodiff = GEN ? (int)P.densitydiffusiontype : RHODIFF;
+	const bool artvisc = GEN ? P.turbmodel == B200SPH_TURB_ARTIFICIAL : ARTVISC;
+	const bool laminar = GEN ? !P.inviscid : LAMINAR;
 	const int nfnum = MULTIFLUID ? __float_as_int(ne.w) : 0;
 	const float r = r2 * rsqrt_approx(r2 + 1e-30f);
 	// common_neib_data :1099-1130
@@ -127,19 +148,24 @@ pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, cons
 	// --- continuity: mass_continuity_div_vel_term :2140-2150 ---
 	float DrDt = mf * vel_dot_pos;
 	if (nfluid) {
-		if (RHODIFF == B200SPH_RHODIFF_FERRARI) {                   // :1614-1636
+		if (rhodiff == B200SPH_RHODIFF_FERRARI) {                   // :1614-1636
 			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
 			const float grav_corr = -gdot * (MULTIFLUID ? P.rho0[c.fnum] / P.sqC0[c.fnum] : k.grav_scale);
 			// ferraricor . relPos = max(c) (rho - rho_j + corr)/rho / r * r^2   (zero for r <= 1e-4 h)
 			const float s = (r > 1e-4f * k.h) ? fmaxf(c.sspeed, nsspeed) * (rho - nrho + grav_corr) * rcp_approx(rho) * r : 0.0f;
 			DrDt = fmaf(k.diff * mf, s, DrDt);
-		} else if (RHODIFF == B200SPH_RHODIFF_COLAGROSSI) {         // :1916-1951
+		} else if (rhodiff == B200SPH_RHODIFF_COLAGROSSI) {         // :1916-1951
 			if (!MULTIFLUID || c.fnum == nfnum) {
 				const float Pi = c.p_precalc * (rho * rho), Pj = np_precalc * (nrho * nrho);
 				const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
 				if (!(fabsf(Pi - Pj) < fabsf(gdot * rho)))
 					DrDt -= k.diff * (MULTIFLUID ? P.sscoeff[c.fnum] : 1.0f) * (nrho * rcp_approx(rho) - 1.0f) * mf;
 			}
+		} else if (GEN && rhodiff == B200SPH_RHODIFF_BREZZI) {      // :1765-1782
+			const float dt = P.dev_state ? (P.cmd_step == 1 ? P.dev_state->dt / 2 : P.dev_state->dt) : P.cmd_dt;
+			const float Pi = eos_pressure(P, c.vel.w, c.fnum), Pj = eos_pressure(P, nv.w, nfnum);
+			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
+			DrDt += k.diff * ((2.0f / (rho + nrho)) * (Pi - Pj) - gdot) * nmass / nrho * f * dt * 2.0f * rho;
 		}
 	}
 	acc.w += DrDt;                                                  // :2189
@@ -148,23 +174,83 @@ pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, cons
 		// compute_pressure_contrib, general formulation :2450-2466:  -(P_i/rho_i^2 + P_j/rho_j^2) m_j F r_ij
 		float coef = -(c.p_precalc + np_precalc) * mf;
 		// artificial viscosity :2744-2764, artvisc visc_kernel.cu:75-85
-		if (ARTVISC) {
+		if (artvisc) {
 			const float visc = vel_dot_pos * k.h_alpha * (c.sspeed + nsspeed) * rcp_approx((r2 + k.eps) * (rho + nrho));
 			coef = (vel_dot_pos < 0.0f) ? fmaf(visc, mf, coef) : coef;
 		}
 		float dvx = coef * rx, dvy = coef * ry, dvz = coef * rz;
-		// laminar (Morris) :2605-2625
-		if (LAMINAR) {
+		// laminar viscosity :2605-2625 (Morris / Monaghan), :2651-2678 (Espanol & Revenga)
+		if (laminar) {
 			const float vc = P.visccoeff[c.fnum], nvc = P.visccoeff[nfnum];
-			float visc;
-			if (P.compvisc == B200SPH_COMPVISC_KINEMATIC)
-				visc = P.is_const_visc ? vc * visc_avg_density(P, rho, nrho, nmass) : visc_avg_dyn(P, vc * rho, nvc * nrho, rho, nrho, nmass);
-			else
-				visc = P.is_const_visc ? 2 * nmass * vc / (rho * nrho) : visc_avg_dyn(P, vc, nvc, rho, nrho, nmass);
-			const float s = visc * f;
-			dvx = fmaf(s, rvx, dvx); dvy = fmaf(s, rvy, dvy); dvz = fmaf(s, rvz, dvz);
+			if (GEN && P.viscmodel == B200SPH_VISCMODEL_ESPANOL_REVENGA) {
+				// dynamic viscosities (get_dynamic_visc :276-289), bulk viscosities d_visc2coeff
+				const float pvisc = P.compvisc == B200SPH_COMPVISC_KINEMATIC ? vc * rho : vc;
+				const float nvisc = P.compvisc == B200SPH_COMPVISC_KINEMATIC ? nvc * nrho : nvc;
+				const float visc_thirds = average_op(P.viscavgop, pvisc, nvisc) / 3;
+				const float bulk = average_op(P.viscavgop, P.visc2coeff[c.fnum], P.visc2coeff[nfnum]);
+				const float cf = nmass / (rho * nrho) * f;            // viscous_volume_coefficient :2575-2580
+				const float pos_den = r2 + k.eps;
+				const float a = 5 * visc_thirds - bulk, b = 5 * (visc_thirds + bulk) * vel_dot_pos / pos_den;
+				dvx += cf * (a * rvx + b * rx); dvy += cf * (a * rvy + b * ry); dvz += cf * (a * rvz + b * rz);
+			} else {
+				float visc;
+				if (P.compvisc == B200SPH_COMPVISC_KINEMATIC)
+					visc = P.is_const_visc ? vc * visc_avg_density(P, rho, nrho, nmass) : visc_avg_dyn(P, vc * rho, nvc * nrho, rho, nrho, nmass);
+				else
+					visc = P.is_const_visc ? 2 * nmass * vc / (rho * nrho) : visc_avg_dyn(P, vc, nvc, rho, nrho, nmass);
+				const float s = visc * f;
+				if (GEN && P.viscmodel == B200SPH_VISCMODEL_MONAGHAN) {
+					// viscous_vector_component<MONAGHAN> :2534-2559: along relPos, only for approaching particles
+					const float m = vel_dot_pos < 0 ? P.monaghanViscCoeff * vel_dot_pos / (r2 + k.eps) : 0.0f;
+					dvx = fmaf(s, m * rx, dvx); dvy = fmaf(s, m * ry, dvy); dvz = fmaf(s, m * rz, dvz);
+				} else {
+					dvx = fmaf(s, rvx, dvx); dvy = fmaf(s, rvy, dvy); dvz = fmaf(s, rvz, dvz);
+				}
+			}
+		}
+		// compute_mean_vel :2986-2992 (fluid central, fluid neighbour, ENABLE_XSPH)
+		if (GEN && nfluid && c.xsph) {
+			float w = fmaf(-0.5f * r, k.inv_h, 1.0f);                 // W<WENDLAND>, sph_core.cu:104-117
+			w *= w; w *= w;
+			w *= fmaf(2.0f * r, k.inv_h, 1.0f);
+			const float s = nmass * w * P.wcoeff_wendland / (rho + nrho);
+			xs.x -= s * rvx; xs.y -= s * rvy; xs.z -= s * rvz;
 		}
 		acc.x += dvx; acc.y += dvy; acc.z += dvz;                   // :3590
+	}
+}
+
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
+__device__ __forceinline__ void
+pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
+	const float r2, const float nmass, const float4 nv, const float4 ne, const bool nfluid, float4 &acc)
+{
+	float3 xs = make_float3(0.f, 0.f, 0.f);
+	pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, nmass, nv, ne, nfluid, acc, xs);
+}
+
+// Lennard-Jones repulsion and wall friction of the geometric planes on a fluid particle: GeometryForce / PlaneForce /
+// LJForce, src/cuda/forces_kernel.cu:94-204; PlaneDistance src/cuda/geom_core.cu:65-85.
+__device__ __forceinline__ void plane_forces(const DevParams &P, const int3 gp, const float4 pos, const float4 vel,
+	const float dynvisc, float4 &acc)
+{
+	for (uint i = 0; i < P.numplanes; ++i) {
+		const float nx = P.planeNormal[i][0], ny = P.planeNormal[i][1], nz = P.planeNormal[i][2];
+		// globalDistance(gridPos, pos, plane.gridPos, plane.pos), cellgrid.cuh:152-160
+		const float dx = (float)(gp.x - P.planeGridPos[i][0]) * P.cellSize[0] + (pos.x - P.planePos[i][0]);
+		const float dy = (float)(gp.y - P.planeGridPos[i][1]) * P.cellSize[1] + (pos.y - P.planePos[i][1]);
+		const float dz = (float)(gp.z - P.planeGridPos[i][2]) * P.cellSize[2] + (pos.z - P.planePos[i][2]);
+		const float r = fabsf(dx * nx + dy * ny + dz * nz);
+		if (r < P.r0) {
+			const float q = P.r0 / r;
+			const float DvDt = P.dcoeff * (__powf(q, P.p1coeff) - __powf(q, P.p2coeff)) / (r * r);   // r <= r0 always here
+			const float px = nx * r, py = ny * r, pz = nz * r;         // relPos = normal * r
+			acc.x += DvDt * px; acc.y += DvDt * py; acc.z += DvDt * pz;
+			// tangential velocity v_t = vel - dot(vel, relPos)/r * relPos/r, friction -mu A / (m r)
+			const float vn = (vel.x * px + vel.y * py + vel.z * pz) / r;
+			const float coeff = -dynvisc * P.partsurf / (pos.w * r);
+			acc.x += coeff * (vel.x - vn * px / r); acc.y += coeff * (vel.y - vn * py / r); acc.z += coeff * (vel.z - vn * pz / r);
+		}
 	}
 }
 
@@ -175,15 +261,22 @@ pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, cons
 struct BodyOut {
 	const BodyData *bodies;     // NULL: no body output requested
 	float4 *rb_forces, *rb_torques;
+	float4 *xsph;               // XSPH mean-velocity output (general variant, ENABLE_XSPH), else NULL
 };
 
 __device__ __forceinline__ float finalize_particle(const DevParams &P, const int type, const int fnum, const float sspeed,
-	const ushort4 info, const float4 pos, const uint cellHash, const BodyOut &bo, float4 &acc)
+	const ushort4 info, const float4 pos, const float4 vel, const float rho, const uint cellHash, const BodyOut &bo, float4 &acc)
 {
 	acc.w /= P.rho0[fnum];
 	float cfl_term = 0.0f;
 	if (type == PT_FLUID) {
 		acc.x += P.gravity[0]; acc.y += P.gravity[1]; acc.z += P.gravity[2];
+		if (P.numplanes) {
+			// viscous_plane_coefficient :3103-3113: free slip when inviscid, else the laminar dynamic viscosity
+			const float dynvisc = P.inviscid ? 0.0f :
+				(P.compvisc == B200SPH_COMPVISC_KINEMATIC ? P.visccoeff[fnum] * rho : P.visccoeff[fnum]);
+			plane_forces(P, grid_pos(P, cellHash), pos, vel, dynvisc, acc);          // :4105-4110
+		}
 		cfl_term = fmaxf(sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z), sspeed * sspeed / P.slength);
 	}
 	if (bo.bodies && (info.x & B200SPH_FG_COMPUTE_FORCE) && type != PT_VERTEX) {

@@ -39,6 +39,14 @@ BUFFER_COMPACT_DEV_MAP = "BUFFER_COMPACT_DEV_MAP"
 BUFFER_RB_FORCES = "BUFFER_RB_FORCES"
 BUFFER_RB_TORQUES = "BUFFER_RB_TORQUES"
 BUFFER_RB_KEYS = "BUFFER_RB_KEYS"
+BUFFER_XSPH = "BUFFER_XSPH"
+BUFFER_TKE = "BUFFER_TKE"
+BUFFER_EPSILON = "BUFFER_EPSILON"
+
+# filter / post-process types (src/particledefine.h: FilterType, PostProcessType)
+SHEPARD_FILTER = "SHEPARD_FILTER"
+MLS_FILTER = "MLS_FILTER"
+TESTPOINTS = "TESTPOINTS"
 
 
 class BufferList(dict):
@@ -176,16 +184,32 @@ class ForcesEngine:
     def round_particles(self, n: int) -> int:
         return int(self.lib.b200sph_round_particles(n))
 
+    def setplanes(self, planes) -> None:
+        """planes: sequence of (normal[3], gridPos[3], pos[3]) like plane_t (src/planes.h:42-46)."""
+        import numpy as np
+        n = len(planes)
+        nrm = np.ascontiguousarray(np.asarray([p[0] for p in planes], dtype=np.float32).reshape(n, 3))
+        gp = np.ascontiguousarray(np.asarray([p[1] for p in planes], dtype=np.int32).reshape(n, 3))
+        pp = np.ascontiguousarray(np.asarray([p[2] for p in planes], dtype=np.float32).reshape(n, 3))
+        capi.check(self.lib.b200sph_set_planes(self.ctx.handle, nrm.ctypes.data_as(C.POINTER(C.c_float)),
+                                               gp.ctypes.data_as(C.POINTER(C.c_int)), pp.ctypes.data_as(C.POINTER(C.c_float)), n))
+
     def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, fromParticle: int,
-                  toParticle: int, cflOffset: int = 0, compute_object_forces: bool = False) -> int:
+                  toParticle: int, cflOffset: int = 0, compute_object_forces: bool = False,
+                  step: int = 0, dt: float = 0.0, dt_from_device: bool = False) -> int:
+        """step / dt = the command's integrator step and dt (src/GPUWorker.cc:1931-1932), read by BREZZI diffusion only;
+        dt_from_device: take dt from the context's device-resident record instead."""
         nblocks = C.c_uint32()
-        capi.check(self.lib.b200sph_forces_bodies(
-            self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
-            bufread.ptr(BUFFER_HASH), bufread.ptr(BUFFER_CELLSTART), bufread.ptr(BUFFER_NEIBSLIST),
-            bufwrite.ptr(BUFFER_FORCES), bufwrite.ptr(BUFFER_CFL, False),
-            bufwrite.ptr(BUFFER_RB_FORCES) if compute_object_forces else 0,
-            bufwrite.ptr(BUFFER_RB_TORQUES) if compute_object_forces else 0,
-            numParticles, fromParticle, toParticle, cflOffset, C.byref(nblocks)))
+        a = capi.ForcesArgs()
+        a.pos, a.vel, a.info = bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO)
+        a.hash, a.cell_start, a.neibs_list = bufread.ptr(BUFFER_HASH), bufread.ptr(BUFFER_CELLSTART), bufread.ptr(BUFFER_NEIBSLIST)
+        a.forces, a.cfl = bufwrite.ptr(BUFFER_FORCES), bufwrite.ptr(BUFFER_CFL, False)
+        a.rb_forces = bufwrite.ptr(BUFFER_RB_FORCES) if compute_object_forces else 0
+        a.rb_torques = bufwrite.ptr(BUFFER_RB_TORQUES) if compute_object_forces else 0
+        a.xsph = bufwrite.ptr(BUFFER_XSPH, False)
+        a.num_particles, a.from_particle, a.to_particle, a.cfl_offset = numParticles, fromParticle, toParticle, cflOffset
+        a.dt, a.step, a.dt_from_device = dt, step, 1 if dt_from_device else 0
+        capi.check(self.lib.b200sph_forces_ex(self.ctx.handle, C.byref(a), C.byref(nblocks)))
         return nblocks.value
 
     # ---- moving / force-feedback bodies (src/engine_forces.h:62-74) ----
@@ -263,10 +287,10 @@ class IntegrationEngine:
 
     def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
                   dt: float, step: int) -> None:
-        capi.check(self.lib.b200sph_euler(
+        capi.check(self.lib.b200sph_euler_ex(
             self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
-            bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES),
-            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, dt, step))
+            bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES), bufread.ptr(BUFFER_XSPH, False),
+            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, dt, step, 0))
 
 
     # ---- moving bodies (src/engine_integration.h:54-68) ----
@@ -292,10 +316,62 @@ class IntegrationEngine:
     def basicstep_async(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
                         step: int) -> None:
         """basicstep with dt taken from the context's device-resident record (no host round trip)."""
-        capi.check(self.lib.b200sph_euler_async(
+        capi.check(self.lib.b200sph_euler_ex(
             self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
-            bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES),
-            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, step))
+            bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES), bufread.ptr(BUFFER_XSPH, False),
+            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, 0.0, step, 1))
+
+
+class FilterEngine:
+    """AbstractFilterEngine (src/engine_filter.h:40-83) for SHEPARD_FILTER / MLS_FILTER
+    (src/cuda/forces.cu:1026-1146): runs every `frequency` iterations, reads VEL of bufread, writes VEL of bufwrite."""
+
+    def __init__(self, ctx: DeviceContext, filtertype: str, frequency: int):
+        if filtertype not in (SHEPARD_FILTER, MLS_FILTER):
+            raise ValueError(f"unknown filter type {filtertype}")          # reference: std::invalid_argument
+        self.ctx, self.lib = ctx, ctx.lib
+        self.filtertype = filtertype
+        self._frequency = int(frequency)
+
+    def set_frequency(self, frequency: int) -> None:
+        self._frequency = int(frequency)
+
+    def frequency(self) -> int:
+        return self._frequency
+
+    def process(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
+                slength: float = 0.0, influenceradius: float = 0.0) -> None:
+        fn = self.lib.b200sph_filter_shepard if self.filtertype == SHEPARD_FILTER else self.lib.b200sph_filter_mls
+        capi.check(fn(self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufwrite.ptr(BUFFER_VEL),
+                      bufread.ptr(BUFFER_INFO), bufread.ptr(BUFFER_HASH), bufread.ptr(BUFFER_CELLSTART),
+                      bufread.ptr(BUFFER_NEIBSLIST), numParticles, particleRangeEnd))
+
+
+class PostProcessEngine:
+    """AbstractPostProcessEngine (src/engine_postprocess.h:47-116) for TESTPOINTS (src/cuda/post_process.cu:148-216):
+    VEL (and TKE / EPSILON when present) of the test points are updated in place in bufwrite."""
+
+    def __init__(self, ctx: DeviceContext, pptype: str = TESTPOINTS, options: int = 0):
+        if pptype != TESTPOINTS:
+            raise capi.B200Unsupported(f"post-processing {pptype} is out of scope (SURVEY.md section 8)")
+        self.ctx, self.lib = ctx, ctx.lib
+        self.options = options
+
+    def get_options(self) -> int:
+        return self.options
+
+    def get_updated_buffers(self):
+        return (BUFFER_VEL, BUFFER_TKE, BUFFER_EPSILON)
+
+    def get_written_buffers(self):
+        return ()
+
+    def process(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
+                deviceIndex: int = 0, gdata=None) -> None:
+        capi.check(self.lib.b200sph_testpoints(
+            self.ctx.handle, bufread.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), bufwrite.ptr(BUFFER_TKE, False),
+            bufwrite.ptr(BUFFER_EPSILON, False), bufread.ptr(BUFFER_INFO), bufread.ptr(BUFFER_HASH),
+            bufread.ptr(BUFFER_CELLSTART), bufread.ptr(BUFFER_NEIBSLIST), numParticles, particleRangeEnd))
 
 
 class SimFramework:
@@ -306,6 +382,14 @@ class SimFramework:
         self.neibsEngine = NeibsEngine(self.ctx)
         self.forcesEngine = ForcesEngine(self.ctx)
         self.integrationEngine = IntegrationEngine(self.ctx)
+
+    def newFilterEngine(self, filtertype: str, frequency: int) -> FilterEngine:
+        """src/cuda/cudasimframework.cu:236-245"""
+        return FilterEngine(self.ctx, filtertype, frequency)
+
+    def newPostProcessEngine(self, pptype: str, options: int = 0) -> PostProcessEngine:
+        """src/cuda/cudasimframework.cu:210-234"""
+        return PostProcessEngine(self.ctx, pptype, options)
 
     @property
     def params(self) -> capi.Params:

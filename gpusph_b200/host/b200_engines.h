@@ -8,8 +8,10 @@
  * that pull raw device pointers out of the BufferLists exactly like the reference's CUDA engines do
  * (src/cuda/buildneibs.cu:166-171, src/cuda/forces.cu:901-932, src/cuda/euler.cu:330-372) and forward them
  * to the C ABI of include/b200sph.h. Error codes are turned back into the exceptions the reference throws.
- * Methods that belong to out-of-scope subsystems (SA boundaries, DEM, density summation, repacking, rigid
- * bodies: SURVEY.md section 8 rows "out of scope" / "next") throw std::runtime_error — they never fall back.
+ * FilterEngine (SHEPARD_FILTER / MLS_FILTER, src/engine_filter.h:40-83) and TestpointsEngine (TESTPOINTS,
+ * src/engine_postprocess.h:47-116) bind the two neighbour-list consumers DamBreak3D / Poiseuille enable next to the forces.
+ * Methods that belong to out-of-scope subsystems (SA boundaries, DEM, density summation, repacking: SURVEY.md
+ * section 8 rows "out of scope") throw std::runtime_error — they never fall back.
  *
  * Engines are shared by all worker threads (one SimFramework per process, SURVEY.md section 8b "Threading"), so the
  * per-device context lives in a map keyed by the CUDA device of the calling thread.
@@ -24,11 +26,15 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include <cfloat>
 
 #include "engine_neibs.h"
 #include "engine_forces.h"
 #include "engine_integration.h"
+#include "engine_filter.h"
+#include "engine_postprocess.h"
+#include "simframework.h"
 #include "simparams.h"
 #include "physparams.h"
 #include "buffer.h"
@@ -109,6 +115,12 @@ public:
 		p.max_sound_speed_cfl = max_ss * 1.1f;                    // src/GPUWorker.cc:3010-3011
 		p.max_kinvisc = sp->rheologytype == INVISCID ? 0.0f : max_kin;
 		p.dtadapt = (sp->simflags & ENABLE_DTADAPT) ? 1 : 0;
+		// ENABLE_DTADAPT, ENABLE_XSPH, ENABLE_PLANES, ENABLE_DEM have the reference's bit values (src/simflags.h:71-86)
+		p.simflags = (uint32_t)(sp->simflags & (ENABLE_DTADAPT | ENABLE_XSPH | ENABLE_PLANES | ENABLE_DEM));
+		p.epsxsph = pp->epsxsph;
+		p.monaghan_visc_coeff = pp->monaghan_visc_coeff;
+		for (uint32_t f = 0; f < p.num_fluids; ++f) p.visc2coeff[f] = pp->visc2coeff[f];
+		p.r0 = pp->r0; p.dcoeff = pp->dcoeff; p.p1coeff = pp->p1coeff; p.p2coeff = pp->p2coeff; p.partsurf = pp->partsurf;
 		check(b200sph_validate(&p));      // unsupported option combinations fail here, loudly
 		m_params = p;
 		m_have_params = true;
@@ -237,7 +249,18 @@ public:
 
 	void getconstants(PhysParams *pp) override { if (m_ref) m_ref->getconstants(pp); }
 
-	void setplanes(PlaneList const& planes) override { if (!planes.empty()) unsupported("geometric planes (ENABLE_PLANES)"); }
+	void setplanes(PlaneList const& planes) override
+	{
+		if (m_ref) m_ref->setplanes(planes);
+		// plane_t = { float3 normal; int3 gridPos; float3 pos; } (src/planes.h:42-46)
+		std::vector<float> nrm, pos; std::vector<int> gp;
+		for (auto const& pl : planes) {
+			nrm.push_back(pl.normal.x); nrm.push_back(pl.normal.y); nrm.push_back(pl.normal.z);
+			gp.push_back(pl.gridPos.x); gp.push_back(pl.gridPos.y); gp.push_back(pl.gridPos.z);
+			pos.push_back(pl.pos.x); pos.push_back(pl.pos.y); pos.push_back(pl.pos.z);
+		}
+		check(b200sph_set_planes(m_c->get(), nrm.data(), gp.data(), pos.data(), (int)planes.size()));
+	}
 	void setgravity(float3 const& g) override
 	{ if (m_ref) m_ref->setgravity(g); const float v[3] = { g.x, g.y, g.z }; check(b200sph_set_gravity(m_c->get(), v)); }
 	// moving / force-feedback bodies (src/cuda/forces.cu:430-447, 967-1003)
@@ -269,19 +292,25 @@ public:
 		const float, const float) override { unsupported("density-sum density diffusion"); }
 
 	uint basicstep(const BufferList& bufread, BufferList& bufwrite, uint numParticles, uint fromParticle, uint toParticle,
-		float, float, float, float, const float, uint*, uint cflOffset, const RunMode run_mode, const int, const float,
+		float, float, float, float, const float, uint*, uint cflOffset, const RunMode run_mode, const int step, const float dt,
 		const bool compute_object_forces) override
 	{
 		if (run_mode == REPACK) unsupported("repacking");
 		uint32_t nblocks = 0;
+		(void)compute_object_forces;
+		b200sph_forces_args a;
+		memset(&a, 0, sizeof(a));
+		a.pos = bufread.getData<BUFFER_POS>(); a.vel = bufread.getData<BUFFER_VEL>(); a.info = bufread.getData<BUFFER_INFO>();
+		a.hash = bufread.getData<BUFFER_HASH>(); a.cell_start = bufread.getData<BUFFER_CELLSTART>();
+		a.neibs_list = bufread.getData<BUFFER_NEIBSLIST>();
+		a.forces = bufwrite.getData<BUFFER_FORCES>(); a.cfl = bufwrite.getData<BUFFER_CFL>();
 		// the reference's finalize kernel scatters body forces whenever the particle carries FG_COMPUTE_FORCE
 		// (forces_kernel.def:4116-4141); the RB buffers exist exactly when there are force-feedback bodies
-		float4 *rbf = bufwrite.getData<BUFFER_RB_FORCES>(), *rbt = bufwrite.getData<BUFFER_RB_TORQUES>();
-		(void)compute_object_forces;
-		check(b200sph_forces_bodies(m_c->get(), bufread.getData<BUFFER_POS>(), bufread.getData<BUFFER_VEL>(),
-			bufread.getData<BUFFER_INFO>(), bufread.getData<BUFFER_HASH>(), bufread.getData<BUFFER_CELLSTART>(),
-			bufread.getData<BUFFER_NEIBSLIST>(), bufwrite.getData<BUFFER_FORCES>(), bufwrite.getData<BUFFER_CFL>(),
-			rbf, rbt, numParticles, fromParticle, toParticle, cflOffset, &nblocks));
+		a.rb_forces = bufwrite.getData<BUFFER_RB_FORCES>(); a.rb_torques = bufwrite.getData<BUFFER_RB_TORQUES>();
+		a.xsph = bufwrite.getData<BUFFER_XSPH>();           // exists iff ENABLE_XSPH (src/GPUWorker.cc:135-136)
+		a.num_particles = numParticles; a.from_particle = fromParticle; a.to_particle = toParticle; a.cfl_offset = cflOffset;
+		a.dt = dt; a.step = step;                           // read by BREZZI diffusion only
+		check(b200sph_forces_ex(m_c->get(), &a, &nblocks));
 		return nblocks;
 	}
 
@@ -333,13 +362,93 @@ public:
 		const float dt, const int step, const float, const float, const float, const RunMode run_mode) override
 	{
 		if (run_mode == REPACK) unsupported("repacking");
-		check(b200sph_euler(m_c->get(), bufread.getData<BUFFER_POS>(), bufread.getData<BUFFER_VEL>(),
+		check(b200sph_euler_ex(m_c->get(), bufread.getData<BUFFER_POS>(), bufread.getData<BUFFER_VEL>(),
 			bufread.getData<BUFFER_INFO>(), bufread.getData<BUFFER_HASH>(), bufread.getData<BUFFER_FORCES>(),
-			bufwrite.getData<BUFFER_POS>(), bufwrite.getData<BUFFER_VEL>(), numParticles, particleRangeEnd, dt, step));
+			bufread.getData<BUFFER_XSPH>(),
+			bufwrite.getData<BUFFER_POS>(), bufwrite.getData<BUFFER_VEL>(), numParticles, particleRangeEnd, dt, step, 0));
 	}
 
 	void disableFreeSurfParts(float4*, const particleinfo*, const uint, const uint) override { unsupported("repacking"); }
 };
+
+//! SHEPARD_FILTER / MLS_FILTER (src/cuda/forces.cu:1026-1146)
+class FilterEngine : public AbstractFilterEngine
+{
+	std::shared_ptr<Contexts> m_c;
+	FilterType m_type;
+public:
+	FilterEngine(std::shared_ptr<Contexts> c, FilterType type, uint frequency) :
+		AbstractFilterEngine(frequency), m_c(c), m_type(type)
+	{
+		if (type != SHEPARD_FILTER && type != MLS_FILTER)
+			throw std::invalid_argument("B200 filter engine: unknown filter type");
+	}
+
+	void setconstants() override {}
+	void getconstants() override {}
+
+	void process(const BufferList& bufread, BufferList& bufwrite, uint numParticles, uint particleRangeEnd,
+		float, float) override
+	{
+		auto fn = m_type == SHEPARD_FILTER ? b200sph_filter_shepard : b200sph_filter_mls;
+		check(fn(m_c->get(), bufread.getData<BUFFER_POS>(), bufread.getData<BUFFER_VEL>(), bufwrite.getData<BUFFER_VEL>(),
+			bufread.getData<BUFFER_INFO>(), bufread.getData<BUFFER_HASH>(), bufread.getData<BUFFER_CELLSTART>(),
+			bufread.getData<BUFFER_NEIBSLIST>(), numParticles, particleRangeEnd));
+	}
+};
+
+//! TESTPOINTS post-processing (src/cuda/post_process.cu:148-216): VEL / TKE / EPSILON updated in place
+class TestpointsEngine : public AbstractPostProcessEngine
+{
+	std::shared_ptr<Contexts> m_c;
+	AbstractPostProcessEngine *m_ref;   // stock engine: only its setconstants is forwarded (GPUWorker uploads the
+	                                    // post-processing constants through the FIRST engine of the set, GPUWorker.cc:3000-3001)
+public:
+	TestpointsEngine(std::shared_ptr<Contexts> c, flag_t options = NO_FLAGS, AbstractPostProcessEngine *ref = NULL) :
+		AbstractPostProcessEngine(options), m_c(c), m_ref(ref) {}
+
+	void setconstants(const SimParams *sp, const PhysParams *pp, idx_t const& n) const override
+	{ if (m_ref) m_ref->setconstants(sp, pp, n); }
+	void getconstants() override {}
+
+	void process(const BufferList& bufread, BufferList& bufwrite, uint numParticles, uint particleRangeEnd,
+		uint, const GlobalData * const) override
+	{
+		check(b200sph_testpoints(m_c->get(), bufread.getData<BUFFER_POS>(), bufwrite.getData<BUFFER_VEL>(),
+			bufwrite.getData<BUFFER_TKE>(), bufwrite.getData<BUFFER_EPSILON>(), bufread.getData<BUFFER_INFO>(),
+			bufread.getData<BUFFER_HASH>(), bufread.getData<BUFFER_CELLSTART>(), bufread.getData<BUFFER_NEIBSLIST>(),
+			numParticles, particleRangeEnd));
+	}
+
+	flag_t get_written_buffers() const override { return NO_FLAGS; }
+	flag_t get_updated_buffers() const override { return BUFFER_VEL | BUFFER_TKE | BUFFER_EPSILON; }
+
+	void hostAllocate(const GlobalData * const) override {}
+	void hostProcess(const GlobalData * const) override {}
+	void write(WriterMap, double) override {}
+};
+
+//! The framework's filter set with SHEPARD / MLS replaced by ours (same frequencies). GPUWorker keeps a reference to
+//! the set (src/GPUWorker.h:79), hence the static storage.
+inline FilterEngineSet const& filters(std::shared_ptr<Contexts> c, FilterEngineSet const& stock)
+{
+	static FilterEngineSet ours;
+	ours.clear();
+	for (auto const& kv : stock)
+		ours[kv.first] = (kv.first == SHEPARD_FILTER || kv.first == MLS_FILTER) ?
+			new FilterEngine(c, kv.first, kv.second->frequency()) : kv.second;
+	return ours;
+}
+
+//! The framework's post-processing set with TESTPOINTS replaced by ours
+inline PostProcessEngineSet const& postprocess(std::shared_ptr<Contexts> c, PostProcessEngineSet const& stock)
+{
+	static PostProcessEngineSet ours;
+	ours.clear();
+	for (auto const& kv : stock)
+		ours[kv.first] = kv.first == TESTPOINTS ? new TestpointsEngine(c, kv.second->get_options(), kv.second) : kv.second;
+	return ours;
+}
 
 } // namespace b200
 #endif

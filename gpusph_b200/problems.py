@@ -49,7 +49,9 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
                 density_diff_coeff: float | None = None,
                 rheology: int = capi.RHEOLOGY_INVISCID, turbmodel: int = capi.TURB_ARTIFICIAL,
                 kinvisc: float = 0.0, viscavgop: int = capi.AVG_ARITHMETIC,
-                artvisccoeff: float = 0.3, dtadaptfactor: float = 0.3, fluids=None) -> capi.Params:
+                artvisccoeff: float = 0.3, dtadaptfactor: float = 0.3, fluids=None,
+                viscmodel: int = capi.VISCMODEL_MORRIS, compvisc: int = capi.COMPVISC_KINEMATIC, bulkvisc: float = 0.0,
+                simflags: int = capi.ENABLE_DTADAPT, epsxsph: float = 0.5) -> capi.Params:
     """Build b200sph_params the way ProblemCore + the engines' setconstants derive them."""
     p = capi.Params()
     p.abi_version = capi.ABI_VERSION
@@ -77,8 +79,8 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
     p.boundarytype = capi.DYN_BOUNDARY
     p.rheologytype = rheology
     p.turbmodel = turbmodel
-    p.compvisc = capi.COMPVISC_KINEMATIC
-    p.viscmodel = capi.VISCMODEL_MORRIS
+    p.compvisc = compvisc
+    p.viscmodel = viscmodel
     p.viscavgop = viscavgop
     p.is_const_visc = 1 if rheology == capi.RHEOLOGY_NEWTONIAN else 0   # single fluid, Newtonian, no k-eps (visc_spec.h:262)
     p.slength = slength
@@ -114,7 +116,17 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
     p.epsartvisc = np.float32(0.01 * float(slength) * float(slength))   # ProblemCore.cc:160-161
     p.max_sound_speed_cfl = np.float32(np.float32(c0) * 1.1)     # GPUWorker.cc:3010-3011
     p.max_kinvisc = kinvisc if rheology != capi.RHEOLOGY_INVISCID else 0.0
-    p.dtadapt = 1
+    p.dtadapt = 1 if simflags & capi.ENABLE_DTADAPT else 0
+    p.simflags = simflags
+    p.epsxsph = epsxsph                                         # physparams.h:409
+    p.monaghan_visc_coeff = 10.0                                # 2(d+2), physparams.h:396
+    for f in range(p.num_fluids):
+        p.visc2coeff[f] = (fluids[f - 1].get("bulkvisc", bulkvisc) if f else bulkvisc)
+    # Lennard-Jones defaults of ProblemCore::initialize (src/ProblemCore.cc:121-140, physparams.h:398-403)
+    p.r0 = np.float32(deltap)
+    p.dcoeff = np.float32(5.0 * math.sqrt(sum(float(g) ** 2 for g in gravity)))
+    p.p1coeff, p.p2coeff = 12.0, 6.0
+    p.partsurf = 0.0
     return p
 
 
@@ -204,7 +216,7 @@ def _box_shell(lo, hi, dp, layers):
 
 
 def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_COLAGROSSI, layers: int = 3,
-                     alloc_extra: float = 0.0, width_scale: int = 1, obstacle: bool = False, **kw):
+                     alloc_extra: float = 0.0, width_scale: int = 1, obstacle: bool = False, testpoints: int = 0, **kw):
     """DamBreak3D-like setup (src/problems/DamBreak3D.cu:36-205 with --num_obstacles 0): a 1.6 x 0.67 x 0.6 m
     tank lined with `layers` layers of DYN boundary particles, a 0.4 m long, 0.4 m high water column,
     Wendland kernel, artificial viscosity, c0 = 20, gamma = 7. Fill order/ids are ours, not the reference's
@@ -230,12 +242,18 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
         blo = np.array([0.9 - side / 2, dim[1] / 2 - side / 2, bd])
         body = _box_shell(blo, blo + np.array([side, side, dim[2] - 2 * bd]), dp, min(layers, 2))
     nob = body.shape[0]
-    N = nfl + nb + nob
+    # test points (src/problems/DamBreak3D.cu:201-213): `testpoints` per probe column at 0.25, 0.4, 0.75, 0.9 of the length
+    tp = np.zeros((0, 3))
+    if testpoints > 0:
+        dist = dim[2] / (testpoints + 1)
+        tp = np.array([[fx * dim[0], dim[1] / 2.0, (t + 1) * dist / 2.0] for fx in (0.25, 0.4, 0.75, 0.9) for t in range(testpoints)])
+    ntp = tp.shape[0]
+    N = nfl + nb + nob + ntp
     rho0 = 1000.0
     c0 = 20.0
     params = make_params(origin=np.zeros(3), size=dim, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
                          rho0=rho0, c0=c0, densitydiffusion=densitydiffusion, **kw)
-    gpos = np.concatenate([fluid, wall, body], axis=0)
+    gpos = np.concatenate([fluid, wall, body, tp], axis=0)
     mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
     pos, hashv = localpos_and_hash(params, gpos, mass)
     vel = np.zeros((N, 4), dtype=np.float32)
@@ -250,13 +268,14 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
     info = np.concatenate([make_info(capi.PT_FLUID, ids=np.arange(nfl)),
                            make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, nfl + nb)),
                            make_info(capi.PT_BOUNDARY, flags=capi.FG_MOVING_BOUNDARY | capi.FG_COMPUTE_FORCE, obj=1,
-                                     ids=np.arange(nfl + nb, N))], axis=0)
+                                     ids=np.arange(nfl + nb, nfl + nb + nob)),
+                           make_info(capi.PT_TESTPOINT, ids=np.arange(nfl + nb + nob, N))], axis=0)
     return params, ParticleArrays(pos, vel, info, hashv)
 
 
 def poiseuille_problem(ppH: int = 32, *, lz: float = 1.0, kinvisc: float = 0.1, driving_force: float = 0.05,
                        rho0: float = 1.0, viscavgop: int = capi.AVG_ARITHMETIC, steady_init: bool = True,
-                       layers: int = 3, alloc_extra: float = 0.0):
+                       layers: int = 3, alloc_extra: float = 0.0, **kw):
     """Plane Poiseuille flow like src/problems/Poiseuille.inc:60-232: fluid between two DYN-boundary plates at
     z = +-lz/2, periodic in x and y, Newtonian laminar (Morris) viscosity with constant kinematic viscosity,
     driven by a body force along x. Analytic steady profile (Poiseuille.inc:187-232, scripts/validate-poiseuille.py:32-37):
@@ -289,7 +308,7 @@ def poiseuille_problem(ppH: int = 32, *, lz: float = 1.0, kinvisc: float = 0.1, 
     N = nfl + nb
     params = make_params(origin=origin, size=size, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
                          rho0=rho0, c0=c0, gravity=(driving_force, 0.0, 0.0), periodic=capi.PERIODIC_X | capi.PERIODIC_Y,
-                         rheology=capi.RHEOLOGY_NEWTONIAN, turbmodel=capi.TURB_LAMINAR, kinvisc=kinvisc, viscavgop=viscavgop)
+                         rheology=capi.RHEOLOGY_NEWTONIAN, turbmodel=capi.TURB_LAMINAR, kinvisc=kinvisc, viscavgop=viscavgop, **kw)
     gpos = np.concatenate([fluid, wall], axis=0)
     mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
     pos, hashv = localpos_and_hash(params, gpos, mass)

@@ -13,7 +13,7 @@ import torch
 from . import capi
 from .engines import (BUFFER_CELLEND, BUFFER_CELLSTART, BUFFER_CFL, BUFFER_CFL_TEMP, BUFFER_COMPACT_DEV_MAP,
                       BUFFER_FORCES, BUFFER_HASH, BUFFER_INFO, BUFFER_NEIBSLIST, BUFFER_PARTINDEX, BUFFER_POS,
-                      BUFFER_VEL, BufferList, SimFramework)
+                      BUFFER_VEL, BUFFER_XSPH, TESTPOINTS, BufferList, SimFramework)
 from .problems import ParticleArrays, initial_dt
 
 
@@ -30,7 +30,9 @@ class Worker:
     def __init__(self, params: capi.Params, particles: ParticleArrays, device=None, *,
                  buildneibsfreq: int = 10, clobber: bool = False, fixed_dt: float | None = None,
                  compact_dev_map: np.ndarray | None = None, start_iteration: int = 0, dt: float | None = None,
-                 device_dt: bool = True):
+                 device_dt: bool = True, filters: dict | None = None, planes=None):
+        """filters: {SHEPARD_FILTER | MLS_FILTER: frequency in iterations} (Problem::addFilter);
+        planes: [(normal, gridPos, pos)] for ENABLE_PLANES (AbstractForcesEngine::setplanes)."""
         self.framework = SimFramework(params, device)
         self.params = self.framework.params
         self.device = self.framework.ctx.device
@@ -80,6 +82,12 @@ class Worker:
         self._stale = False
         if self.device_dt:
             self.forces.step_set_dt(self._dt)
+        # XSPH mean velocity (BUFFER_XSPH exists iff ENABLE_XSPH, src/GPUWorker.cc:135-136)
+        self.xsph = f4() if self.params.simflags & capi.ENABLE_XSPH else None
+        self.filters = [(self.framework.newFilterEngine(k, v), int(v)) for k, v in (filters or {}).items() if v > 0]
+        self.postproc = self.framework.newPostProcessEngine(TESTPOINTS)
+        if planes:
+            self.forces.setplanes(planes)
         self.last_neibs_info = None
         self.total_interactions = 0       # sum over steps of list entries x 2 force evaluations
         self.launches = 0                 # hand-written kernels launched (CUB's sort passes not counted)
@@ -117,6 +125,8 @@ class Worker:
              BUFFER_FORCES: self.forces_buf, BUFFER_CFL: self.cfl, BUFFER_CFL_TEMP: self.cfl_temp}
         if self.compact_dev_map is not None:
             d[BUFFER_COMPACT_DEV_MAP] = self.compact_dev_map
+        if self.xsph is not None:
+            d[BUFFER_XSPH] = self.xsph
         return d
 
     def state(self, which: int) -> BufferList:
@@ -153,12 +163,36 @@ class Worker:
         self.last_neibs_info = self.neibs.getinfo()
         self.launches += 6                # calc/fixHash, make_keys, apply_sort, reorder, reset_counters, build_neibs
 
+    # ---- FILTER phases (src/integrators/PredictorCorrectorIntegrator.cc:800-877, 1010-1040) ----
+    def run_filters(self) -> None:
+        """After NEIBS_LIST, for iterations > 0: every enabled filter whose frequency divides the iteration count reads
+        VEL of step n, writes the filtered VEL into the scratch state, and the two VEL buffers are swapped."""
+        if self.iterations == 0:
+            return
+        cur, oth = self.cur, 1 - self.cur
+        for eng, freq in self.filters:
+            if self.iterations % freq:
+                continue
+            rd = self.state(cur)
+            wr = BufferList({BUFFER_VEL: self.vel[oth]})
+            eng.process(rd, wr, self.numParticles, self.particleRangeEnd, self.params.slength, self.params.influenceradius)
+            self.vel[cur], self.vel[oth] = self.vel[oth], self.vel[cur]
+            self.launches += 1
+
+    def postprocess(self) -> None:
+        """TESTPOINTS post-processing before a write (src/GPUWorker.cc:2545-2580): in place on the current state."""
+        s = self.state(self.cur)
+        self.postproc.process(s, s, self.numParticles, self.particleRangeEnd)
+        self.launches += 1
+
     # ---- one force evaluation + integration sub-step ----
-    def _forces(self, which: int) -> float:
+    def _forces(self, which: int, step: int = 0, dt: float = 0.0) -> float:
         s = self.state(which)
         if self.clobber:
             self.forces_buf.zero_()                # pre_forces: clobber FORCES, src/GPUWorker.cc:1949
-        nblocks = self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0)
+        if self.xsph is not None:
+            self.xsph.zero_()                      # :1951-1952
+        nblocks = self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0, step=step, dt=dt)
         self.launches += 1                # fused forces kernel
         if self.fixed_dt is not None:
             return self.fixed_dt
@@ -169,6 +203,8 @@ class Worker:
         """One predictor-corrector time step (src/integrators/PredictorCorrectorIntegrator.cc:917-1068)."""
         if self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None:
             self.build_neibs()
+        if self.filters:
+            self.run_filters()
         n, end = self.numParticles, self.particleRangeEnd
         cur, oth = self.cur, 1 - self.cur
         rd, wr = self.state(cur), self.state(oth)
@@ -178,7 +214,9 @@ class Worker:
             for which, st in ((1, rd), (2, wr)):
                 if self.clobber:
                     self.forces_buf.zero_()
-                nblocks = self.forces.basicstep(st, st, n, 0, end, 0)
+                if self.xsph is not None:
+                    self.xsph.zero_()
+                nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True)
                 self.forces.dtreduce_async(st, nblocks, which)
                 self.integration.basicstep_async(rd, wr, n, end, which)
             self.forces.step_end()
@@ -187,10 +225,10 @@ class Worker:
         else:
             dt = self._dt
             # predictor: forces(n) -> euler step 1 with dt/2 writes n*
-            dt1 = self._forces(cur)
+            dt1 = self._forces(cur, 1, dt / 2)
             self.integration.basicstep(rd, wr, n, end, dt / 2, 1)
             # corrector: forces(n*) -> euler step 2 with dt, reading pos/vel of n, updating n* in place -> n+1
-            dt2 = self._forces(oth)
+            dt2 = self._forces(oth, 2, dt)
             self.integration.basicstep(rd, wr, n, end, dt, 2)
             self.launches += 2                # two euler launches
             self._t += dt

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200SPH_ABI_VERSION 1
+#define B200SPH_ABI_VERSION 2
 
 /* error codes */
 #define B200SPH_OK        0
@@ -64,10 +64,18 @@ enum { B200SPH_PERIODIC_X = 1, B200SPH_PERIODIC_Y = 2, B200SPH_PERIODIC_Z = 4 };
 enum { B200SPH_RHEOLOGY_INVISCID = 0, B200SPH_RHEOLOGY_NEWTONIAN = 1 };
 enum { B200SPH_TURB_LAMINAR = 0, B200SPH_TURB_ARTIFICIAL = 1 };
 enum { B200SPH_COMPVISC_KINEMATIC = 0, B200SPH_COMPVISC_DYNAMIC = 1 };
-enum { B200SPH_VISCMODEL_MORRIS = 0, B200SPH_VISCMODEL_MONAGHAN = 1 };
+enum { B200SPH_VISCMODEL_MORRIS = 0, B200SPH_VISCMODEL_MONAGHAN = 1, B200SPH_VISCMODEL_ESPANOL_REVENGA = 2 };
 enum { B200SPH_AVG_ARITHMETIC = 0, B200SPH_AVG_HARMONIC = 1, B200SPH_AVG_GEOMETRIC = 2 };
 
+/* simulation flags honoured by these engines; numeric values are the reference's (src/simflags.h:71-83) so that
+ * SimParams::simflags can be passed through (other bits are ignored or rejected by b200sph_validate) */
+#define B200SPH_ENABLE_DTADAPT 1u
+#define B200SPH_ENABLE_XSPH    2u
+#define B200SPH_ENABLE_PLANES  4u
+#define B200SPH_ENABLE_DEM     8u
+
 #define B200SPH_MAX_FLUIDS 4
+#define B200SPH_MAX_PLANES 8   /* src/particledefine.h:325 */
 
 /* particle type / flag bits (src/particleinfo.h:135-165) */
 #define B200SPH_PT_FLUID     0
@@ -121,6 +129,13 @@ typedef struct b200sph_params {
 	float    max_sound_speed_cfl;  /* 1.1 * max c0 */
 	float    max_kinvisc;          /* max kinematic viscosity (0 if inviscid) */
 	uint32_t dtadapt;              /* ENABLE_DTADAPT */
+	/* ---- ABI version 2 ---- */
+	uint32_t simflags;             /* SimParams::simflags; B200SPH_ENABLE_XSPH and B200SPH_ENABLE_PLANES are honoured */
+	float    epsxsph;              /* PhysParams::epsxsph (src/cuda/euler.cu:56) */
+	float    monaghan_visc_coeff;  /* PhysParams::monaghan_visc_coeff = 2(d+2) (src/cuda/forces.cu:334) */
+	float    visc2coeff[B200SPH_MAX_FLUIDS]; /* bulk viscosity, ESPANOL_REVENGA only (src/cuda/forces.cu:328) */
+	/* Lennard-Jones repulsion of geometric planes (src/cuda/forces.cu:339-368; partsurf 0 => r0^2) */
+	float    r0, dcoeff, p1coeff, p2coeff, partsurf;
 } b200sph_params;
 
 /* mirror of TimingInfo's neighbour counters (src/timing.h:42-97) */
@@ -152,6 +167,11 @@ int b200sph_validate(const b200sph_params *params);
 int b200sph_set_stream(b200sph_ctx *ctx, void *cuda_stream);
 /* AbstractForcesEngine::setgravity (src/engine_forces.h:58) */
 int b200sph_set_gravity(b200sph_ctx *ctx, const float gravity[3]);
+/* AbstractForcesEngine::setplanes (src/engine_forces.h:56; src/cuda/forces.cu:443-447). Host arrays of numplanes
+ * (<= B200SPH_MAX_PLANES) entries laid out like plane_t (src/planes.h:42-46): unit normal, cell of the reference
+ * point, in-cell position of the reference point. Planes act on fluid particles in the finalize stage of
+ * b200sph_forces when params.simflags has B200SPH_ENABLE_PLANES (src/cuda/forces_kernel.def:4105-4110). */
+int b200sph_set_planes(b200sph_ctx *ctx, const float *normals, const int *grid_pos, const float *pos, int numplanes);
 /* AbstractNeibsEngine::getconstants (src/engine_neibs.h:57): returns neibboundpos */
 int b200sph_get_neibboundpos(const b200sph_ctx *ctx, uint32_t *neibboundpos);
 
@@ -263,6 +283,30 @@ int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const void *vel, co
 	uint32_t num_particles, uint32_t from_particle, uint32_t to_particle,
 	uint32_t cfl_offset, uint32_t *num_cfl_blocks);
 
+/* The complete AbstractForcesEngine::basicstep (src/engine_forces.h:133-149): everything b200sph_forces_bodies takes,
+ * plus the arguments that only some option combinations read:
+ *   xsph   float4[N], written for fluid particles when params.simflags has B200SPH_ENABLE_XSPH: 2 x the mean
+ *          neighbourhood velocity (src/cuda/forces_kernel.def:2986-2992, 3366-3368); must have been zeroed by the
+ *          caller (src/GPUWorker.cc:1951-1952). NULL otherwise.
+ *   dt     the command's dt (dt/2 on the predictor, dt on the corrector, src/GPUWorker.cc:1932), read by the BREZZI
+ *          density diffusion only (src/cuda/forces_kernel.def:1765-1782)
+ *   step   1 or 2; with dt_from_device != 0, dt is taken from the context's device-resident record instead
+ *          (dt/2 for step 1), see "device-resident time stepping" below. */
+typedef struct b200sph_forces_args {
+	const void *pos, *vel, *info;
+	const uint32_t *hash, *cell_start;
+	const uint16_t *neibs_list;
+	void *forces;
+	float *cfl;
+	void *rb_forces, *rb_torques;   /* NULL: no body output */
+	void *xsph;                     /* NULL unless ENABLE_XSPH */
+	uint32_t num_particles, from_particle, to_particle, cfl_offset;
+	float dt;
+	int step;
+	int dt_from_device;
+} b200sph_forces_args;
+int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks);
+
 /* AbstractForcesEngine::reduceRbForces (src/engine_forces.h:68-74; src/cuda/forces.cu:967-1003): in-place segmented
  * inclusive scan of rb_forces / rb_torques keyed by rb_keys, then the last element of each body's segment
  * (lastindex[b], host array) is copied to total_force / total_torque (host float[3*numbodies]). Synchronises. */
@@ -279,6 +323,32 @@ int b200sph_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
 	const void *info, const uint32_t *hash, const void *forces,
 	void *new_pos, void *new_vel,
 	uint32_t num_particles, uint32_t particle_range_end, float dt, int step);
+
+/* b200sph_euler with the XSPH correction (src/cuda/euler_kernel.def:165-180): velc += epsxsph * xsph[i]. xsph = the
+ * buffer b200sph_forces_ex wrote (NULL: same as b200sph_euler). dt_from_device != 0: dt from the device record. */
+int b200sph_euler_ex(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
+	const void *info, const uint32_t *hash, const void *forces, const void *xsph,
+	void *new_pos, void *new_vel,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step, int dt_from_device);
+
+/* ---- filter engines and post-processing ---------
+ * AbstractFilterEngine::process for SHEPARD_FILTER and MLS_FILTER (src/engine_filter.h:75-82;
+ * src/cuda/forces.cu:1026-1122; kernels src/cuda/forces_kernel.cu:418-507, 509-721): density of every fluid
+ * particle (MLS: of every particle) re-initialised from its neighbours through the neighbour list; old_vel is read,
+ * new_vel written for [0, particle_range_end) (other particles' velocities are copied through). */
+int b200sph_filter_shepard(b200sph_ctx *ctx, const void *pos, const void *old_vel, void *new_vel, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	uint32_t num_particles, uint32_t particle_range_end);
+int b200sph_filter_mls(b200sph_ctx *ctx, const void *pos, const void *old_vel, void *new_vel, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	uint32_t num_particles, uint32_t particle_range_end);
+
+/* AbstractPostProcessEngine::process for TESTPOINTS (src/engine_postprocess.h:85-92; src/cuda/post_process.cu:148-216;
+ * kernel src/cuda/post_process_kernel.cu:134-240): every PT_TESTPOINT particle gets the Shepard-normalised velocity
+ * (xyz) and pressure (w) of its fluid neighbours, IN PLACE in vel; tke / epsilon (float[N], in place) may be NULL. */
+int b200sph_testpoints(b200sph_ctx *ctx, const void *pos, void *vel, float *tke, float *epsilon, const void *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	uint32_t num_particles, uint32_t particle_range_end);
 
 /* ---- device-resident time stepping (no reference counterpart) ---------------
  * The reference reads the CFL maximum back to the host after every force evaluation (two blocking 4-byte copies

@@ -376,7 +376,44 @@ static inline float visc_avg_dyn(const b200sph_params *P, float v, float nv, flo
 /* ------------------------------------------------------------------------ */
 typedef struct { float x, y, z; } f3;
 
-static void forces_pass(const b200sph_params *P, int cptype, int nptype,
+/* arguments only some option combinations read (b200sph_forces_args / b200sph_set_planes on the product side) */
+typedef struct {
+	float dt;                 /* the command's dt: BREZZI diffusion (forces_kernel.def:1765-1782) */
+	f4 *xsph;                 /* ENABLE_XSPH output, zeroed by the caller (forces_kernel.def:3366-3368) */
+	int numplanes;            /* geometric planes, plane_t layout (src/planes.h:42-46) */
+	float plane_normal[B200SPH_MAX_PLANES][3];
+	int plane_gridpos[B200SPH_MAX_PLANES][3];
+	float plane_pos[B200SPH_MAX_PLANES][3];
+} oracle_forces_opts;
+
+/* average<avgop>, src/average.h:75-100 */
+static inline float average_op(unsigned op, float a, float b)
+{
+	switch (op) {
+	case B200SPH_AVG_ARITHMETIC: return (a + b) * 0.5f;
+	case B200SPH_AVG_HARMONIC: return 2.0f * a * b / (a + b);
+	default: return sqrtf(a * b);
+	}
+}
+
+/* W<WENDLAND>, src/cuda/sph_core.cu:104-117; coefficient src/cuda/forces.cu:274-284 */
+static inline float kernel_wcoeff(const b200sph_params *P)
+{
+	const float h = P->slength; const float h2 = h * h; const float h3 = h2 * h;
+	return (float)(21.0f / (16.0f * M_PI * h3));
+}
+static inline float wendland_W(float r, float h, float wcoeff)
+{
+	const float R = r / h;
+	float val = 1.0f - 0.5f * R;
+	val *= val;
+	val *= val;
+	val *= 1.0f + 2.0f * R;
+	val *= wcoeff;
+	return val;
+}
+
+static void forces_pass(const b200sph_params *P, const oracle_forces_opts *opts, int cptype, int nptype,
 	const f4 *pos, const f4 *vel, const us4 *info, const uint32_t *hash,
 	const uint32_t *cell_start, const uint16_t *neibs_list,
 	const float *pprec, const float *ssp,
@@ -384,8 +421,11 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 {
 	const size_t stride = P->neiblist_stride;
 	const float fcoeff = kernel_fcoeff(P);
+	const float wcoeff = kernel_wcoeff(P);
 	const float h = P->slength;
 	const int inviscid = P->rheologytype == B200SPH_RHEOLOGY_INVISCID;
+	/* computes_xsph :176-189: ENABLE_XSPH, fluid central, fluid neighbour */
+	const int xsph = (P->simflags & B200SPH_ENABLE_XSPH) && cptype == B200SPH_PT_FLUID && nptype == B200SPH_PT_FLUID && opts && opts->xsph;
 #pragma omp parallel for schedule(dynamic, 512)
 	for (uint32_t index = from; index < to; ++index) {
 		const us4 inf = info[index];
@@ -400,6 +440,7 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 		const float sspeed = ssp[index];
 		f4 force = forces[index];             /* common_particle_output: RMW, :886-897 */
 		f4 asum = abssum ? abssum[index] : (f4){ 0, 0, 0, 0 };
+		f3 mean_vel = { 0, 0, 0 };            /* xsph_particle_output :962-969 */
 
 		/* neighbour-list traversal: src/cuda/neibs_iteration.cuh:56-200, src/cuda/cellgrid.cuh:198-226 */
 		float pcx = 0, pcy = 0, pcz = 0;
@@ -466,6 +507,12 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 							DrDt -= t; a_w += fabsf(t);
 						}
 					}
+				} else if (P->densitydiffusiontype == B200SPH_RHODIFF_BREZZI) {     /* :1765-1782 */
+					const float Pi = eos_P(P, v.w, fnum), Pj = eos_P(P, nrho_t, nfnum);
+					const float gdot = P->gravity[0] * rx + P->gravity[1] * ry + P->gravity[2] * rz;
+					const float dt = opts ? opts->dt : 0.0f;
+					const float t = P->density_diff_coeff * ((2.0f / (rho + nrho)) * (Pi - Pj) - gdot) * nmass / nrho * f * dt * 2.0f * rho;
+					DrDt += t; a_w += fabsf(t);
 				}
 			}
 			force.w += DrDt;
@@ -484,7 +531,20 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 					dvx += visc * rx * nmass * f; dvy += visc * ry * nmass * f; dvz += visc * rz * nmass * f;
 					a_v += fabsf(s) * r;
 				}
-				/* laminar Morris :2605-2625 */
+				/* Espanol & Revenga :2651-2678 */
+				if (!inviscid && P->viscmodel == B200SPH_VISCMODEL_ESPANOL_REVENGA) {
+					const float vc = P->visccoeff[fnum], nvc = P->visccoeff[nfnum];
+					const float pvisc = P->compvisc == B200SPH_COMPVISC_KINEMATIC ? vc * rho : vc;      /* get_dynamic_visc :276-289 */
+					const float nvisc = P->compvisc == B200SPH_COMPVISC_KINEMATIC ? nvc * nrho : nvc;
+					const float visc_thirds = average_op(P->viscavgop, pvisc, nvisc) / 3;
+					const float bulk = average_op(P->viscavgop, P->visc2coeff[fnum], P->visc2coeff[nfnum]);
+					const float coeff = nmass / (rho * nrho) * f;                                        /* :2575-2580 */
+					const float pos_den = (rx * rx + ry * ry + rz * rz) + P->epsartvisc;
+					const float a = 5 * visc_thirds - bulk, b = 5 * (visc_thirds + bulk) * vel_dot_pos / pos_den;
+					dvx += coeff * (a * rvx + b * rx); dvy += coeff * (a * rvy + b * ry); dvz += coeff * (a * rvz + b * rz);
+					a_v += fabsf(coeff) * (fabsf(a) * sqrtf(rvx * rvx + rvy * rvy + rvz * rvz) + fabsf(b) * r);
+				} else
+				/* laminar Morris / Monaghan :2605-2625 */
 				if (!inviscid) {
 					float visc;
 					const float vc = P->visccoeff[fnum], nvc = P->visccoeff[nfnum];
@@ -496,8 +556,20 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 						else visc = visc_avg_dyn(P, vc, nvc, rho, nrho, nmass);
 					}
 					const float s = visc * f;
-					dvx += s * rvx; dvy += s * rvy; dvz += s * rvz;
-					a_v += fabsf(s) * sqrtf(rvx * rvx + rvy * rvy + rvz * rvz);
+					if (P->viscmodel == B200SPH_VISCMODEL_MONAGHAN) {       /* viscous_vector_component<MONAGHAN> :2534-2559 */
+						const float den = (rx * rx + ry * ry + rz * rz) + P->epsartvisc;
+						const float m = vel_dot_pos < 0 ? P->monaghan_visc_coeff * vel_dot_pos / den : 0.0f;
+						dvx += s * (m * rx); dvy += s * (m * ry); dvz += s * (m * rz);
+						a_v += fabsf(s * m) * r;
+					} else {
+						dvx += s * rvx; dvy += s * rvy; dvz += s * rvz;
+						a_v += fabsf(s) * sqrtf(rvx * rvx + rvy * rvy + rvz * rvz);
+					}
+				}
+				/* compute_mean_vel :2986-2992 */
+				if (xsph) {
+					const float s = nmass * wendland_W(r, h, wcoeff) / (rho + nrho);
+					mean_vel.x -= s * rvx; mean_vel.y -= s * rvy; mean_vel.z -= s * rvz;
 				}
 				force.x += dvx; force.y += dvy; force.z += dvz;
 			}
@@ -505,6 +577,7 @@ static void forces_pass(const b200sph_params *P, int cptype, int nptype,
 		}
 		forces[index] = force;
 		if (abssum) abssum[index] = asum;
+		if (xsph) opts->xsph[index] = (f4){ 2.0f * mean_vel.x, 2.0f * mean_vel.y, 2.0f * mean_vel.z, 0.0f };   /* write_xsph :3366-3368 */
 	}
 }
 
@@ -522,12 +595,12 @@ typedef struct {
 
 /* forces + finalize. Returns the number of CFL blocks written, like
  * CUDAForcesEngine::basicstep (src/cuda/forces.cu:901-932). forces must be zeroed by the caller. */
-uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, const us4 *info,
+uint32_t oracle_forces_ex(const b200sph_params *P, const f4 *pos, const f4 *vel, const us4 *info,
 	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
 	const float *eos_p_in, const float *eos_c_in,
 	f4 *forces, float *cfl, f4 *abssum,
 	uint32_t num_particles, uint32_t from, uint32_t to, uint32_t cfl_offset,
-	const oracle_bodies *bodies, f4 *rb_forces, f4 *rb_torques)
+	const oracle_bodies *bodies, f4 *rb_forces, f4 *rb_torques, const oracle_forces_opts *opts)
 {
 	float *pprec = (float *)malloc(sizeof(float) * (num_particles ? num_particles : 1));
 	float *ssp = (float *)malloc(sizeof(float) * (num_particles ? num_particles : 1));
@@ -540,10 +613,10 @@ uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, co
 		ssp[i] = eos_c_in ? eos_c_in[i] : eos_c(P, vel[i].w, f);
 	}
 	/* src/cuda/forces.cu:759,782,792: fluid<-fluid, fluid<-boundary, boundary<-fluid */
-	forces_pass(P, B200SPH_PT_FLUID, B200SPH_PT_FLUID, pos, vel, info, hash, cell_start, neibs_list, pprec, ssp, forces, abssum, from, to);
-	forces_pass(P, B200SPH_PT_FLUID, B200SPH_PT_BOUNDARY, pos, vel, info, hash, cell_start, neibs_list, pprec, ssp, forces, abssum, from, to);
+	forces_pass(P, opts, B200SPH_PT_FLUID, B200SPH_PT_FLUID, pos, vel, info, hash, cell_start, neibs_list, pprec, ssp, forces, abssum, from, to);
+	forces_pass(P, opts, B200SPH_PT_FLUID, B200SPH_PT_BOUNDARY, pos, vel, info, hash, cell_start, neibs_list, pprec, ssp, forces, abssum, from, to);
 	if (P->boundarytype == B200SPH_DYN_BOUNDARY)
-		forces_pass(P, B200SPH_PT_BOUNDARY, B200SPH_PT_FLUID, pos, vel, info, hash, cell_start, neibs_list, pprec, ssp, forces, abssum, from, to);
+		forces_pass(P, opts, B200SPH_PT_BOUNDARY, B200SPH_PT_FLUID, pos, vel, info, hash, cell_start, neibs_list, pprec, ssp, forces, abssum, from, to);
 
 	/* finalizeforcesDevice :4037-4153 with forces_fixup :3212-3219, gravity :4091,
 	 * dyndt_forces_shared_data :3436-3456, maxBlockReduce device_core.cu:40-59.
@@ -565,6 +638,33 @@ uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, co
 			fo.w /= P->rho0[f];
 			if (is_fluid(inf)) {
 				fo.x += P->gravity[0]; fo.y += P->gravity[1]; fo.z += P->gravity[2];
+				/* geometric planes :4105-4110: GeometryForce / PlaneForce / LJForce src/cuda/forces_kernel.cu:94-204,
+				 * PlaneDistance src/cuda/geom_core.cu:65-85, viscous_plane_coefficient :3103-3113 */
+				if ((P->simflags & B200SPH_ENABLE_PLANES) && opts && opts->numplanes) {
+					const float rho = phys_rho(P, vel[index].w, f);
+					const float dynvisc = P->rheologytype == B200SPH_RHEOLOGY_INVISCID ? 0.0f :
+						(P->compvisc == B200SPH_COMPVISC_KINEMATIC ? P->visccoeff[f] * rho : P->visccoeff[f]);
+					const float partsurf = P->partsurf == 0.0f ? P->r0 * P->r0 : P->partsurf;
+					const i3 gp = grid_pos_from_hash(P, hash[index] & CELLTYPE_BITMASK);
+					const int gpa[3] = { gp.x, gp.y, gp.z };
+					const float pa[3] = { p.x, p.y, p.z };
+					const f4 v4 = vel[index];
+					for (int k = 0; k < opts->numplanes; ++k) {
+						float d[3];
+						for (int a = 0; a < 3; ++a)
+							d[a] = (float)(gpa[a] - opts->plane_gridpos[k][a]) * P->cell_size[a] + (pa[a] - opts->plane_pos[k][a]);
+						const float *nrm = opts->plane_normal[k];
+						const float r = fabsf(d[0] * nrm[0] + d[1] * nrm[1] + d[2] * nrm[2]);
+						if (r < P->r0) {
+							const float DvDt = P->dcoeff * (powf(P->r0 / r, P->p1coeff) - powf(P->r0 / r, P->p2coeff)) / (r * r);
+							const float rp[3] = { nrm[0] * r, nrm[1] * r, nrm[2] * r };
+							fo.x += DvDt * rp[0]; fo.y += DvDt * rp[1]; fo.z += DvDt * rp[2];
+							const float vn = (v4.x * rp[0] + v4.y * rp[1] + v4.z * rp[2]) / r;
+							const float coeff = -dynvisc * partsurf / (p.w * r);
+							fo.x += coeff * (v4.x - vn * rp[0] / r); fo.y += coeff * (v4.y - vn * rp[1] / r); fo.z += coeff * (v4.z - vn * rp[2] / r);
+						}
+					}
+				}
 				const float c = ssp[index];
 				const float v = fmaxf(sqrtf(fo.x * fo.x + fo.y * fo.y + fo.z * fo.z), c * c / P->slength);
 				if (v > m) m = v;
@@ -588,6 +688,17 @@ uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, co
 	}
 	free(pprec); free(ssp);
 	return nblocks;
+}
+
+uint32_t oracle_forces(const b200sph_params *P, const f4 *pos, const f4 *vel, const us4 *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
+	const float *eos_p_in, const float *eos_c_in,
+	f4 *forces, float *cfl, f4 *abssum,
+	uint32_t num_particles, uint32_t from, uint32_t to, uint32_t cfl_offset,
+	const oracle_bodies *bodies, f4 *rb_forces, f4 *rb_torques)
+{
+	return oracle_forces_ex(P, pos, vel, info, hash, cell_start, neibs_list, eos_p_in, eos_c_in, forces, cfl, abssum,
+		num_particles, from, to, cfl_offset, bodies, rb_forces, rb_torques, NULL);
 }
 
 /* per-particle EOS quantities as the oracle evaluates them (for tests) */
@@ -621,6 +732,16 @@ void oracle_euler(const b200sph_params *P, const f4 *old_pos, const f4 *old_vel,
 	const uint32_t *hash, const f4 *forces, f4 *new_pos, f4 *new_vel,
 	uint32_t num_particles, uint32_t range_end, float dt, int step, const oracle_bodies *bodies)
 {
+	void oracle_euler_ex(const b200sph_params *, const f4 *, const f4 *, const us4 *, const uint32_t *, const f4 *, const f4 *,
+		f4 *, f4 *, uint32_t, uint32_t, float, int, const oracle_bodies *);
+	oracle_euler_ex(P, old_pos, old_vel, info, hash, forces, NULL, new_pos, new_vel, num_particles, range_end, dt, step, bodies);
+}
+
+/* ... with the XSPH correction (euler_kernel.def:165-180): velc += epsxsph * xsph */
+void oracle_euler_ex(const b200sph_params *P, const f4 *old_pos, const f4 *old_vel, const us4 *info,
+	const uint32_t *hash, const f4 *forces, const f4 *xsph, f4 *new_pos, f4 *new_vel,
+	uint32_t num_particles, uint32_t range_end, float dt, int step, const oracle_bodies *bodies)
+{
 	(void)num_particles;
 	const int integrate_boundary = (P->boundarytype == B200SPH_DYN_BOUNDARY || P->boundarytype == B200SPH_SA_BOUNDARY);
 #pragma omp parallel for
@@ -632,6 +753,9 @@ void oracle_euler(const b200sph_params *P, const f4 *old_pos, const f4 *old_vel,
 		if (!inactive(p) && !(t == B200SPH_PT_BOUNDARY && !integrate_boundary && !is_moving(inf))) {
 			float vcx = v.x, vcy = v.y, vcz = v.z;
 			if (step == 2) { const float hdt = dt / 2; vcx += f.x * hdt; vcy += f.y * hdt; vcz += f.z * hdt; }
+			if (xsph && (P->simflags & B200SPH_ENABLE_XSPH)) {
+				vcx += P->epsxsph * xsph[i].x; vcy += P->epsxsph * xsph[i].y; vcz += P->epsxsph * xsph[i].z;
+			}
 			if (t == B200SPH_PT_FLUID) {
 				p.x += vcx * dt; p.y += vcy * dt; p.z += vcz * dt;
 				v.w += dt * f.w;
@@ -677,4 +801,256 @@ void oracle_localpos_and_hash(const b200sph_params *P, const double *gpos /* xyz
 	localpos->y = (float)(gpos[1] - (double)P->world_origin[1] - (g[1] + 0.5) * (double)P->cell_size[1]);
 	localpos->z = (float)(gpos[2] - (double)P->world_origin[2] - (g[2] + 0.5) * (double)P->cell_size[2]);
 	localpos->w = mass;
+}
+
+/* ------------------------------------------------------------------------ */
+/* neighbour-list traversal as an iterator: src/cuda/neibs_iteration.cuh      */
+/* :56-396 (for_each_neib2), getNeibIndex src/cuda/cellgrid.cuh:198-226       */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+	const b200sph_params *P; const uint32_t *cell_start; const uint16_t *list; const f4 *pos;
+	uint32_t index; f4 p; i3 gp;
+	int section, nsections; long long row;
+	uint32_t base; float pcx, pcy, pcz;
+	uint32_t j; f4 rel;     /* current neighbour and relPos (w = neighbour mass) */
+} neib_iter;
+
+static void neib_iter_init(neib_iter *it, const b200sph_params *P, uint32_t index, const f4 *pos, const uint32_t *hash,
+	const uint32_t *cell_start, const uint16_t *list, int with_boundary)
+{
+	it->P = P; it->cell_start = cell_start; it->list = list; it->pos = pos;
+	it->index = index; it->p = pos[index];
+	it->gp = grid_pos_from_hash(P, hash[index] & CELLTYPE_BITMASK);
+	it->section = 0; it->nsections = with_boundary ? 2 : 1; it->row = -1;
+	it->base = 0; it->pcx = it->pcy = it->pcz = 0;
+}
+static int neib_iter_next(neib_iter *it)
+{
+	const b200sph_params *P = it->P;
+	for (;;) {
+		if (it->section >= it->nsections) return 0;
+		if (it->row < 0) it->row = it->section == 0 ? 0 : (long long)P->neibboundpos;
+		else it->row += it->section == 0 ? 1 : -1;
+		if (it->row < 0 || it->row >= (long long)P->neiblistsize) { it->section++; it->row = -1; continue; }
+		uint32_t nd = it->list[(size_t)it->row * P->neiblist_stride + it->index];
+		if (nd == NEIBS_END) { it->section++; it->row = -1; continue; }
+		if (nd >= CELLNUM_ENCODED) {
+			const int cell = (int)(nd >> CELLNUM_SHIFT) - 1;
+			nd &= NEIBINDEX_MASK;
+			const int ox = cell % 3 - 1, oy = (cell / 3) % 3 - 1, oz = cell / 9 - 1;
+			it->pcx = it->p.x - (float)ox * P->cell_size[0];
+			it->pcy = it->p.y - (float)oy * P->cell_size[1];
+			it->pcz = it->p.z - (float)oz * P->cell_size[2];
+			i3 ng = { it->gp.x + ox, it->gp.y + oy, it->gp.z + oz };
+			it->base = it->cell_start[calc_grid_hash_periodic(P, ng)];
+		}
+		it->j = it->base + nd;
+		const f4 np = it->pos[it->j];
+		it->rel.x = it->pcx - np.x; it->rel.y = it->pcy - np.y; it->rel.z = it->pcz - np.z; it->rel.w = np.w;
+		return 1;
+	}
+}
+
+/* Shepard filter: shepardDevice, src/cuda/forces_kernel.cu:418-507 */
+void oracle_shepard(const b200sph_params *P, const f4 *pos, const f4 *old_vel, f4 *new_vel, const us4 *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list, uint32_t range_end)
+{
+	const float wcoeff = kernel_wcoeff(P), h = P->slength;
+#pragma omp parallel for schedule(dynamic, 512)
+	for (uint32_t index = 0; index < range_end; ++index) {
+		const us4 inf = info[index];
+		const f4 p = pos[index];
+		if (inactive(p)) continue;
+		f4 v = old_vel[index];
+		if (!is_fluid(inf)) { new_vel[index] = v; continue; }
+		const int fnum = fluid_num(inf);
+		float temp1 = p.w * wendland_W(0, h, wcoeff);
+		float temp2 = temp1 / phys_rho(P, v.w, fnum);
+		neib_iter it;
+		neib_iter_init(&it, P, index, pos, hash, cell_start, neibs_list, P->boundarytype == B200SPH_DYN_BOUNDARY);
+		while (neib_iter_next(&it)) {
+			if (!isfinite(it.rel.w)) continue;
+			const float r = sqrtf(it.rel.x * it.rel.x + it.rel.y * it.rel.y + it.rel.z * it.rel.z);
+			const float neib_rho = phys_rho(P, old_vel[it.j].w, fluid_num(info[it.j]));
+			if (r < P->influenceradius) {
+				const float w = wendland_W(r, h, wcoeff) * it.rel.w;
+				temp1 += w;
+				temp2 += w / neib_rho;
+			}
+		}
+		v.w = (temp1 / temp2) / P->rho0[fnum] - 1.0f;      /* numerical_density, phys_core.cu:145-151 */
+		new_vel[index] = v;
+	}
+}
+
+/* symtensor4 algebra: src/cuda/tensor.cu:64-100 (det), :240-249 (dot), :261-271 (ddot), :273-283 (adjugate_row1);
+ * hypot: src/vector_math.h:1231-1240 (float4 / float multiplies by the reciprocal, :1093-1097) */
+typedef struct { float xx, xy, xz, xw, yy, yz, yw, zz, zw, ww; } st4;
+static float st4_det(const st4 *T)
+{
+	float ret = 0, M = 0;
+	M += T->xx * (T->yy * T->zz - T->yz * T->yz);
+	M -= T->xy * (T->xy * T->zz - T->xz * T->yz);
+	M += T->xz * (T->xy * T->yz - T->xz * T->yy);
+	ret += M * T->ww;
+	M = 0;
+	M += T->xx * (T->yy * T->zw - T->yz * T->yw);
+	M -= T->xy * (T->xy * T->zw - T->xz * T->yw);
+	M += T->xw * (T->xy * T->yz - T->xz * T->yy);
+	ret -= M * T->zw;
+	M = 0;
+	M += T->xx * (T->yz * T->zw - T->zz * T->yw);
+	M -= T->xz * (T->xy * T->zw - T->xz * T->yw);
+	M += T->xw * (T->xy * T->zz - T->xz * T->yz);
+	ret += M * T->yw;
+	M = 0;
+	M += T->xy * (T->yz * T->zw - T->zz * T->yw);
+	M -= T->xz * (T->yy * T->zw - T->yz * T->yw);
+	M += T->xw * (T->yy * T->zz - T->yz * T->yz);
+	ret -= M * T->xw;
+	return ret;
+}
+static f4 st4_dot(const st4 *T, f4 v)
+{
+	f4 r = { T->xx * v.x + T->xy * v.y + T->xz * v.z + T->xw * v.w,
+	         T->xy * v.x + T->yy * v.y + T->yz * v.z + T->yw * v.w,
+	         T->xz * v.x + T->yz * v.y + T->zz * v.z + T->zw * v.w,
+	         T->xw * v.x + T->yw * v.y + T->zw * v.z + T->ww * v.w };
+	return r;
+}
+static float st4_ddot(const st4 *T, f4 v)
+{
+	return T->xx * v.x * v.x + T->yy * v.y * v.y + T->zz * v.z * v.z + T->ww * v.w * v.w +
+		2 * ((T->xy * v.y + T->xw * v.w) * v.x + (T->yz * v.z + T->yw * v.w) * v.y + (T->xz * v.x + T->zw * v.w) * v.z);
+}
+static f4 st4_adj_row1(const st4 *T)
+{
+	f4 r = {
+		T->yy * T->zz * T->ww + T->yz * T->zw * T->yw + T->yw * T->yz * T->zw - T->yy * T->zw * T->zw - T->yz * T->yz * T->ww - T->yw * T->zz * T->yw,
+		T->xy * T->zw * T->zw + T->yz * T->xz * T->ww + T->yw * T->zz * T->xw - T->xy * T->zz * T->ww - T->yz * T->zw * T->xw - T->yw * T->xz * T->zw,
+		T->xy * T->yz * T->ww + T->yy * T->zw * T->xw + T->yw * T->xz * T->yw - T->xy * T->zw * T->yw - T->yy * T->xz * T->ww - T->yw * T->yz * T->xw,
+		T->xy * T->zz * T->yw + T->yy * T->xz * T->zw + T->yz * T->yz * T->xw - T->xy * T->yz * T->zw - T->yy * T->zz * T->xw - T->yz * T->xz * T->yw };
+	return r;
+}
+static float f4_hypot(f4 v)
+{
+	const float p = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+	if (!p) return 0;
+	const float inv = 1.0f / p;
+	const float wx = v.x * inv, wy = v.y * inv, wz = v.z * inv, ww = v.w * inv;
+	return p * sqrtf(wx * wx + wy * wy + wz * wz + ww * ww);
+}
+
+/* MLS filter: MlsDevice, src/cuda/forces_kernel.cu:509-721 (MlsMatrixContrib :235-249, MlsCorrContrib :256-260) */
+void oracle_mls(const b200sph_params *P, const f4 *pos, const f4 *old_vel, f4 *new_vel, const us4 *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list, uint32_t range_end)
+{
+	const float wcoeff = kernel_wcoeff(P), h = P->slength;
+	const int dyn = P->boundarytype == B200SPH_DYN_BOUNDARY;
+#pragma omp parallel for schedule(dynamic, 512)
+	for (uint32_t index = 0; index < range_end; ++index) {
+		const us4 inf = info[index];
+		const f4 p = pos[index];
+		if (inactive(p)) continue;
+		f4 v = old_vel[index];
+		const int fnum = fluid_num(inf);
+		st4 mls; memset(&mls, 0, sizeof(mls));
+		mls.xx = wendland_W(0, h, wcoeff) * p.w / phys_rho(P, v.w, fnum);
+		neib_iter it;
+		neib_iter_init(&it, P, index, pos, hash, cell_start, neibs_list, dyn);
+		while (neib_iter_next(&it)) {
+			if (!isfinite(it.rel.w)) continue;
+			const float r = sqrtf(it.rel.x * it.rel.x + it.rel.y * it.rel.y + it.rel.z * it.rel.z);
+			const float neib_rho = phys_rho(P, old_vel[it.j].w, fluid_num(info[it.j]));
+			if (r < P->influenceradius) {
+				const float w = wendland_W(r, h, wcoeff) * it.rel.w / neib_rho;
+				const float inv_h = 1.0f / h;
+				const float x = it.rel.x * inv_h, y = it.rel.y * inv_h, z = it.rel.z * inv_h;
+				mls.xx += w;
+				mls.xy += x * w; mls.xz += y * w; mls.xw += z * w;
+				mls.yy += x * x * w; mls.yz += x * y * w; mls.yw += x * z * w;
+				mls.zz += y * y * w; mls.zw += y * z * w;
+				mls.ww += z * z * w;
+			}
+		}
+		const float D = st4_det(&mls);
+		f4 B;
+		if (fabsf(D) < 1.1920929e-07f) {
+			st4 m2 = mls;
+			const float eps = fabsf(D) + 1.1920929e-07f;
+			m2.xx += eps; m2.yy += eps; m2.zz += eps; m2.ww += eps;
+			const float inv = 1.0f / st4_det(&m2);
+			const f4 a = st4_adj_row1(&m2);
+			B = (f4){ a.x * inv, a.y * inv, a.z * inv, a.w * inv };
+		} else {
+			const float inv = 1.0f / D;
+			const f4 a = st4_adj_row1(&mls);
+			B = (f4){ a.x * inv, a.y * inv, a.z * inv, a.w * inv };
+		}
+		for (unsigned steps = 0; steps < 32; ++steps) {
+			const float lenB = f4_hypot(B);
+			const f4 MB = st4_dot(&mls, B);
+			const f4 res = { 1.0f - MB.x, 0.0f - MB.y, 0.0f - MB.z, 0.0f - MB.w };
+			const float num = st4_ddot(&mls, res);
+			const f4 Mp = st4_dot(&mls, res);
+			const float den = Mp.x * Mp.x + Mp.y * Mp.y + Mp.z * Mp.z + Mp.w * Mp.w;
+			const float s = num / den;
+			const f4 corr = { s * res.x, s * res.y, s * res.z, s * res.w };
+			const float lencorr = f4_hypot(corr);
+			if (f4_hypot(res) < lenB * 1.1920929e-07f) break;
+			if (lencorr < 2 * lenB * 1.1920929e-07f) break;
+			B.x += corr.x; B.y += corr.y; B.z += corr.z; B.w += corr.w;
+		}
+		B.y /= h; B.z /= h; B.w /= h;
+		v.w = B.x * wendland_W(0, h, wcoeff) * p.w;
+		neib_iter_init(&it, P, index, pos, hash, cell_start, neibs_list, dyn);
+		while (neib_iter_next(&it)) {
+			if (!isfinite(it.rel.w)) continue;
+			const float r = sqrtf(it.rel.x * it.rel.x + it.rel.y * it.rel.y + it.rel.z * it.rel.z);
+			if (r < P->influenceradius && (dyn || is_fluid(info[it.j]))) {
+				const float w = wendland_W(r, h, wcoeff) * it.rel.w;
+				v.w += (B.x + B.y * it.rel.x + B.z * it.rel.y + B.w * it.rel.z) * w;
+			}
+		}
+		v.w = v.w / P->rho0[fnum] - 1.0f;
+		new_vel[index] = v;
+	}
+}
+
+/* TESTPOINTS: calcTestpointsVelocityDevice, src/cuda/post_process_kernel.cu:134-240 (vel / tke / epsilon in place) */
+void oracle_testpoints(const b200sph_params *P, const f4 *pos, f4 *vel, float *tke, float *epsilon, const us4 *info,
+	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list, uint32_t range_end)
+{
+	const float wcoeff = kernel_wcoeff(P), h = P->slength;
+	for (uint32_t index = 0; index < range_end; ++index) {
+		if (!is_testpoint(info[index])) continue;
+		f4 avg = { 0, 0, 0, 0 };
+		float tkeavg = 0, epsavg = 0, alpha = 0;
+		neib_iter it;
+		neib_iter_init(&it, P, index, pos, hash, cell_start, neibs_list, 0);
+		while (neib_iter_next(&it)) {
+			const float r = sqrtf(it.rel.x * it.rel.x + it.rel.y * it.rel.y + it.rel.z * it.rel.z);
+			if (r < P->influenceradius) {
+				const f4 nv = vel[it.j];
+				const int nf = fluid_num(info[it.j]);
+				const float w = wendland_W(r, h, wcoeff) * it.rel.w / phys_rho(P, nv.w, nf);
+				avg.x += w * nv.x; avg.y += w * nv.y; avg.z += w * nv.z;
+				avg.w += w * eos_P(P, nv.w, nf);
+				if (tke) tkeavg += w * tke[it.j];
+				if (epsilon) epsavg += w * epsilon[it.j];
+				alpha += w;
+			}
+		}
+		if (alpha > 1e-5f) {
+			const float inv = 1.0f / alpha;
+			avg.x *= inv; avg.y *= inv; avg.z *= inv; avg.w *= inv;
+			tkeavg /= alpha; epsavg /= alpha;
+		} else {
+			avg = (f4){ 0, 0, 0, 0 };
+			tkeavg = epsavg = 0;
+		}
+		vel[index] = avg;
+		if (tke) tke[index] = tkeavg;
+		if (epsilon) epsilon[index] = epsavg;
+	}
 }

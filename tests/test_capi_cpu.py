@@ -48,7 +48,7 @@ def test_validate_accepts_supported_and_rejects_unsupported():
     params, _ = lattice_problem(4)
     assert lib.b200sph_validate(C.byref(params)) == 0
     for field, bad in [("kerneltype", 1), ("sph_formulation", 3), ("boundarytype", capi.SA_BOUNDARY),
-                       ("boundarytype", capi.LJ_BOUNDARY), ("densitydiffusiontype", capi.RHODIFF_BREZZI),
+                       ("boundarytype", capi.LJ_BOUNDARY), ("simflags", capi.ENABLE_DTADAPT | capi.ENABLE_DEM),
                        ("turbmodel", 2), ("rheologytype", 3)]:
         p = params.copy()
         setattr(p, field, bad)
@@ -56,6 +56,19 @@ def test_validate_accepts_supported_and_rejects_unsupported():
         with pytest.raises(capi.B200Unsupported):
             capi.check(lib.b200sph_validate(C.byref(p)))
         assert b"unsupported" in lib.b200sph_last_error()
+    # everything reachable from the CLI options of DamBreak3D / Poiseuille is accepted
+    for field, ok in [("densitydiffusiontype", capi.RHODIFF_BREZZI), ("simflags", capi.ENABLE_DTADAPT | capi.ENABLE_XSPH),
+                      ("simflags", capi.ENABLE_DTADAPT | capi.ENABLE_PLANES)]:
+        p = params.copy()
+        setattr(p, field, ok)
+        assert lib.b200sph_validate(C.byref(p)) == 0, field
+    for vm in (capi.VISCMODEL_MONAGHAN, capi.VISCMODEL_ESPANOL_REVENGA):
+        p = params.copy()
+        p.rheologytype, p.viscmodel = capi.RHEOLOGY_NEWTONIAN, vm
+        assert lib.b200sph_validate(C.byref(p)) == 0
+    p = params.copy()
+    p.rheologytype, p.viscmodel = capi.RHEOLOGY_NEWTONIAN, 3
+    assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL
     p = params.copy()
     p.abi_version = 99
     assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL

@@ -1,0 +1,264 @@
+"""GPU parity tests for the "next" rows of SURVEY.md section 8f, through the C ABI against the CPU oracle on the same
+seeded inputs: density filters (Shepard, MLS), TESTPOINTS, the general forces variant (BREZZI diffusion, MONAGHAN /
+ESPANOL_REVENGA viscosity, XSPH), geometric planes, and the Worker-level call order (filters after NEIBS_LIST)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_binding as ob
+import test_gpu_parity as tg
+from gpusph_b200 import capi
+from gpusph_b200.engines import (BUFFER_CFL, BUFFER_FORCES, BUFFER_POS, BUFFER_VEL, BUFFER_XSPH, MLS_FILTER, SHEPARD_FILTER,
+                                 TESTPOINTS, BufferList)
+from gpusph_b200.problems import dambreak_problem, global_positions, lattice_problem, poiseuille_problem
+from gpusph_b200.simulation import Worker
+
+pytestmark = pytest.mark.gpu
+DEV = tg.DEV
+dev, host = tg.dev, tg.host
+
+
+def make_pipe(name, builder):
+    """A test_gpu_parity.Pipeline (neighbour pipeline on the GPU and on the oracle) for an ad-hoc problem."""
+    tg.get("lattice")                                   # initialise the shared problem table
+    if name not in tg.PROBLEMS:
+        params, parts = builder()
+        rng = np.random.default_rng(17)
+        fl = (parts.info[:, 0] & 7) == 0
+        parts.vel[:, :3] += rng.normal(0, 0.3, size=(parts.n, 3)).astype(np.float32) * fl[:, None]
+        parts.vel[:, 3] += rng.normal(0, 1e-3, size=parts.n).astype(np.float32)
+        tg.PROBLEMS[name] = (params, parts)
+    return tg.Pipeline(name)
+
+
+def run_forces(pipe, *, step=0, dt=0.0, xsph=False):
+    n, fw = pipe.n, pipe.fw
+    f = torch.zeros((n, 4), dtype=torch.float32, device=DEV)
+    cfl = torch.zeros(fw.forcesEngine.getFmaxElements(n) + 8, dtype=torch.float32, device=DEV)
+    b = BufferList(pipe.sorted)
+    b[BUFFER_FORCES], b[BUFFER_CFL] = f, cfl
+    xs = None
+    if xsph:
+        xs = torch.zeros((n, 4), dtype=torch.float32, device=DEV)
+        b[BUFFER_XSPH] = xs
+    nb = fw.forcesEngine.basicstep(b, b, n, 0, n, 0, step=step, dt=dt)
+    return host(f), host(cfl)[:nb], None if xs is None else host(xs), b
+
+
+def check_forces(pipe, f, opts=None, tol=5e-4):
+    """tol relative to the per-particle sum of |pair terms| (see test_gpu_parity.test_forces_parity); 5e-4 covers the
+    device's approximate pow in the EOS."""
+    o, params = pipe.o, pipe.params
+    fo, cflo, ab = ob.forces(params, o["spos"], o["svel"], o["info"], o["hash"], o["cs"], o["nl"], want_abssum=True, opts=opts)
+    sv = ab[:, 0] + 1e-3 * np.abs(fo[:, :3]).max() + 1e-12
+    sw = ab[:, 3] / float(params.rho0[0]) + 1e-7 * np.abs(fo[:, 3]).max() + 1e-12
+    ev = np.abs(f[:, :3] - fo[:, :3]).max(axis=1) / sv
+    ew = np.abs(f[:, 3] - fo[:, 3]) / sw
+    assert ev.max() < tol, f"momentum error {ev.max():.3e}"
+    assert ew.max() < tol, f"continuity error {ew.max():.3e}"
+    return fo, cflo
+
+
+# ---------------------------------------------------------------------------------------------- filters
+@pytest.mark.parametrize("kind", [SHEPARD_FILTER, MLS_FILTER])
+@pytest.mark.parametrize("name", ["dambreak", "periodic", "twofluid"])
+def test_density_filters_parity(kind, name):
+    pipe = tg.Pipeline(name)
+    o, params, n = pipe.o, pipe.params, pipe.n
+    eng = pipe.fw.newFilterEngine(kind, 10)
+    assert eng.frequency() == 10
+    out = torch.full((n, 4), 7.0, dtype=torch.float32, device=DEV)
+    eng.process(pipe.sorted, BufferList({BUFFER_VEL: out}), n, n, params.slength, params.influenceradius)
+    fn = ob.shepard if kind == SHEPARD_FILTER else ob.mls
+    exp = fn(params, o["spos"], o["svel"], o["info"], o["hash"], o["cs"], o["nl"])
+    got = host(out)
+    assert np.array_equal(got[:, :3], exp[:, :3])        # velocities are copied through bit for bit
+    # density: ~75-term float sums (contraction differences); MLS adds a 4x4 solve whose conditioning varies per particle
+    tol = 2e-6 if kind == SHEPARD_FILTER else 2e-4
+    assert np.abs(got[:, 3] - exp[:, 3]).max() < tol
+    with pytest.raises(ValueError):
+        eng.process(pipe.sorted, BufferList({BUFFER_VEL: pipe.sorted[BUFFER_VEL]}), n, n)    # in-place is a caller error
+
+
+def test_filter_partial_range_leaves_the_rest_untouched():
+    pipe = tg.Pipeline("dambreak")
+    n = pipe.n
+    out = torch.full((n, 4), 7.0, dtype=torch.float32, device=DEV)
+    pipe.fw.newFilterEngine(MLS_FILTER, 1).process(pipe.sorted, BufferList({BUFFER_VEL: out}), n, n - 300)
+    got = host(out)
+    assert (got[n - 300:] == 7.0).all() and not (got[:n - 300, 3] == 7.0).any()
+
+
+def test_testpoints_parity():
+    pipe = make_pipe("dambreak_tp", lambda: dambreak_problem(0.03, testpoints=3))
+    o, params, n = pipe.o, pipe.params, pipe.n
+    vel = pipe.sorted[BUFFER_VEL].clone()
+    rng = np.random.default_rng(2)
+    tke = np.abs(rng.normal(0, 1, size=n)).astype(np.float32)
+    eps = np.abs(rng.normal(0, 1, size=n)).astype(np.float32)
+    b = BufferList(pipe.sorted)
+    b[BUFFER_VEL] = vel
+    from gpusph_b200.engines import BUFFER_EPSILON, BUFFER_TKE
+    b[BUFFER_TKE], b[BUFFER_EPSILON] = dev(tke), dev(eps)
+    eng = pipe.fw.newPostProcessEngine(TESTPOINTS)
+    eng.process(b, b, n, n)
+    v, k, e = ob.testpoints(params, o["spos"], o["svel"], o["info"], o["hash"], o["cs"], o["nl"], tke=tke, epsilon=eps)
+    tp = (o["info"][:, 0] & 7) == 3
+    assert tp.sum() == 12 and (np.abs(v[tp]).sum(axis=1) > 0).sum() >= 3
+    gv, gk, ge = host(vel), host(b[BUFFER_TKE]), host(b[BUFFER_EPSILON])
+    assert np.array_equal(gv[~tp], v[~tp]) and np.array_equal(gk[~tp], k[~tp]) and np.array_equal(ge[~tp], e[~tp])
+    assert np.allclose(gv[tp, :3], v[tp, :3], rtol=2e-5, atol=1e-6)
+    # pressure goes through the device's approximate pow (src/cuda/phys_core.cu:99-110)
+    assert np.allclose(gv[tp, 3], v[tp, 3], rtol=5e-4, atol=0.05)
+    assert np.allclose(gk[tp], k[tp], rtol=2e-5) and np.allclose(ge[tp], e[tp], rtol=2e-5)
+    with pytest.raises(capi.B200Unsupported):
+        pipe.fw.newPostProcessEngine("VORTICITY")
+
+
+# ---------------------------------------------------------------------------------------------- general forces variant
+def test_brezzi_diffusion_parity():
+    pipe = make_pipe("dambreak_brezzi", lambda: dambreak_problem(0.03, densitydiffusion=capi.RHODIFF_BREZZI, density_diff_coeff=0.1))
+    dt = 1.7e-4
+    f, cfl, _, b = run_forces(pipe, step=2, dt=dt)
+    # (P_i - P_j) is a difference of approximate-pow values: 2e-3 of the summed magnitudes
+    fo, cflo = check_forces(pipe, f, ob.forces_opts(dt=dt), tol=2e-3)
+    assert np.allclose(cfl, cflo, rtol=1e-3)
+    # the term is really there: the result differs from the no-diffusion right-hand side
+    nodiff = pipe.params.copy()
+    nodiff.densitydiffusiontype = capi.RHODIFF_NONE
+    o = pipe.o
+    f0, _, _ = ob.forces(nodiff, o["spos"], o["svel"], o["info"], o["hash"], o["cs"], o["nl"])
+    assert np.abs(f[:, 3] - f0[:, 3]).max() > 100 * np.abs(f[:, 3] - fo[:, 3]).max()
+    with pytest.raises(ValueError):
+        pipe.fw.forcesEngine.basicstep(b, b, pipe.n, 0, pipe.n, 0)          # BREZZI without the command's dt
+
+
+def test_brezzi_with_device_resident_dt_equals_host_dt_bitwise():
+    params, parts = dambreak_problem(0.04, densitydiffusion=capi.RHODIFF_BREZZI, density_diff_coeff=0.1)
+    a = Worker(params, parts, 0, device_dt=True)
+    b = Worker(params, parts, 0, device_dt=False)
+    for _ in range(12):
+        a.step()
+        b.step()
+    ga, gb = a.download(), b.download()
+    assert a.dt == b.dt
+    assert np.array_equal(ga.pos.view(np.uint32), gb.pos.view(np.uint32))
+    assert np.array_equal(ga.vel.view(np.uint32), gb.vel.view(np.uint32))
+
+
+@pytest.mark.parametrize("viscmodel,avg,compvisc", [
+    (capi.VISCMODEL_MONAGHAN, capi.AVG_HARMONIC, capi.COMPVISC_KINEMATIC),
+    (capi.VISCMODEL_MONAGHAN, capi.AVG_ARITHMETIC, capi.COMPVISC_DYNAMIC),
+    (capi.VISCMODEL_ESPANOL_REVENGA, capi.AVG_ARITHMETIC, capi.COMPVISC_KINEMATIC),
+    (capi.VISCMODEL_ESPANOL_REVENGA, capi.AVG_GEOMETRIC, capi.COMPVISC_DYNAMIC)])
+def test_viscous_models_parity(viscmodel, avg, compvisc):
+    name = f"poiseuille_vm{viscmodel}_{avg}_{compvisc}"
+    pipe = make_pipe(name, lambda: poiseuille_problem(10, kinvisc=0.05, viscavgop=avg, viscmodel=viscmodel, compvisc=compvisc,
+                                                      bulkvisc=0.3))
+    f, cfl, _, _ = run_forces(pipe)
+    fo, cflo = check_forces(pipe, f)
+    assert np.allclose(cfl, cflo, rtol=1e-3)
+    # and it is not the MORRIS result
+    morris = pipe.params.copy()
+    morris.viscmodel = capi.VISCMODEL_MORRIS
+    o = pipe.o
+    fm, _, _ = ob.forces(morris, o["spos"], o["svel"], o["info"], o["hash"], o["cs"], o["nl"])
+    assert np.abs(f[:, :3] - fm[:, :3]).max() > 100 * np.abs(f[:, :3] - fo[:, :3]).max()
+
+
+def test_xsph_parity_forces_and_euler():
+    pipe = make_pipe("dambreak_xsph", lambda: dambreak_problem(0.03, simflags=capi.ENABLE_DTADAPT | capi.ENABLE_XSPH))
+    o, params, n = pipe.o, pipe.params, pipe.n
+    f, cfl, xs, b = run_forces(pipe, xsph=True)
+    xo = np.zeros((n, 4), dtype=np.float32)
+    fo, _ = check_forces(pipe, f, ob.forces_opts(xsph=xo))
+    scale = np.abs(o["svel"][:, :3]).max()
+    assert np.abs(xs - xo).max() < 2e-5 * scale
+    assert (xs[(o["info"][:, 0] & 7) != 0] == 0).all()
+    with pytest.raises(ValueError):
+        nb = BufferList(b)
+        del nb[BUFFER_XSPH]
+        pipe.fw.forcesEngine.basicstep(nb, nb, n, 0, n, 0)                  # ENABLE_XSPH without the buffer
+    # euler with the XSPH-corrected velocity
+    dt = 1.3e-4
+    for step, d in ((1, dt / 2), (2, dt)):
+        po, vo = ob.euler(params, o["spos"], o["svel"], o["info"], o["hash"], fo, d, step, xsph=xo)
+        npos = torch.zeros((n, 4), dtype=torch.float32, device=DEV)
+        nvel = torch.zeros((n, 4), dtype=torch.float32, device=DEV)
+        rd = BufferList(pipe.sorted)
+        rd[BUFFER_FORCES], rd[BUFFER_XSPH] = dev(fo), dev(xo)
+        pipe.fw.integrationEngine.basicstep(rd, BufferList({BUFFER_POS: npos, BUFFER_VEL: nvel}), n, n, d, step)
+        assert np.allclose(host(npos), po, rtol=3e-7, atol=1e-10)
+        assert np.allclose(host(nvel), vo, rtol=3e-7, atol=1e-9)
+
+
+def plane_set(params, gpos):
+    """Two planes hugging the particle block (floor, +x wall) in plane_t form (normal, cell, in-cell position)."""
+    cs3 = np.array([params.cell_size[a] for a in range(3)], dtype=np.float64)
+    org = np.array([params.world_origin[a] for a in range(3)], dtype=np.float64)
+
+    def plane(normal, point):
+        point = np.asarray(point, dtype=np.float64)
+        gp = np.floor((point - org) / cs3).astype(int)
+        return (normal, gp, (point - org - (gp + 0.5) * cs3).astype(np.float32))
+    z0 = float(gpos[:, 2].min()) - 0.3 * float(params.r0)
+    x1 = float(gpos[:, 0].max()) + 0.5 * float(params.r0)
+    return [plane((0.0, 0.0, 1.0), (0.02, 0.03, z0)), plane((-1.0, 0.0, 0.0), (x1, 0.01, 0.04))]
+
+
+@pytest.mark.parametrize("viscous", [False, True])
+def test_plane_forces_parity(viscous):
+    kw = dict(rheology=capi.RHEOLOGY_NEWTONIAN, kinvisc=0.02) if viscous else {}
+    name = f"lattice_planes_{int(viscous)}"
+    pipe = make_pipe(name, lambda: lattice_problem(14, jitter=0.2, simflags=capi.ENABLE_DTADAPT | capi.ENABLE_PLANES,
+                                                   densitydiffusion=capi.RHODIFF_COLAGROSSI, **kw))
+    o, params = pipe.o, pipe.params
+    planes = plane_set(params, global_positions(params, o["spos"], o["hash"]))
+    f_before, _, _, _ = run_forces(pipe)
+    pipe.fw.forcesEngine.setplanes(planes)
+    f, cfl, _, _ = run_forces(pipe)
+    fo, cflo = check_forces(pipe, f, ob.forces_opts(planes=planes))
+    assert np.allclose(cfl, cflo, rtol=1e-3)
+    touched = np.abs(f[:, :3] - f_before[:, :3]).max(axis=1) > 0
+    assert 30 < touched.sum() < pipe.n // 2
+    # the plane terms themselves (large, few particles) agree to float accuracy of the LJ powers
+    d_gpu, d_cpu = f[touched, :3] - f_before[touched, :3], None
+    f0, _, _ = ob.forces(params, o["spos"], o["svel"], o["info"], o["hash"], o["cs"], o["nl"])
+    d_cpu = fo[touched, :3] - f0[touched, :3]
+    assert np.allclose(d_gpu, d_cpu, rtol=2e-3, atol=2e-3 * np.abs(d_cpu).max())
+    pipe.fw.forcesEngine.setplanes([])
+    f_after, _, _, _ = run_forces(pipe)
+    assert np.array_equal(f_after, f_before)
+
+
+def test_planes_need_the_simflag():
+    pipe = tg.Pipeline("lattice")
+    with pytest.raises(ValueError):
+        pipe.fw.forcesEngine.setplanes([((0, 0, 1.0), (0, 0, 0), (0, 0, 0))])
+
+
+# ---------------------------------------------------------------------------------------------- call order
+def test_worker_with_mls_filter_and_testpoints_tracks_oracle():
+    """DamBreak3D without density diffusion enables MLS every 10 iterations (src/problems/DamBreak3D.cu:63-71) and always
+    post-processes its test points; here every 3 iterations so that filters run both right after a neighbour rebuild and
+    between rebuilds."""
+    params, parts = dambreak_problem(0.04, densitydiffusion=capi.RHODIFF_NONE, testpoints=3)
+    w = Worker(params, parts, 0, filters={MLS_FILTER: 3})
+    ref = ob.OracleWorker(params, parts, filters={"MLS_FILTER": 3})
+    for _ in range(11):
+        dt = w.dt
+        w.step()
+        ref.step(dt=dt)
+    w.postprocess()
+    ref.postprocess()
+    got, exp = w.download(), ref.download()
+    assert np.array_equal(got.hash, exp.hash) and np.array_equal(got.info, exp.info)
+    dp = 0.04
+    assert np.abs(got.pos[:, :3] - exp.pos[:, :3]).max() < 1e-4 * dp
+    vs = np.abs(exp.vel[:, :3]).max()
+    fl = (exp.info[:, 0] & 7) != 3
+    assert np.abs(got.vel[fl, :3] - exp.vel[fl, :3]).max() < 1e-3 * vs
+    assert np.abs(got.vel[fl, 3] - exp.vel[fl, 3]).max() < 2e-5
+    tp = ~fl
+    assert np.allclose(got.vel[tp, :3], exp.vel[tp, :3], rtol=1e-3, atol=1e-3 * vs)
+    assert np.allclose(got.vel[tp, 3], exp.vel[tp, 3], rtol=2e-3, atol=1.0)

@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # Drop-in demonstration: link the REFERENCE's host code (GPUSPH orchestrator, integrator, GPUWorker, problem API,
-# writers) and its stock framework (visc / BC / filter / post-process engines) with OUR three hot engines
+# writers) and its stock framework (visc / BC engines, other post-processing) with OUR engines: neibs, forces, integration,
+# the SHEPARD / MLS filters and the TESTPOINTS post-process
 # (gpusph_b200/host/b200_engines.h -> libb200sph.so). The only reference-side change is the 3-line patch of
 # GPUWorker's constructor shown in INTEGRATION.md; the problem file (DamBreak3D.cu) is compiled unchanged.
 # Needs the scratch tree and objects produced by oracle/build_ref.sh. Output: build/dropin/<Problem>_b200
@@ -18,6 +19,8 @@ sed -i 's|^using namespace std;|#include "b200_engines.h"\nstatic std::shared_pt
 sed -i 's|neibsEngine(gdata->simframework->getNeibsEngine()),|neibsEngine(new b200::NeibsEngine(b200_contexts(), gdata->simframework->getNeibsEngine())),|' src/GPUWorker_b200.cc
 sed -i 's|forcesEngine(gdata->simframework->getForcesEngine()),|forcesEngine(new b200::ForcesEngine(b200_contexts(), gdata->simframework->getForcesEngine())),|' src/GPUWorker_b200.cc
 sed -i 's|integrationEngine(gdata->simframework->getIntegrationEngine()),|integrationEngine(new b200::IntegrationEngine(b200_contexts(), gdata->simframework->getIntegrationEngine())),|' src/GPUWorker_b200.cc
+sed -i 's|filterEngines(gdata->simframework->getFilterEngines()),|filterEngines(b200::filters(b200_contexts(), gdata->simframework->getFilterEngines())),|' src/GPUWorker_b200.cc
+sed -i 's|postProcEngines(gdata->simframework->getPostProcEngines()),|postProcEngines(b200::postprocess(b200_contexts(), gdata->simframework->getPostProcEngines())),|' src/GPUWorker_b200.cc
 grep -c "b200::" src/GPUWorker_b200.cc
 INC="-Isrc -Isrc/adaptors -Isrc/cuda -Isrc/geometries -Isrc/integrators -Isrc/problem_api -Isrc/problems -Isrc/writers -Isrc/problems/user -Ioptions"
 g++ -include cstdint -include climits -include cstring $INC -I/usr/local/cuda/include -I"$HERE/include" -I"$HERE/gpusph_b200/host" \

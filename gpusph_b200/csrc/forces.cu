@@ -266,7 +266,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 			// neighbour data straight from the reference's own pos / vel buffers (two 128-bit gathers); EOS terms from
 			// rho~ on the fly
 			auto fetch = [&](const uint j, float4 &np, float4 &nv, float4 &ne) {
-				np = __ldg(posArray + j); nv = __ldg(velArray + j);
+				np = ld_gather(posArray + j); nv = ld_gather(velArray + j);
 				ne = MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
 			};
 			const float4 vel = velArray[index];

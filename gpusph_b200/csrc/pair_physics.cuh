@@ -64,7 +64,37 @@ __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P)
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // 16-bit neighbour-list entry, zero-extended, through the read-only path
-__device__ __forceinline__ uint ld_neib(const ushort *p) { uint v; asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// B200_LIST_CACHE: L1 policy of the list stream (every entry is used exactly once by exactly one thread, so it only
+// displaces the neighbour records the gathers want to find in L1): 0 default, 1 no_allocate, 2 evict_first
+#ifndef B200_LIST_CACHE
+#define B200_LIST_CACHE 0
+#endif
+__device__ __forceinline__ uint ld_neib(const ushort *p)
+{
+	uint v;
+#if B200_LIST_CACHE == 1
+	asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=r"(v) : "l"(p));
+#elif B200_LIST_CACHE == 2
+	asm volatile("ld.global.nc.L1::evict_first.u16 %0, [%1];" : "=r"(v) : "l"(p));
+#else
+	asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
+	return v;
+}
+// B200_GATHER_EVICT_LAST: neighbour records (pos / vel) are the data with reuse: keep them in L1 preferentially
+#ifndef B200_GATHER_EVICT_LAST
+#define B200_GATHER_EVICT_LAST 0
+#endif
+__device__ __forceinline__ float4 ld_gather(const float4 *p)
+{
+#if B200_GATHER_EVICT_LAST
+	float4 v;
+	asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+#else
+	return __ldg(p);
+#endif
+}
 
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

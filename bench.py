@@ -212,6 +212,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphs", action="store_true", help="replay the time step as a CUDA graph between neighbour rebuilds")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e: plain upload / step / download instead of Worker.step_host")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -242,7 +244,7 @@ def main():
         from gpusph_b200.multigpu import SlabWorker
         w = SlabWorker(params, parts, local, rank=rank, world=world)
     else:
-        w = Worker(params, parts, local)
+        w = Worker(params, parts, local, graphs=args.graphs)
     n_global = parts.n
 
     def barrier():
@@ -299,15 +301,21 @@ def main():
             # host -> device: the step's inputs = the evolving state n (pos, vel) of this rank's slab. info/hash are
             # constant between neighbour rebuilds and already resident (the reference uploads them once,
             # GPUWorker::uploadSubdomain)
-            w.pos[w.cur][:n].copy_(hp[0][:n], non_blocking=True)
-            w.vel[w.cur][:n].copy_(hp[1][:n], non_blocking=True)
-            h2d += n * 32
             rebuilt = w.iterations % w.buildneibsfreq == 0
-            w.step()
-            n = w.numParticles
-            # device -> host: the step's result (state n+1); after a rebuild also the re-sorted info/hash
-            hp[0][:n].copy_(w.pos[w.cur][:n], non_blocking=True)
-            hp[1][:n].copy_(w.vel[w.cur][:n], non_blocking=True)
+            if world == 1 and not args.no_pipeline:
+                # Worker.step_host: the same copies, pipelined with the force evaluations in stripes of cell layers
+                h2d += n * 32
+                w.step_host(hp[0], hp[1])
+                n = w.numParticles
+            else:
+                w.pos[w.cur][:n].copy_(hp[0][:n], non_blocking=True)
+                w.vel[w.cur][:n].copy_(hp[1][:n], non_blocking=True)
+                h2d += n * 32
+                w.step()
+                n = w.numParticles
+                # device -> host: the step's result (state n+1); after a rebuild also the re-sorted info/hash
+                hp[0][:n].copy_(w.pos[w.cur][:n], non_blocking=True)
+                hp[1][:n].copy_(w.vel[w.cur][:n], non_blocking=True)
             d2h += n * 32
             if rebuilt:
                 hi[:n].copy_(w.info[:n], non_blocking=True)

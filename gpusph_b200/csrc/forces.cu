@@ -271,7 +271,8 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 			};
 			const float4 vel = velArray[index];
 			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE>(P, k, index, info, type, pos,
-				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, forces);
+				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, forces,
+				GEN ? bo.xsph : NULL);
 		}
 	}
 

@@ -204,6 +204,11 @@ class SlabWorker:
         self.cfl = torch.zeros(self.backend.fmax_elements(A), dtype=torch.float32, device=dev)
         self.segments = torch.zeros(4, dtype=torch.int32, device=dev)
         self.cfl_scalar = torch.zeros(1, dtype=torch.float32, device=dev)
+        # device-dt path: local CFL maxima of the two force evaluations of a step, and the copy that is all-reduced
+        # (asynchronously, once per step) while the next step's first force evaluation is already running
+        self.cfl_local = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.cfl_global = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._pending_dt = None
         self.new_num = torch.zeros(1, dtype=torch.int32, device=dev)
         self.cdm = torch.from_numpy(compact_device_map(p, self.slab, rank, world).view(np.int32)).to(dev)
         self.pos[0][:n].copy_(torch.from_numpy(particles.pos[sel]).to(dev))
@@ -227,7 +232,21 @@ class SlabWorker:
         # ranges for the per-evaluation force exchange: (start, count)
         self.edge_left = self.edge_right = self.halo_left = self.halo_right = (0, 0)
 
+    def _finish_dt(self):
+        """Complete the step whose dt candidates are still being all-reduced: dt = f(global CFL maxima), t += dt."""
+        if self._pending_dt is None:
+            return
+        if self._pending_dt is not True:
+            self._pending_dt.wait()
+        be = self.backend
+        be.dtreduce_async(self.cfl_global[0:1], 1, 1)
+        be.dtreduce_async(self.cfl_global[1:2], 1, 2)
+        be.step_end()
+        self.launches += 3
+        self._pending_dt = None
+
     def _sync_time(self):
+        self._finish_dt()
         if self._stale:
             self._t, self._dt, _ = self.backend.step_query()
             self._stale = False
@@ -377,13 +396,13 @@ class SlabWorker:
         if self.fixed_dt is not None:
             return self.fixed_dt
         if self.device_dt:
+            # local maximum only: the two maxima of a step are all-reduced together at the end of the step (step())
+            mine = self.cfl_local[cand - 1:cand]
             if n_own > 0:
-                be.cflmax(self.cfl, nblocks, self.cfl_scalar)
+                be.cflmax(self.cfl, nblocks, mine)
             else:
-                self.cfl_scalar.zero_()
-            dist.all_reduce(self.cfl_scalar, op=dist.ReduceOp.MAX, group=self.group)
-            be.dtreduce_async(self.cfl_scalar, 1, cand)      # dt candidate from the global maximum, on the device
-            self.launches += 2
+                mine.zero_()
+            self.launches += 1
             return 0.0
         # dt = min over ranks (src/GPUSPH.cc:650-657) = dt(max over ranks of the CFL maxima): the block maxima are
         # reduced on the device, all-reduced(MAX) on the device, and read back once
@@ -408,11 +427,15 @@ class SlabWorker:
         cur, oth = self.cur, 1 - self.cur
         eargs = (self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n)
         if self.device_dt:
+            # dt of a step only depends on the CFL maxima of the PREVIOUS step (src/GPUSPH.cc:636-699), and nothing before
+            # the first euler needs it: the all-reduce (one per step, both maxima) overlaps with the forces kernel
             self._forces(cur, 1)
+            self._finish_dt()
             be.euler_async(*eargs, 1)
             self._forces(oth, 2)
             be.euler_async(*eargs, 2)
-            be.step_end()
+            self.cfl_global.copy_(self.cfl_local)
+            self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True
             self._stale = True
         else:
             dt = self._dt

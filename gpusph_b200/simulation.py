@@ -17,6 +17,10 @@ from .engines import (BUFFER_CELLEND, BUFFER_CELLSTART, BUFFER_CFL, BUFFER_CFL_T
 from .problems import ParticleArrays, initial_dt
 
 
+# buffers indexed by particle (sliceable to a particle range)
+_PER_PARTICLE = (BUFFER_POS, BUFFER_VEL, BUFFER_INFO, BUFFER_HASH, BUFFER_FORCES, BUFFER_XSPH)
+
+
 def _dev(a: np.ndarray, device, dtype=None) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
@@ -30,9 +34,11 @@ class Worker:
     def __init__(self, params: capi.Params, particles: ParticleArrays, device=None, *,
                  buildneibsfreq: int = 10, clobber: bool = False, fixed_dt: float | None = None,
                  compact_dev_map: np.ndarray | None = None, start_iteration: int = 0, dt: float | None = None,
-                 device_dt: bool = True, filters: dict | None = None, planes=None):
+                 device_dt: bool = True, filters: dict | None = None, planes=None, graphs: bool = False):
         """filters: {SHEPARD_FILTER | MLS_FILTER: frequency in iterations} (Problem::addFilter);
-        planes: [(normal, gridPos, pos)] for ENABLE_PLANES (AbstractForcesEngine::setplanes)."""
+        planes: [(normal, gridPos, pos)] for ENABLE_PLANES (AbstractForcesEngine::setplanes);
+        graphs: replay the command stream of a time step (static between neighbour rebuilds once dt lives on the
+        device) as a CUDA graph instead of re-issuing its launches from the host."""
         self.framework = SimFramework(params, device)
         self.params = self.framework.params
         self.device = self.framework.ctx.device
@@ -63,7 +69,9 @@ class Worker:
         self.cellend = torch.empty(ncells, dtype=torch.int32, device=dev)
         self.neibslist = torch.empty((int(self.params.neiblistsize), A), dtype=torch.int16, device=dev)
         self.neibslist.fill_(-1)
-        ncfl = self.forces.getFmaxElements(A)
+        self.host_stripes = 8             # stripes of the pipelined host-buffer step (step_host)
+        # striped force evaluations round every stripe's CFL blocks up to a multiple of 4: room for that
+        ncfl = self.forces.getFmaxElements(A) + 4 * (self.host_stripes + 1)
         self.cfl = torch.zeros(ncfl, dtype=torch.float32, device=dev)
         self.cfl_temp = torch.zeros(max(self.forces.getFmaxTempElements(ncfl), 4), dtype=torch.float32, device=dev)
         self.new_num = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -88,6 +96,8 @@ class Worker:
         self.postproc = self.framework.newPostProcessEngine(TESTPOINTS)
         if planes:
             self.forces.setplanes(planes)
+        self.graphs = bool(graphs) and self.device_dt
+        self._graphs = {}                 # (state buffers, numParticles, range end) -> [eager runs so far, CUDAGraph | None]
         self.last_neibs_info = None
         self.total_interactions = 0       # sum over steps of list entries x 2 force evaluations
         self.launches = 0                 # hand-written kernels launched (CUB's sort passes not counted)
@@ -209,17 +219,10 @@ class Worker:
         cur, oth = self.cur, 1 - self.cur
         rd, wr = self.state(cur), self.state(oth)
         if self.device_dt:
-            # everything enqueued, nothing read back: forces(n) -> dt candidate 1 -> euler step 1 (dt/2) ->
-            # forces(n*) -> dt candidate 2 -> euler step 2 (dt) -> t += dt, dt = min(candidates)
-            for which, st in ((1, rd), (2, wr)):
-                if self.clobber:
-                    self.forces_buf.zero_()
-                if self.xsph is not None:
-                    self.xsph.zero_()
-                nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True)
-                self.forces.dtreduce_async(st, nblocks, which)
-                self.integration.basicstep_async(rd, wr, n, end, which)
-            self.forces.step_end()
+            if self.graphs:
+                self._step_graph(cur, n, end)
+            else:
+                self._enqueue_step(rd, wr, n, end)
             self.launches += 2 * 3 + 1
             self._stale = True
         else:
@@ -238,6 +241,147 @@ class Worker:
         self.iterations += 1
         if self.last_neibs_info is not None:
             self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
+
+    def _enqueue_step(self, rd: BufferList, wr: BufferList, n: int, end: int) -> None:
+        """Everything enqueued, nothing read back: forces(n) -> dt candidate 1 -> euler step 1 (dt/2) -> forces(n*) ->
+        dt candidate 2 -> euler step 2 (dt) -> t += dt, dt = min(candidates)."""
+        for which, st in ((1, rd), (2, wr)):
+            if self.clobber:
+                self.forces_buf.zero_()
+            if self.xsph is not None:
+                self.xsph.zero_()
+            nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True)
+            self.forces.dtreduce_async(st, nblocks, which)
+            self.integration.basicstep_async(rd, wr, n, end, which)
+        self.forces.step_end()
+
+    def _step_graph(self, cur: int, n: int, end: int) -> None:
+        """One time step as a CUDA graph replay. The step's launches depend only on which of the two states is "step n"
+        and on the particle counts, so one graph per (state, counts) is captured (after one eager run that fills the
+        library's lazily sized scratch) and replayed until the next neighbour rebuild changes the counts."""
+        # the buffers a graph was captured with are part of its identity (filters swap the two VEL buffers)
+        key = (self.pos[cur].data_ptr(), self.vel[cur].data_ptr(), self.pos[1 - cur].data_ptr(), self.vel[1 - cur].data_ptr(), n, end)
+        slot = self._graphs.setdefault(key, [0, None])
+        rd, wr = self.state(cur), self.state(1 - cur)
+        if slot[1] is None:
+            if slot[0] < 1:
+                slot[0] += 1
+                self._enqueue_step(rd, wr, n, end)
+                return
+            if len(self._graphs) > 8:            # counts changed at rebuilds: drop graphs of stale shapes
+                for k in [k for k in self._graphs if k[4:] != (n, end)]:
+                    del self._graphs[k]
+            ctx = self.framework.ctx
+            main = ctx.stream
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(main)
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, stream=side):
+                    ctx.use_stream(torch.cuda.current_stream(self.device))
+                    self._enqueue_step(rd, wr, n, end)
+            finally:
+                ctx.use_stream(main)
+            main.wait_stream(side)
+            slot[1] = g
+        slot[1].replay()
+
+    # ---- stepping a state that lives in HOST memory (the e2e path of bench.py) ----
+    def _stripes(self) -> list:
+        """Particle ranges [a, b) made of whole COORD3 cell layers, so that every neighbour of a particle of stripe s
+        lies in stripes s-1, s or s+1 (cells are sorted by hash and COORD3 is the slowest hash digit). Cached per
+        neighbour rebuild (one small readback)."""
+        key = (self.iterations // self.buildneibsfreq, self.numParticles)
+        if getattr(self, "_stripes_key", None) == key:
+            return self._stripes_val
+        n = self.numParticles
+        c = self.params.coord
+        S = int(self.params.grid_size[c[0]]) * int(self.params.grid_size[c[1]])
+        cs2 = self.cellstart.view(-1, S)
+        big = torch.iinfo(torch.int32).max
+        first = torch.where(cs2 != -1, cs2, big).min(dim=1).values.cpu().numpy().astype(np.int64)
+        starts = sorted(set(int(x) for x in first if x != big and 0 < x < n))
+        bounds = [0]
+        for k in range(1, self.host_stripes):
+            target = n * k // self.host_stripes
+            nxt = next((x for x in starts if x >= target), None)
+            if nxt is not None and nxt > bounds[-1]:
+                bounds.append(nxt)
+        bounds.append(n)
+        self._stripes_key, self._stripes_val = key, [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        return self._stripes_val
+
+    def step_host(self, hpos: torch.Tensor, hvel: torch.Tensor) -> None:
+        """One time step of a state owned by the HOST: hpos / hvel (pinned, [allocated, 4] float32, sorted order) hold
+        state n on entry and state n+1 on return (after torch.cuda.synchronize()). Results are bitwise those of step().
+
+        Between neighbour rebuilds the copies are pipelined with the force evaluations in stripes of whole cell layers
+        on three streams: the predictor's forces of stripe s start as soon as stripes <= s+1 have arrived, and the
+        corrector integrates stripe s (in place, into the state-n buffers) and sends it back while the forces of the
+        later stripes are still running. A rebuild step (1 in buildneibsfreq) re-sorts the particles: plain
+        upload / step / download."""
+        n = self.numParticles
+        rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
+        wraps = bool(self.params.periodic & (1 << self.params.coord[2]))     # first and last cell layer are neighbours
+        if rebuild or not self.device_dt or self.filters or self.particleRangeEnd != n or wraps:
+            self.pos[self.cur][:n].copy_(hpos[:n], non_blocking=True)
+            self.vel[self.cur][:n].copy_(hvel[:n], non_blocking=True)
+            self.step()
+            n = self.numParticles
+            hpos[:n].copy_(self.pos[self.cur][:n], non_blocking=True)
+            hvel[:n].copy_(self.vel[self.cur][:n], non_blocking=True)
+            return
+        ctx = self.framework.ctx
+        C = ctx.stream
+        if not hasattr(self, "_up"):
+            self._up, self._down = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        U, D = self._up, self._down
+        stripes = self._stripes()
+        cur, oth = self.cur, 1 - self.cur
+        pos, vel = self.pos[cur], self.vel[cur]
+        rd, wr = self.state(cur), self.state(oth)
+        # uploads: after everything that still reads / writes the state-n buffers
+        U.wait_stream(C)
+        U.wait_stream(D)
+        ups = []
+        with torch.cuda.stream(U):
+            for a, b in stripes:
+                pos[a:b].copy_(hpos[a:b], non_blocking=True)
+                vel[a:b].copy_(hvel[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(U)
+                ups.append(ev)
+        # predictor: forces(n) stripe by stripe behind the uploads, then dt candidate 1 and euler step 1 (dt/2) -> n*
+        off = 0
+        for k, (a, b) in enumerate(stripes):
+            C.wait_event(ups[min(k + 1, len(stripes) - 1)])
+            if self.xsph is not None:
+                self.xsph[a:b].zero_()
+            off += self.forces.basicstep(rd, rd, n, a, b, off, step=1, dt_from_device=True)
+        self.forces.dtreduce_async(rd, off, 1)
+        self.integration.basicstep_async(rd, wr, n, n, 1)
+        # corrector: forces(n*) of stripe s, euler step 2 of stripe s IN PLACE into the state-n buffers (elementwise; the
+        # forces of later stripes read n*, not these), download of stripe s
+        off = 0
+        for a, b in stripes:
+            if self.xsph is not None:
+                self.xsph[a:b].zero_()
+            off += self.forces.basicstep(wr, wr, n, a, b, off, step=2, dt_from_device=True)
+            sl = BufferList({k_: v[a:b] for k_, v in rd.items() if k_ in _PER_PARTICLE})
+            self.integration.basicstep_async(sl, sl, b - a, b - a, 2)
+            ev = torch.cuda.Event()
+            ev.record(C)
+            with torch.cuda.stream(D):
+                D.wait_event(ev)
+                hpos[a:b].copy_(pos[a:b], non_blocking=True)
+                hvel[a:b].copy_(vel[a:b], non_blocking=True)
+        self.forces.dtreduce_async(wr, off, 2)
+        self.forces.step_end()
+        C.wait_stream(D)                  # a following synchronize of the compute stream covers the downloads
+        self.launches += 2 * len(stripes) * 2 + 4
+        self._stale = True
+        self.iterations += 1              # state n+1 is in the SAME buffers: self.cur does not flip
+        self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
 
     def forces_once(self) -> None:
         """One force evaluation on the current state (bench.py roofline timing)."""

@@ -67,3 +67,33 @@ class OracleBackend:
 
     def fmax_elements(self, n):
         return ((n + 127) // 128 + 3) // 4 * 4
+
+
+class OracleDeviceDtBackend(OracleBackend):
+    """OracleBackend + a host emulation of the device-resident dt record (b200sph_step_* / b200sph_cflmax), so that the
+    SlabWorker's device-dt control flow (deferred, once-per-step all-reduce of the CFL maxima) runs on gloo too."""
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.st = dict(t=0.0, it=0, dt=0.0, dt1=0.0, dt2=0.0)
+
+    def step_set_dt(self, dt):
+        self.st.update(dt=float(np.float32(dt)), dt1=float(np.float32(dt)), dt2=float(np.float32(dt)))
+
+    def cflmax(self, cfl, nblocks, out):
+        _np(out)[0] = _np(cfl)[:nblocks].max() if nblocks else 0.0
+
+    def dtreduce_async(self, cfl, nblocks, which):
+        self.st["dt1" if which == 1 else "dt2"] = ob.dtreduce(self.params, _np(cfl)[:nblocks])
+
+    def euler_async(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, step):
+        dt = np.float32(self.st["dt"])
+        self.euler(opos, ovel, info, hashv, forces, npos, nvel, n, range_end, float(dt / np.float32(2)) if step == 1 else float(dt), step)
+
+    def step_end(self):
+        self.st["t"] += self.st["dt"]
+        self.st["it"] += 1
+        self.st["dt"] = min(self.st["dt1"], self.st["dt2"])
+
+    def step_query(self):
+        return self.st["t"], self.st["dt"], self.st["it"]

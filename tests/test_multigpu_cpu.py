@@ -27,14 +27,15 @@ def make_problem():
     return params, parts
 
 
-def _rank_main(rank, world, port, steps, outdir):
+def _rank_main(rank, world, port, steps, outdir, device_dt=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     from gpusph_b200.multigpu import SlabWorker
-    from oracle_backend import OracleBackend
+    from oracle_backend import OracleBackend, OracleDeviceDtBackend
     params, parts = make_problem()
-    w = SlabWorker(params, parts, None, rank=rank, world=world, backend=OracleBackend)
+    w = SlabWorker(params, parts, None, rank=rank, world=world, backend=OracleDeviceDtBackend if device_dt else OracleBackend)
+    assert w.device_dt == device_dt
     own0 = None
     dts = []
     for _ in range(steps):
@@ -72,7 +73,10 @@ def test_partition_and_device_map():
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_gloo_run_matches_single_domain_bitwise():
+@pytest.mark.parametrize("device_dt", [False, True], ids=["host_dt", "deferred_device_dt"])
+def test_two_rank_gloo_run_matches_single_domain_bitwise(device_dt):
+    """device_dt: the production control flow on GPUs — dt record owned by the backend, CFL maxima of both force
+    evaluations all-reduced once per step, asynchronously, and consumed just before the next step's first euler."""
     import oracle_binding as ob
     steps = 12
     params, parts = make_problem()
@@ -84,7 +88,7 @@ def test_two_rank_gloo_run_matches_single_domain_bitwise():
     exp = ref.download()
     with tempfile.TemporaryDirectory() as d:
         port = 29500 + (os.getpid() % 2000)
-        mp.spawn(_rank_main, args=(2, port, steps, d), nprocs=2, join=True)
+        mp.spawn(_rank_main, args=(2, port + int(device_dt), steps, d, device_dt), nprocs=2, join=True)
         r = [np.load(os.path.join(d, f"rank{k}.npz")) for k in range(2)]
     # same adaptive time-step sequence on both ranks and in the single-domain run
     assert np.array_equal(r[0]["dts"], r[1]["dts"])

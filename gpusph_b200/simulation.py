@@ -69,7 +69,8 @@ class Worker:
         self.cellend = torch.empty(ncells, dtype=torch.int32, device=dev)
         self.neibslist = torch.empty((int(self.params.neiblistsize), A), dtype=torch.int16, device=dev)
         self.neibslist.fill_(-1)
-        self.host_stripes = 8             # stripes of the pipelined host-buffer step (step_host)
+        self.host_stripes = 8             # stripes of the pipelined host-buffer step (step_host) ...
+        self.host_stripe_min = 200_000    # ... of at least this many particles each
         # striped force evaluations round every stripe's CFL blocks up to a multiple of 4: room for that
         ncfl = self.forces.getFmaxElements(A) + 4 * (self.host_stripes + 1)
         self.cfl = torch.zeros(ncfl, dtype=torch.float32, device=dev)
@@ -301,9 +302,11 @@ class Worker:
         big = torch.iinfo(torch.int32).max
         first = torch.where(cs2 != -1, cs2, big).min(dim=1).values.cpu().numpy().astype(np.int64)
         starts = sorted(set(int(x) for x in first if x != big and 0 < x < n))
+        # small systems: the per-stripe launch / event overhead outweighs the overlap
+        want = max(1, min(self.host_stripes, n // self.host_stripe_min))
         bounds = [0]
-        for k in range(1, self.host_stripes):
-            target = n * k // self.host_stripes
+        for k in range(1, want):
+            target = n * k // want
             nxt = next((x for x in starts if x >= target), None)
             if nxt is not None and nxt > bounds[-1]:
                 bounds.append(nxt)
@@ -323,7 +326,7 @@ class Worker:
         n = self.numParticles
         rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
         wraps = bool(self.params.periodic & (1 << self.params.coord[2]))     # first and last cell layer are neighbours
-        if rebuild or not self.device_dt or self.filters or self.particleRangeEnd != n or wraps:
+        if rebuild or not self.device_dt or self.filters or self.particleRangeEnd != n or wraps or len(self._stripes()) < 2:
             self.pos[self.cur][:n].copy_(hpos[:n], non_blocking=True)
             self.vel[self.cur][:n].copy_(hvel[:n], non_blocking=True)
             self.step()

@@ -289,6 +289,7 @@ def test_pipelined_host_stepping_equals_resident_stepping_bitwise(name):
     params, parts = tg.get(name)
     a = Worker(params, parts, 0)
     b = Worker(params, parts, 0)
+    a.host_stripes, a.host_stripe_min = 6, 1000       # stripe even this small system
     A = a.pos[0].shape[0]
     hp, hv = torch.zeros((A, 4)).pin_memory(), torch.zeros((A, 4)).pin_memory()
     n = a.numParticles

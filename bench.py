@@ -296,6 +296,7 @@ def main():
         esteps = max(freq, int(round(args.steps / 2 / freq)) * freq)      # whole rebuild periods: 1 rebuild step in `freq`
         pipelined = world == 1 and not args.no_pipeline
         traffic = [0, 0]
+        side = torch.cuda.Stream()
 
         def e2e_step():
             # host -> device: the step's inputs = the evolving state n (pos, vel) of this rank's slab. info/hash are
@@ -318,10 +319,17 @@ def main():
                 hp[1][:n].copy_(w.vel[w.cur][:n], non_blocking=True)
             traffic[1] += n * 32
             if rebuilt:
-                hi[:n].copy_(w.info[:n], non_blocking=True)
-                hh[:n].copy_(w.hash[:n], non_blocking=True)
+                # the re-sorted info / hash go back on a side stream (they do not change until the next rebuild)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    hi[:n].copy_(w.info[:n], non_blocking=True)
+                    hh[:n].copy_(w.hash[:n], non_blocking=True)
                 traffic[1] += n * 12
-            torch.cuda.synchronize()
+            if not pipelined:
+                torch.cuda.synchronize()
+            # pipelined: no host synchronisation between steps. Step n+1's upload of a stripe is ordered after step n's
+            # download of that stripe by events inside the library (b200sph_step_host), so every byte uploaded is a
+            # byte the previous step downloaded into the host buffers.
 
         # untimed: first use of this path (side streams, stripe table), then up to the next neighbour rebuild so that the
         # timed region holds whole rebuild periods
@@ -335,6 +343,9 @@ def main():
         for _ in range(esteps):
             e2e_step()
         h2d, d2h = traffic
+        if pipelined:
+            w.host_fence()               # the compute stream (where e1 is recorded) waits for the last downloads
+        torch.cuda.current_stream().wait_stream(side)
         e1.record()
         barrier()
         et = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -368,6 +379,9 @@ def main():
         t_kernel = timed(w.forces_once)
         # a streaming kernel for comparison: euler reads pos, vel, forces, info (56 B) and writes pos, vel (32 B)
         t_euler = timed(w.euler_once)
+        # one whole neighbour rebuild (calcHash, sort, reorder, list build; two small readbacks), every 10th step
+        reps = 3
+        t_rebuild = timed(w.build_neibs)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -382,6 +396,7 @@ def main():
                     "timed": "one forces_gather_kernel launch (= one force evaluation), CUDA events, L2 flushed between launches",
                     "streaming_reference": {"kernel": "euler_kernel", "algorithmic_bytes_per_particle": 88, "kernel_ms": t_euler,
                                             "achieved": 88 * n / (t_euler / 1e3) / 1e9, "frac": 88 * n / (t_euler / 1e3) / 1e9 / peak},
+                    "neighbour_rebuild_ms": t_rebuild,
                     "pair_rate_G_per_s": w.last_neibs_info.num_interactions / (t_kernel / 1e3) / 1e9,
                     "note": "the pair kernel is instruction-issue / L1-gather bound (ncu: issue 76 %, L1TEX 87 %, DRAM 8 %; profiles/r01_forces_gather_dambreak2m_ncu.txt), not HBM bound (SURVEY.md 8d); the HBM fraction is reported because the contract asks for it"}
         tr = os.path.join(ROOT, "profiles", "forces_traffic.json")

@@ -111,6 +111,21 @@ class ForcesArgs(C.Structure):
     ]
 
 
+class HostStepArgs(C.Structure):
+    """struct b200sph_host_step_args (include/b200sph.h): one time step of a state that lives in host memory."""
+    _fields_ = [
+        ("host_pos", C.c_void_p), ("host_vel", C.c_void_p),
+        ("pos", C.c_void_p), ("vel", C.c_void_p), ("pos_star", C.c_void_p), ("vel_star", C.c_void_p),
+        ("info", C.c_void_p), ("hash", C.c_void_p), ("cell_start", C.c_void_p), ("neibs_list", C.c_void_p),
+        ("forces", C.c_void_p), ("cfl", C.c_void_p), ("xsph", C.c_void_p),
+        ("cfl_elements", C.c_uint32), ("num_particles", C.c_uint32),
+        ("stripe_bounds", C.POINTER(C.c_uint32)), ("num_stripes", C.c_uint32), ("resident", C.c_int),
+    ]
+
+
+MAX_STRIPES = 32
+
+
 class ReorderExtra(C.Structure):
     _fields_ = [("unsorted", C.c_void_p), ("sorted", C.c_void_p), ("elem_size", C.c_uint32)]
 
@@ -163,6 +178,10 @@ PROTOTYPES = {
     "b200sph_step_end": (C.c_int, [_P]),
     "b200sph_step_query": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "b200sph_euler": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_float, C.c_int]),
+    "b200sph_step_host": (C.c_int, [_P, C.POINTER(HostStepArgs)]),
+    "b200sph_host_upload": (C.c_int, [_P, _P, _P, _P, _P, _U]),
+    "b200sph_host_fence": (C.c_int, [_P]),
+    "b200sph_host_sync": (C.c_int, [_P]),
 }
 
 _lib = None

@@ -141,6 +141,7 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 {
 	if (!ctx) return B200SPH_OK;
 	cudaSetDevice(ctx->device);
+	b200_hoststep_destroy(ctx);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
 	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->plist); cudaFree(ctx->pcount); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);

@@ -111,6 +111,7 @@ struct StepState {
 	float dt, dt1, dt2, pad;
 };
 
+#define B200_MAX_LANES 2
 struct b200sph_ctx {
 	b200sph_params hp;      // host copy
 	DevParams dp;
@@ -138,6 +139,17 @@ struct b200sph_ctx {
 	int *d_flag; int *h_flag;
 	StepState *d_step; StepState *h_step;
 	BodyData *d_bodies; BodyData *h_bodies; int have_bodies;
+	// pipelined stepping of a host-resident state (hoststep.cu): copy streams, per-stripe events, and what the
+	// previous call left in flight (the next call chains on it stripe by stripe)
+	cudaStream_t up_stream, down_stream;
+	cudaEvent_t up_ev[B200SPH_MAX_STRIPES], down_ev[B200SPH_MAX_STRIPES], comp_ev[B200SPH_MAX_STRIPES], pred_ev[B200SPH_MAX_STRIPES];
+	cudaEvent_t fence_ev, up_all_ev, down_all_ev;
+	cudaStream_t lane_stream[B200_MAX_LANES]; int host_lanes;        // extra compute lanes ([0] unused: the context's stream)
+	cudaEvent_t fork_ev[2], join_ev[2 * B200_MAX_LANES];
+	uint32_t host_bounds[B200SPH_MAX_STRIPES + 1]; uint32_t host_nstripes;
+	const void *host_pos_last, *host_vel_last, *dev_pos_last, *dev_vel_last;
+	int host_pending;
+	cudaEvent_t *trace_ev; int trace_resident;      // B200SPH_HOST_TRACE diagnostics
 };
 
 // ---- error plumbing ----
@@ -189,3 +201,4 @@ int b200_coop_list(b200sph_ctx *ctx, const void *info, const void *pos, const ui
 	const uint16_t *neibs_list, uint n);
 void b200_invalidate_coop(b200sph_ctx *ctx);
 void b200_invalidate_tiles(b200sph_ctx *ctx);
+void b200_hoststep_destroy(b200sph_ctx *ctx);

@@ -682,6 +682,18 @@ static int gather_carveout(const void *kernel)
 	return result;
 }
 
+// the carve-out preference is a per-device function attribute: set it once per (kernel, device), not per launch
+// (cudaFuncSetAttribute costs as much host time as the launch itself, and the striped host-buffer step launches 16
+// grids per time step)
+static int set_carveout(const b200sph_ctx *ctx, const void *kernel)
+{
+	static const void *known[256]; static int dev[256]; static int nknown = 0;
+	for (int i = 0; i < nknown; ++i) if (known[i] == kernel && dev[i] == ctx->device) return B200SPH_OK;
+	CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout(kernel)));
+	if (nknown < 256) { known[nknown] = kernel; dev[nknown] = ctx->device; ++nknown; }
+	return B200SPH_OK;
+}
+
 extern "C" int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel, const void *info,
 	const uint32_t *hash, const uint32_t *cell_start, const uint16_t *neibs_list,
 	void *forces, float *cfl, uint32_t num_particles, uint32_t from, uint32_t to,
@@ -748,7 +760,7 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
 		gather_kernel_t gk = wide ? forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, true>
 		                          : forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, false>;
-		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout((const void *)gk)));
+		{ const int rc = set_carveout(ctx, (const void *)gk); if (rc) return rc; }
 		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(dp_launch, (const float4 *)pos, (const float4 *)vel,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
 		KERNEL_TRY();
@@ -784,14 +796,14 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
 		const uint first_warp = from / COOP_PPW, end_warp = div_up(to, COOP_PPW);
 		const uint grid = div_up(end_warp - first_warp, COOP_BLOCK / 32);
-		CUDA_TRY(cudaFuncSetAttribute((const void *)ck, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout((const void *)ck)));
+		{ const int rc = set_carveout(ctx, (const void *)ck); if (rc) return rc; }
 		ck<<<grid, COOP_BLOCK, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel, (const ushort4 *)info, hash,
 			ctx->plist, ctx->pcount, div_up(d.neiblistsize, COOP_LPP), (float4 *)forces, cfl, bo, from, to, cfl_offset);
 	} else {
 		// 32-bit list offsets unless the list has 2^31 entries or more
 		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
 		gather_kernel_t gk = gks[wide ? 1 : 0];
-		CUDA_TRY(cudaFuncSetAttribute((const void *)gk, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout((const void *)gk)));
+		{ const int rc = set_carveout(ctx, (const void *)gk); if (rc) return rc; }
 		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
 	}

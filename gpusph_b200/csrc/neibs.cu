@@ -336,6 +336,9 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
 	uint nf = 0, nb = 0, nv = 0;
 	const size_t stride = P.stride;
+	// the search radius is used once per candidate: passing it through a shuffle pins it in a register (ptxas would
+	// otherwise re-load it from the constant bank inside the candidate loop)
+	const float R2_pinned = __shfl_sync(0xffffffffu, P.nlSqInflRad, 0);
 
 	if (index < numParticles) {
 		const ushort4 info = infoArray[index];
@@ -347,6 +350,7 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 		if (build_nl && !inactive_w(pos.w)) {
 			const int3 gp = grid_pos(P, particleHash[index] & CELLTYPE_BITMASK);
 			const bool boundary = mytype == PT_BOUNDARY;
+			const float R2 = R2_pinned;
 			for (int z = -1; z <= 1; ++z) for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) {
 				int gx = gp.x + x, gy = gp.y + y, gz = gp.z + z;
 				// calcNeibCell :317-384
@@ -378,9 +382,41 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 				const bool uniform = t_first == t_last;
 				const bool skip_bb = boundary && (P.boundarytype == B200SPH_DYN_BOUNDARY || P.boundarytype == B200SPH_LJ_BOUNDARY);
 				if (uniform && (t_first == PT_TESTPOINT || (skip_bb && t_first == PT_BOUNDARY))) continue;
+				// appends candidate j (already known to be inside the search radius) exactly like neibsInCell :618-634
+				auto append = [&](const uint j, const int nt) {
+					const uint cnt = nt == PT_FLUID ? nf : (nt == PT_BOUNDARY ? nb : nv);
+					const uint offset = neib_list_offset(P, cnt, nt);
+					if (nt == PT_FLUID) ++nf; else if (nt == PT_BOUNDARY) ++nb; else ++nv;
+					if (!too_many_neibs(P, nf, nb, nv, nt)) {                             // :626-634
+						const uint enc = encode_cell ? ((cell + 1) << CELLNUM_SHIFT) : 0u;
+						neibsList[offset * stride + index] = (ushort)((j - bucketStart) + enc);
+						encode_cell = false;
+					}
+				};
+				if (uniform) {
+					// one particle type in the whole cell (the common case): nothing but the distance test per candidate.
+					// The empty asm keeps the cell's base pointer in registers (otherwise it is re-derived from the
+					// constant bank for every candidate).
+					const float4 *cand = posArray + bucketStart;
+					asm volatile("" : "+l"(cand));
+					const uint count = bucketEnd - bucketStart;
+					const uint self = index - bucketStart;                              // >= count when in another cell
+#pragma unroll 2
+					for (uint k = 0; k < count; ++k) {
+						const float4 np = __ldg(cand + k);
+						const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);
+						// sqlength(relPos) = x*x + y*y + z*z as nvcc contracts it
+						const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
+						if (r2 < R2) {                                                  // :386-392 (85 % of the candidates fail)
+							// :553 self, :612 an inactive candidate has a non-finite w
+							if (k != self && !inactive_w(np.w)) append(bucketStart + k, t_first);
+						}
+					}
+					continue;
+				}
 				for (uint j = bucketStart; j < bucketEnd; ++j) {
 					if (j == index) continue;
-					const int nt = uniform ? t_first : ptype_of(__ldg(infoArray + j));
+					const int nt = ptype_of(__ldg(infoArray + j));
 					if (nt == PT_TESTPOINT) continue;                                     // :584
 					if (!encode_cell && neib_type != nt) encode_cell = true;             // :588
 					neib_type = nt;
@@ -390,16 +426,7 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);
 					// sqlength(relPos) = x*x + y*y + z*z as nvcc contracts it
 					const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
-					if (r2 < P.nlSqInflRad) {                                             // :386-392
-						const uint cnt = nt == PT_FLUID ? nf : (nt == PT_BOUNDARY ? nb : nv);
-						const uint offset = neib_list_offset(P, cnt, nt);
-						if (nt == PT_FLUID) ++nf; else if (nt == PT_BOUNDARY) ++nb; else ++nv;
-						if (!too_many_neibs(P, nf, nb, nv, nt)) {                         // :626-634
-							const uint enc = encode_cell ? ((cell + 1) << CELLNUM_SHIFT) : 0u;
-							neibsList[offset * stride + index] = (ushort)((j - bucketStart) + enc);
-							encode_cell = false;
-						}
-					}
+					if (r2 < R2) append(j, nt);                                           // :386-392
 				}
 			}
 		}

@@ -7,6 +7,9 @@ src/Integrator.cc:93-249, src/GPUSPH.cc:636-699). torch is used for device memor
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 import numpy as np
 import torch
 
@@ -69,10 +72,11 @@ class Worker:
         self.cellend = torch.empty(ncells, dtype=torch.int32, device=dev)
         self.neibslist = torch.empty((int(self.params.neiblistsize), A), dtype=torch.int16, device=dev)
         self.neibslist.fill_(-1)
-        self.host_stripes = 8             # stripes of the pipelined host-buffer step (step_host) ...
-        self.host_stripe_min = 200_000    # ... of at least this many particles each
+        # stripes of the pipelined host-buffer step (step_host) ... of at least this many particles each
+        self.host_stripes = min(int(os.environ.get("B200SPH_HOST_STRIPES", "8")), capi.MAX_STRIPES)
+        self.host_stripe_min = int(os.environ.get("B200SPH_HOST_STRIPE_MIN", "200000"))
         # striped force evaluations round every stripe's CFL blocks up to a multiple of 4: room for that
-        ncfl = self.forces.getFmaxElements(A) + 4 * (self.host_stripes + 1)
+        ncfl = 2 * (self.forces.getFmaxElements(A) + 4 * (capi.MAX_STRIPES + 1))
         self.cfl = torch.zeros(ncfl, dtype=torch.float32, device=dev)
         self.cfl_temp = torch.zeros(max(self.forces.getFmaxTempElements(ncfl), 4), dtype=torch.float32, device=dev)
         self.new_num = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -147,7 +151,9 @@ class Worker:
         return b
 
     # ---- NEIBS_LIST phase (src/Integrator.cc:93-249) ----
-    def build_neibs(self) -> None:
+    def build_neibs(self, _fenced: bool = False) -> None:
+        if not _fenced:
+            self.host_fence()
         n = self.numParticles
         cur, oth = self.cur, 1 - self.cur
         s = self.state(cur)
@@ -212,6 +218,7 @@ class Worker:
 
     def step(self) -> None:
         """One predictor-corrector time step (src/integrators/PredictorCorrectorIntegrator.cc:917-1068)."""
+        self.host_fence()
         if self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None:
             self.build_neibs()
         if self.filters:
@@ -316,17 +323,22 @@ class Worker:
 
     def step_host(self, hpos: torch.Tensor, hvel: torch.Tensor) -> None:
         """One time step of a state owned by the HOST: hpos / hvel (pinned, [allocated, 4] float32, sorted order) hold
-        state n on entry and state n+1 on return (after torch.cuda.synchronize()). Results are bitwise those of step().
+        state n on entry and state n+1 once the copies have landed (host_sync() or torch.cuda.synchronize()); nothing
+        is synchronised here, and consecutive calls chain on each other stripe by stripe. Results are bitwise those of
+        step(). The work is done by the library (b200sph_step_host, csrc/hoststep.cu): uploads, striped force
+        evaluations, in-place corrector and downloads pipelined on three streams.
 
-        Between neighbour rebuilds the copies are pipelined with the force evaluations in stripes of whole cell layers
-        on three streams: the predictor's forces of stripe s start as soon as stripes <= s+1 have arrived, and the
-        corrector integrates stripe s (in place, into the state-n buffers) and sends it back while the forces of the
-        later stripes are still running. A rebuild step (1 in buildneibsfreq) re-sorts the particles: plain
-        upload / step / download."""
+        A step that starts with a neighbour rebuild (1 in buildneibsfreq) needs the whole state before the sort: chained
+        upload, rebuild, then the same pipelined step on the (re-sorted) resident state."""
+        lib, ctx = self.framework.ctx.lib, self.framework.ctx
         n = self.numParticles
+        if not (hpos.is_pinned() and hvel.is_pinned()):
+            raise ValueError("step_host needs pinned host buffers")
         rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
         wraps = bool(self.params.periodic & (1 << self.params.coord[2]))     # first and last cell layer are neighbours
-        if rebuild or not self.device_dt or self.filters or self.particleRangeEnd != n or wraps or len(self._stripes()) < 2:
+        if not self.device_dt or self.filters or self.particleRangeEnd != n or wraps:
+            # configurations the pipelined entry point does not serve: plain upload / step / download
+            self.host_fence()
             self.pos[self.cur][:n].copy_(hpos[:n], non_blocking=True)
             self.vel[self.cur][:n].copy_(hvel[:n], non_blocking=True)
             self.step()
@@ -334,57 +346,45 @@ class Worker:
             hpos[:n].copy_(self.pos[self.cur][:n], non_blocking=True)
             hvel[:n].copy_(self.vel[self.cur][:n], non_blocking=True)
             return
-        ctx = self.framework.ctx
-        C = ctx.stream
-        if not hasattr(self, "_up"):
-            self._up, self._down = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
-        U, D = self._up, self._down
+        if rebuild:
+            capi.check(lib.b200sph_host_upload(ctx.handle, hpos.data_ptr(), hvel.data_ptr(), self.pos[self.cur].data_ptr(),
+                                               self.vel[self.cur].data_ptr(), n))
+            self.build_neibs(_fenced=True)
+            n = self.numParticles
         stripes = self._stripes()
         cur, oth = self.cur, 1 - self.cur
-        pos, vel = self.pos[cur], self.vel[cur]
-        rd, wr = self.state(cur), self.state(oth)
-        # uploads: after everything that still reads / writes the state-n buffers
-        U.wait_stream(C)
-        U.wait_stream(D)
-        ups = []
-        with torch.cuda.stream(U):
-            for a, b in stripes:
-                pos[a:b].copy_(hpos[a:b], non_blocking=True)
-                vel[a:b].copy_(hvel[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(U)
-                ups.append(ev)
-        # predictor: forces(n) stripe by stripe behind the uploads, then dt candidate 1 and euler step 1 (dt/2) -> n*
-        off = 0
-        for k, (a, b) in enumerate(stripes):
-            C.wait_event(ups[min(k + 1, len(stripes) - 1)])
-            if self.xsph is not None:
-                self.xsph[a:b].zero_()
-            off += self.forces.basicstep(rd, rd, n, a, b, off, step=1, dt_from_device=True)
-        self.forces.dtreduce_async(rd, off, 1)
-        self.integration.basicstep_async(rd, wr, n, n, 1)
-        # corrector: forces(n*) of stripe s, euler step 2 of stripe s IN PLACE into the state-n buffers (elementwise; the
-        # forces of later stripes read n*, not these), download of stripe s
-        off = 0
-        for a, b in stripes:
-            if self.xsph is not None:
-                self.xsph[a:b].zero_()
-            off += self.forces.basicstep(wr, wr, n, a, b, off, step=2, dt_from_device=True)
-            sl = BufferList({k_: v[a:b] for k_, v in rd.items() if k_ in _PER_PARTICLE})
-            self.integration.basicstep_async(sl, sl, b - a, b - a, 2)
-            ev = torch.cuda.Event()
-            ev.record(C)
-            with torch.cuda.stream(D):
-                D.wait_event(ev)
-                hpos[a:b].copy_(pos[a:b], non_blocking=True)
-                hvel[a:b].copy_(vel[a:b], non_blocking=True)
-        self.forces.dtreduce_async(wr, off, 2)
-        self.forces.step_end()
-        C.wait_stream(D)                  # a following synchronize of the compute stream covers the downloads
+        key = (self._stripes_key, cur, hpos.data_ptr(), hvel.data_ptr())
+        if getattr(self, "_host_args_key", None) != key:
+            bounds = (C.c_uint32 * (len(stripes) + 1))(*([a for a, _ in stripes] + [stripes[-1][1]]))
+            a = capi.HostStepArgs()
+            a.host_pos, a.host_vel = hpos.data_ptr(), hvel.data_ptr()
+            a.pos, a.vel = self.pos[cur].data_ptr(), self.vel[cur].data_ptr()
+            a.pos_star, a.vel_star = self.pos[oth].data_ptr(), self.vel[oth].data_ptr()
+            a.info, a.hash = self.info.data_ptr(), self.hash.data_ptr()
+            a.cell_start, a.neibs_list = self.cellstart.data_ptr(), self.neibslist.data_ptr()
+            a.forces, a.cfl = self.forces_buf.data_ptr(), self.cfl.data_ptr()
+            a.xsph = self.xsph.data_ptr() if self.xsph is not None else None
+            a.cfl_elements, a.num_particles = self.cfl.numel(), n
+            a.stripe_bounds, a.num_stripes = bounds, len(stripes)
+            self._host_args_key, self._host_args, self._host_bounds = key, a, bounds
+        a = self._host_args
+        a.resident = 1 if rebuild else 0
+        capi.check(lib.b200sph_step_host(ctx.handle, C.byref(a)))
+        self._host_pending = True
         self.launches += 2 * len(stripes) * 2 + 4
         self._stale = True
         self.iterations += 1              # state n+1 is in the SAME buffers: self.cur does not flip
         self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
+
+    def host_fence(self) -> None:
+        """The compute stream waits for the copies of earlier step_host calls (before anything else uses the state)."""
+        if getattr(self, "_host_pending", False):
+            capi.check(self.framework.ctx.lib.b200sph_host_fence(self.framework.ctx.handle))
+            self._host_pending = False
+
+    def host_sync(self) -> None:
+        """Block until the state written by the last step_host has landed in the host buffers."""
+        capi.check(self.framework.ctx.lib.b200sph_host_sync(self.framework.ctx.handle))
 
     def forces_once(self) -> None:
         """One force evaluation on the current state (bench.py roofline timing)."""
@@ -398,6 +398,7 @@ class Worker:
 
     # ---- host copies ----
     def download(self) -> ParticleArrays:
+        self.host_fence()
         n = self.numParticles
         return ParticleArrays(
             pos=self.pos[self.cur][:n].cpu().numpy(),

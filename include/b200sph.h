@@ -371,6 +371,48 @@ int b200sph_euler_async(b200sph_ctx *ctx, const void *old_pos, const void *old_v
 int b200sph_step_end(b200sph_ctx *ctx);
 int b200sph_step_query(b200sph_ctx *ctx, double *t, float *dt, uint64_t *iterations);
 
+/* ---- stepping a state that lives in HOST memory (no reference counterpart) ----
+ * The reference keeps the particle state on the device and moves it only for writes (GPUWorker::dumpBuffers,
+ * src/GPUWorker.cc:1227-1300). A caller whose state lives in (pinned) host memory gets one call per time step:
+ * b200sph_step_host uploads state n, runs the command sequence of one predictor-corrector step
+ * (src/integrators/PredictorCorrectorIntegrator.cc:917-1068: forces, dt candidate, euler dt/2, forces, dt candidate,
+ * euler dt, step end - all with the device-resident dt above) and downloads state n+1 into the same host buffers.
+ * The copies are pipelined with the force evaluations in `num_stripes` particle ranges on two extra streams owned by
+ * the context; a stripe must consist of whole cell layers along COORD3 (the slowest hash digit) so that every
+ * neighbour of a particle of stripe s lies in stripes s-1..s+1, and COORD3 must not be periodic. Consecutive calls on
+ * the same buffers are chained stripe by stripe: the upload of stripe s only waits for the previous call's download
+ * of stripe s, so the host never has to synchronise between steps. Results are bitwise those of the resident path.
+ * Nothing is synchronised: the host buffers hold state n+1 after b200sph_host_sync (or a device synchronisation).
+ *   resident != 0   state n is already in pos / vel on the device (it was uploaded with b200sph_host_upload and
+ *                   re-sorted by a neighbour rebuild): no upload, only the striped downloads
+ * b200sph_host_upload: the upload half on its own, for the steps that start with a neighbour rebuild (the sort needs
+ * the whole state): chained on the previous call's downloads like above; the context's stream waits for it.
+ * b200sph_host_fence: the context's stream waits for the copies still in flight; call it before using the state
+ * buffers through any other entry point. */
+#define B200SPH_MAX_STRIPES 32
+typedef struct b200sph_host_step_args {
+	void *host_pos, *host_vel;          /* pinned host float4[num_particles]: state n in, state n+1 out */
+	void *pos, *vel;                    /* device float4[N]: receive state n, end up holding state n+1 */
+	void *pos_star, *vel_star;          /* device float4[N]: scratch for the predicted state n* */
+	const void *info;
+	const uint32_t *hash, *cell_start;
+	const uint16_t *neibs_list;
+	void *forces;                       /* device float4[N] scratch */
+	float *cfl;                         /* device float[cfl_elements]: room for both force evaluations, every stripe's
+	                                       blocks rounded up to 4: 2 x sum_s round4(ceil(stripe_s / 128)) */
+	void *xsph;                         /* NULL unless ENABLE_XSPH */
+	uint32_t cfl_elements;
+	uint32_t num_particles;
+	const uint32_t *stripe_bounds;      /* host array [num_stripes + 1]: 0 = b[0] < b[1] < ... < b[num_stripes] = num_particles */
+	uint32_t num_stripes;               /* 1 .. B200SPH_MAX_STRIPES */
+	int resident;
+} b200sph_host_step_args;
+int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args *args);
+int b200sph_host_upload(b200sph_ctx *ctx, const void *host_pos, const void *host_vel, void *pos, void *vel,
+	uint32_t num_particles);
+int b200sph_host_fence(b200sph_ctx *ctx);
+int b200sph_host_sync(b200sph_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

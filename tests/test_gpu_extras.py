@@ -305,3 +305,57 @@ def test_pipelined_host_stepping_equals_resident_stepping_bitwise(name):
         assert torch.equal(hv[:n].view(torch.int32), exp_v.view(torch.int32)), f"vel differs at step {it}"
     assert len(a._stripes()) > 1, "the test problem should be split into several stripes"
     assert a.dt == b.dt and a.t == pytest.approx(b.t, rel=1e-15)
+
+
+@pytest.mark.parametrize("stripes", [1, 3, 7])
+def test_chained_host_stepping_without_host_synchronisation(stripes):
+    """b200sph_step_host calls chain on each other through per-stripe events only: 23 steps (three neighbour rebuilds)
+    enqueued back to back with no host synchronisation in between must leave exactly the resident result in the host
+    buffers, and mixing in resident step() calls (which fence on the pending copies) must not break the chain."""
+    params, parts = tg.get("dambreak")
+    a = Worker(params, parts, 0)
+    b = Worker(params, parts, 0)
+    a.host_stripes, a.host_stripe_min = stripes, 500
+    A = a.pos[0].shape[0]
+    hp, hv = torch.zeros((A, 4)).pin_memory(), torch.zeros((A, 4)).pin_memory()
+    n = a.numParticles
+    hp[:n].copy_(a.pos[a.cur][:n]); hv[:n].copy_(a.vel[a.cur][:n])
+    for it in range(23):
+        a.step_host(hp, hv)
+    for it in range(23):
+        b.step()
+    a.host_sync()
+    n = b.numParticles
+    assert a.numParticles == n and 1 <= len(a._stripes()) <= stripes
+    exp_p, exp_v = b.pos[b.cur][:n].cpu(), b.vel[b.cur][:n].cpu()
+    assert torch.equal(hp[:n].view(torch.int32), exp_p.view(torch.int32))
+    assert torch.equal(hv[:n].view(torch.int32), exp_v.view(torch.int32))
+    # resident steps in between: the device copy is the state, the host copy is stale until the next download
+    a.step(); b.step()
+    n = a.numParticles
+    hp[:n].copy_(a.pos[a.cur][:n]); hv[:n].copy_(a.vel[a.cur][:n])
+    torch.cuda.synchronize()
+    for it in range(4):
+        a.step_host(hp, hv)
+        b.step()
+    got = a.download()
+    exp = b.download()
+    assert np.array_equal(got.pos.view(np.uint32), exp.pos.view(np.uint32))
+    assert np.array_equal(got.vel.view(np.uint32), exp.vel.view(np.uint32))
+    a.host_sync()
+    assert torch.equal(hp[:n].view(torch.int32), torch.from_numpy(exp.pos).view(torch.int32))
+
+
+def test_step_host_argument_checks():
+    params, parts = tg.get("lattice")
+    w = Worker(params, parts, 0)
+    w.step()
+    lib, ctx = w.framework.ctx.lib, w.framework.ctx
+    import ctypes as C
+    a = capi.HostStepArgs()
+    with pytest.raises(ValueError):
+        capi.check(lib.b200sph_step_host(ctx.handle, C.byref(a)))            # num_particles 0 is a no-op ...
+        a.num_particles = w.numParticles
+        capi.check(lib.b200sph_step_host(ctx.handle, C.byref(a)))            # ... null buffers are not
+    with pytest.raises(ValueError):
+        w.step_host(torch.zeros((w.allocated, 4)), torch.zeros((w.allocated, 4)))   # not pinned

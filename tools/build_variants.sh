@@ -5,7 +5,7 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd); C=$ROOT/gpusph_b200/csrc; O=$ROOT/build/variants; mkdir -p $O/obj
 FL="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I$ROOT/include"
-for f in api neibs tiles euler filters; do
+for f in api neibs tiles euler filters hoststep; do
   if [ ! -f $O/obj/$f.o ] || [ $C/$f.cu -nt $O/obj/$f.o ] || [ $C/common.cuh -nt $O/obj/$f.o ] || [ $ROOT/include/b200sph.h -nt $O/obj/$f.o ]; then nvcc $FL -c -o $O/obj/$f.o $C/$f.cu & fi
 done
 for v in "$@"; do
@@ -15,6 +15,6 @@ done
 wait
 for v in "$@"; do
   name=${v%%:*}
-  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $O/libb200sph_$name.so $O/obj/api.o $O/obj/neibs.o $O/obj/tiles.o $O/obj/euler.o $O/obj/filters.o $O/obj/forces_$name.o
+  nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $O/libb200sph_$name.so $O/obj/api.o $O/obj/neibs.o $O/obj/tiles.o $O/obj/euler.o $O/obj/filters.o $O/obj/hoststep.o $O/obj/forces_$name.o
   echo built $O/libb200sph_$name.so
 done

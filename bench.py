@@ -226,9 +226,11 @@ def main():
     import torch
     import torch.distributed as dist
 
-    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on stdout when NCCL_DEBUG is
+    # VERSION or WARN) get stderr as their fd 1, the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -380,8 +382,9 @@ def main():
         # a streaming kernel for comparison: euler reads pos, vel, forces, info (56 B) and writes pos, vel (32 B)
         t_euler = timed(w.euler_once)
         # one whole neighbour rebuild (calcHash, sort, reorder, list build; two small readbacks), every 10th step
+        # (single GPU only: with slabs the rebuild exchanges halos, a collective the other ranks are not part of here)
         reps = 3
-        t_rebuild = timed(w.build_neibs)
+        t_rebuild = timed(w.build_neibs) if world == 1 else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -425,7 +428,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

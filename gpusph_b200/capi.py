@@ -111,6 +111,14 @@ class ForcesArgs(C.Structure):
     ]
 
 
+class FusedEulerArgs(C.Structure):
+    """struct b200sph_fused_euler_args (include/b200sph.h): the integration half of b200sph_forces_euler."""
+    _fields_ = [
+        ("old_pos", C.c_void_p), ("old_vel", C.c_void_p), ("new_pos", C.c_void_p), ("new_vel", C.c_void_p),
+        ("dt", C.c_float), ("step", C.c_int), ("dt_from_device", C.c_int),
+    ]
+
+
 class HostStepArgs(C.Structure):
     """struct b200sph_host_step_args (include/b200sph.h): one time step of a state that lives in host memory."""
     _fields_ = [
@@ -178,6 +186,7 @@ PROTOTYPES = {
     "b200sph_step_end": (C.c_int, [_P]),
     "b200sph_step_query": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "b200sph_euler": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_float, C.c_int]),
+    "b200sph_forces_euler": (C.c_int, [_P, C.POINTER(ForcesArgs), C.POINTER(FusedEulerArgs), C.POINTER(_U)]),
     "b200sph_step_host": (C.c_int, [_P, C.POINTER(HostStepArgs)]),
     "b200sph_host_upload": (C.c_int, [_P, _P, _P, _P, _P, _U]),
     "b200sph_host_fence": (C.c_int, [_P]),

@@ -2,6 +2,7 @@
 // Behavioural specification: GPUSPH eulerDevice, src/cuda/euler_kernel.def:396-540
 // (corrected velocity :117-134, continuity :200-206). Streaming kernel: 60 B in, 32 B out per particle.
 #include "common.cuh"
+#include "euler_update.cuh"
 
 template<int STEP>
 __global__ void __launch_bounds__(BLOCK_STREAM)
@@ -12,54 +13,13 @@ euler_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ old
 {
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
 	if (index >= numParticles) return;
-	// dt either as an argument (reference-style call) or from the device-resident record: dt/2 on the predictor
-	// (PredictorCorrector::getDtOperatorForStep), dt on the corrector
-	const float dt = dev_state ? (STEP == 1 ? dev_state->dt / 2 : dev_state->dt) : dt_arg;
+	const float dt = euler_dt<STEP>(dev_state, dt_arg);
 	float4 pos = oldPos[index];
 	float4 vel = oldVel[index];
 	const float4 force = forces[index];
 	const ushort4 info = infoArray[index];
-	const int type = ptype_of(info);
-	const bool integrateBoundary = (P.boundarytype == B200SPH_DYN_BOUNDARY || P.boundarytype == B200SPH_SA_BOUNDARY);   // :424-425
-	if (!inactive_w(pos.w) && !(type == PT_BOUNDARY && !integrateBoundary && !(info.x & B200SPH_FG_MOVING_BOUNDARY))) {
-		// velc = vel (+ force*dt/2 on the corrector), :117-134
-		float vcx = vel.x, vcy = vel.y, vcz = vel.z;
-		if (STEP == 2) {
-			const float hdt = dt / 2;
-			vcx += force.x * hdt; vcy += force.y * hdt; vcz += force.z * hdt;
-		}
-		if (xsph) {                                               // XSPH correction, :165-180
-			const float4 mv = xsph[index];
-			vcx += P.epsxsph * mv.x; vcy += P.epsxsph * mv.y; vcz += P.epsxsph * mv.z;
-		}
-		if (type == PT_FLUID) {                                   // :441-462
-			pos.x += vcx * dt; pos.y += vcy * dt; pos.z += vcz * dt;
-			vel.w += dt * force.w;
-			vel.x += dt * force.x; vel.y += dt * force.y; vel.z += dt * force.z;
-		} else if (type == PT_BOUNDARY || type == PT_VERTEX) {     // :468-512
-			// particles of a moving / floating body follow the rigid motion of the body (:470-503)
-			if ((info.x & B200SPH_FG_MOVING_BOUNDARY) && bodies) {
-				const int obj = object_of_y(info.y);
-				const int3 gp = grid_pos(P, particleHash[index] & CELLTYPE_BITMASK);
-				// relPos = x - x_cg (globalDistance, cellgrid.cuh:152-160)
-				const float rx = (float)(gp.x - bodies->cgGridPos[obj][0]) * P.cellSize[0] + (pos.x - bodies->cgPos[obj][0]);
-				const float ry = (float)(gp.y - bodies->cgGridPos[obj][1]) * P.cellSize[1] + (pos.y - bodies->cgPos[obj][1]);
-				const float rz = (float)(gp.z - bodies->cgGridPos[obj][2]) * P.cellSize[2] + (pos.z - bodies->cgPos[obj][2]);
-				const float *rot = bodies->steprot[obj];
-				// applyrot, euler_kernel.cu:67-74
-				pos.x += (rot[0] - 1.0f) * rx + rot[1] * ry + rot[2] * rz;
-				pos.y += rot[3] * rx + (rot[4] - 1.0f) * ry + rot[5] * rz;
-				pos.z += rot[6] * rx + rot[7] * ry + (rot[8] - 1.0f) * rz;
-				pos.x += bodies->trans[obj][0]; pos.y += bodies->trans[obj][1]; pos.z += bodies->trans[obj][2];
-				// V(P) = V(Cg) + omega x PCg
-				const float *w = bodies->angularvel[obj], *lv = bodies->linearvel[obj];
-				vel.x = lv[0] + (w[1] * rz - w[2] * ry);
-				vel.y = lv[1] + (w[2] * rx - w[0] * rz);
-				vel.z = lv[2] + (w[0] * ry - w[1] * rx);
-			}
-			if (P.boundarytype == B200SPH_DYN_BOUNDARY) vel.w += dt * force.w;
-		}
-	}
+	euler_update<STEP>(P, pos, vel, force, info, particleHash, index, dt, bodies, xsph != NULL,
+		xsph ? xsph[index] : make_float4(0.f, 0.f, 0.f, 0.f));
 	newPos[index] = pos;
 	newVel[index] = vel;
 }

@@ -20,6 +20,7 @@
 // Summation order inside each list section is the reference's (list order); the fluid and boundary partial sums
 // are combined as (0 + sum_fluid) + sum_boundary like the reference's RMW sequence.
 #include "pair_physics.cuh"
+#include "euler_update.cuh"
 #include <stdlib.h>
 #include <cub/device/device_scan.cuh>
 
@@ -160,7 +161,7 @@ template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool 
 __device__ __forceinline__ float
 particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
 	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo, Lut lut,
-	const ListGeom &L, Fetch fetch, float4 *__restrict__ forces, float4 *__restrict__ xsph = NULL)
+	const ListGeom &L, Fetch fetch, float4 *__restrict__ forces, float4 *__restrict__ xsph = NULL, float4 *acc_out = NULL)
 {
 	Central c;
 	c.pos = pos; c.vel = vel;
@@ -184,6 +185,7 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 	}
 	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
 	forces[index] = acc;
+	if (acc_out) *acc_out = acc;
 	return cfl_term;
 }
 
@@ -252,7 +254,10 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 		const ushort4 info = infoArray[index];
 		const int type = ptype_of(info);
 		const float4 pos = posArray[index];
+		float4 acc;
+		bool have_acc = false;
 		if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000)) {
+			have_acc = true;
 			uint *my_base = s_cellbase + threadIdx.x;
 			const uint cellHash = particleHash[index] & CELLTYPE_BITMASK;
 			load_cell_starts(P, (int)cellHash, cellStart, my_base, BLOCK_FORCES);
@@ -272,7 +277,20 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 			const float4 vel = velArray[index];
 			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE>(P, k, index, info, type, pos,
 				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, forces,
-				GEN ? bo.xsph : NULL);
+				GEN ? bo.xsph : NULL, &acc);
+		}
+		// fused integration epilogue: exactly the stand-alone euler kernel's update of this particle (euler_update.cuh),
+		// with the forces still in registers. A particle the pair loop skips integrates with its FORCES entry as is.
+		if (bo.eul_step) {
+			if (!have_acc) acc = forces[index];
+			float4 p = bo.eul_old_pos[index], v = bo.eul_old_vel[index];
+			const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (bo.eul_step == 1)
+				euler_update<1>(P, p, v, acc, info, particleHash, index, euler_dt<1>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
+			else
+				euler_update<2>(P, p, v, acc, info, particleHash, index, euler_dt<2>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
+			bo.eul_new_pos[index] = p;
+			bo.eul_new_vel[index] = v;
 		}
 	}
 
@@ -716,7 +734,23 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 	return b200sph_forces_ex(ctx, &a, num_cfl_blocks);
 }
 
+static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *eul, uint32_t *num_cfl_blocks);
+
 extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks)
+{
+	return forces_impl(ctx, args, NULL, num_cfl_blocks);
+}
+
+// forces of [from, to) followed by the integration of the same particles (b200sph_forces_ex + b200sph_euler_ex); the
+// default gather kernel does both in one launch (fused epilogue), every other kernel selection runs the two launches
+extern "C" int b200sph_forces_euler(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *eul,
+	uint32_t *num_cfl_blocks)
+{
+	if (!eul) { b200_set_error("forces_euler: null integration arguments"); return B200SPH_EINVAL; }
+	return forces_impl(ctx, args, eul, num_cfl_blocks);
+}
+
+static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *eul, uint32_t *num_cfl_blocks)
 {
 	CHECK_CTX(ctx);
 	if (!args) { b200_set_error("forces: null argument block"); return B200SPH_EINVAL; }
@@ -728,6 +762,16 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 	const uint32_t num_particles = args->num_particles, from = args->from_particle, to = args->to_particle, cfl_offset = args->cfl_offset;
 	BodyOut bo;
 	bo.bodies = NULL; bo.rb_forces = (float4 *)rb_forces; bo.rb_torques = (float4 *)rb_torques; bo.xsph = NULL;
+	bo.eul_step = 0; bo.eul_dt = 0.0f; bo.eul_state = NULL; bo.eul_old_pos = bo.eul_old_vel = NULL;
+	bo.eul_new_pos = bo.eul_new_vel = NULL; bo.eul_bodies = NULL;
+	if (eul) {
+		if (eul->step != 1 && eul->step != 2) { b200_set_error("unsupported predcorr timestep %d", eul->step); return B200SPH_EINVAL; }
+		if (args && args->to_particle > args->from_particle) {
+			if (!eul->old_pos || !eul->old_vel || !eul->new_pos || !eul->new_vel) { b200_set_error("forces_euler: null buffer"); return B200SPH_EINVAL; }
+			if (eul->new_pos == args->pos || eul->new_vel == args->vel) {
+				b200_set_error("forces_euler: the integrated state must not overwrite the state the pair loop reads"); return B200SPH_EINVAL; }
+		}
+	}
 	if (rb_forces) {
 		if (!rb_torques) { b200_set_error("forces: rb_forces without rb_torques"); return B200SPH_EINVAL; }
 		if (!ctx->have_bodies) { b200_set_error("forces: body output requested before setrbcg/setrbstart"); return B200SPH_EINVAL; }
@@ -756,6 +800,29 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 	DevParams dp_launch = ctx->dp;
 	dp_launch.cmd_dt = args->dt; dp_launch.cmd_step = args->step;
 	dp_launch.dev_state = args->dt_from_device ? ctx->d_step : NULL;
+	// integration: fused into the gather kernel's epilogue, or a second launch behind the other kernels / with XSPH
+	// (whose mean velocity the integration reads from the buffer)
+	if (ctx->tiles_state == 1) {
+		CUDA_TRY(cudaEventSynchronize(ctx->tiles_event));
+		ctx->num_tiles = ctx->h_tile_info[0];
+		ctx->tiles_state = ctx->h_tile_info[1] ? 0 : 2;      // overflow: a tile does not fit in shared memory
+	}
+	const bool use_tiles = !general && ctx->tiles_state == 2 && ctx->tiles_cellstart == cell_start && to <= ctx->tiles_range_end && ctx->num_tiles > 0;
+	const bool use_coop = !general && !use_tiles && ctx->use_coop && num_particles <= COOP_INDEX_MASK;
+	const bool fuse = eul && !xsph && !use_tiles && !use_coop;
+	if (fuse) {
+		bo.eul_step = eul->step; bo.eul_dt = eul->dt; bo.eul_state = eul->dt_from_device ? ctx->d_step : NULL;
+		bo.eul_old_pos = (const float4 *)eul->old_pos; bo.eul_old_vel = (const float4 *)eul->old_vel;
+		bo.eul_new_pos = (float4 *)eul->new_pos; bo.eul_new_vel = (float4 *)eul->new_vel;
+		bo.eul_bodies = ctx->have_bodies ? ctx->d_bodies : NULL;
+	}
+	auto integrate_unfused = [&]() -> int {
+		if (!eul || fuse) return B200SPH_OK;
+		const size_t o = (size_t)from * 16;
+		return b200sph_euler_ex(ctx, (const char *)eul->old_pos + o, (const char *)eul->old_vel + o, (const char *)info + (size_t)from * 8,
+			hash + from, (const char *)forces + o, args->xsph ? (const char *)args->xsph + o : NULL, (char *)eul->new_pos + o,
+			(char *)eul->new_vel + o, to - from, to - from, eul->dt, eul->step, eul->dt_from_device);
+	};
 	if (general) {
 		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
 		gather_kernel_t gk = wide ? forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, true>
@@ -765,7 +832,7 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
 		KERNEL_TRY();
 		if (num_cfl_blocks) *num_cfl_blocks = nblocks;
-		return B200SPH_OK;
+		return integrate_unfused();
 	}
 	switch (d.densitydiffusiontype) {
 	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
@@ -773,12 +840,6 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 	default: pick_kernels<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
 	}
 	// tiles built by the last buildNeibsList for these cell ranges?
-	if (ctx->tiles_state == 1) {
-		CUDA_TRY(cudaEventSynchronize(ctx->tiles_event));
-		ctx->num_tiles = ctx->h_tile_info[0];
-		ctx->tiles_state = ctx->h_tile_info[1] ? 0 : 2;      // overflow: a tile does not fit in shared memory
-	}
-	const bool use_tiles = ctx->tiles_state == 2 && ctx->tiles_cellstart == cell_start && to <= ctx->tiles_range_end && ctx->num_tiles > 0;
 	if (use_tiles) {
 		int rc = aux_precompute(ctx, (const float4 *)vel, (const ushort4 *)info, num_particles);
 		if (rc) return rc;
@@ -787,7 +848,7 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 		tk<<<ctx->num_tiles, ctx->tile_p, smem, ctx->stream>>>(ctx->dp, ctx->tiles, (const float4 *)pos, (const float4 *)vel, ctx->aux,
 			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
-	} else if (ctx->use_coop && num_particles <= COOP_INDEX_MASK) {
+	} else if (use_coop) {
 		// private copy of the list: made by buildNeibsList for the list it wrote; a list from elsewhere is converted here
 		if (ctx->coop_src != (const void *)neibs_list || ctx->coop_n < to) {
 			int rc = b200_coop_list(ctx, info, pos, hash, cell_start, neibs_list, num_particles);
@@ -809,7 +870,7 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 	}
 	KERNEL_TRY();
 	if (num_cfl_blocks) *num_cfl_blocks = nblocks;
-	return B200SPH_OK;
+	return integrate_unfused();
 }
 
 // ---------------------------------------------------------------------------

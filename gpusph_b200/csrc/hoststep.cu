@@ -174,13 +174,13 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		if (xsph) CUDA_TRY(cudaMemsetAsync((char *)a->xsph + o16, 0, (size_t)(e - s) * 16, P));
 		f.pos = a->pos; f.vel = a->vel; f.step = 1;
 		f.from_particle = s; f.to_particle = e; f.cfl_offset = offP;
-		int r = b200sph_forces_ex(ctx, &f, &nb);
+		// forces + euler step 1 (dt/2) of the stripe in one launch (fused epilogue)
+		b200sph_fused_euler_args eu;
+		eu.old_pos = a->pos; eu.old_vel = a->vel; eu.new_pos = a->pos_star; eu.new_vel = a->vel_star;
+		eu.dt = 0.0f; eu.step = 1; eu.dt_from_device = 1;
+		int r = b200sph_forces_euler(ctx, &f, &eu, &nb);
 		if (r) return r;
 		offP += nb;
-		r = b200sph_euler_ex(ctx, (char *)a->pos + o16, (char *)a->vel + o16, (const char *)a->info + (size_t)s * 8, a->hash + s,
-			(char *)a->forces + o16, a->xsph ? (char *)a->xsph + o16 : NULL, (char *)a->pos_star + o16, (char *)a->vel_star + o16,
-			e - s, e - s, 0.0f, 1, 1);
-		if (r) return r;
 		if (Q != P) CUDA_TRY(cudaEventRecord(ctx->pred_ev[k], P));
 		TRACE(TR_PRED + k, P);
 		return B200SPH_OK;
@@ -196,13 +196,13 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		if (xsph) CUDA_TRY(cudaMemsetAsync((char *)a->xsph + o16, 0, (size_t)(e - s) * 16, Q));
 		f.pos = a->pos_star; f.vel = a->vel_star; f.step = 2;
 		f.from_particle = s; f.to_particle = e; f.cfl_offset = cflQ + offQ;
-		int r = b200sph_forces_ex(ctx, &f, &nb);
+		// forces + euler step 2 of the stripe, in place into the state-n buffers, in one launch
+		b200sph_fused_euler_args eu;
+		eu.old_pos = a->pos; eu.old_vel = a->vel; eu.new_pos = a->pos; eu.new_vel = a->vel;
+		eu.dt = 0.0f; eu.step = 2; eu.dt_from_device = 1;
+		int r = b200sph_forces_euler(ctx, &f, &eu, &nb);
 		if (r) return r;
 		offQ += nb;
-		r = b200sph_euler_ex(ctx, (char *)a->pos + o16, (char *)a->vel + o16, (const char *)a->info + (size_t)s * 8, a->hash + s,
-			(char *)a->forces + o16, a->xsph ? (char *)a->xsph + o16 : NULL, (char *)a->pos + o16, (char *)a->vel + o16,
-			e - s, e - s, 0.0f, 2, 1);
-		if (r) return r;
 		CUDA_TRY(cudaEventRecord(ctx->comp_ev[j], Q));
 		TRACE(TR_CORR + j, Q);
 		CUDA_TRY(cudaStreamWaitEvent(D, ctx->comp_ev[j], 0));

@@ -292,6 +292,14 @@ struct BodyOut {
 	const BodyData *bodies;     // NULL: no body output requested
 	float4 *rb_forces, *rb_torques;
 	float4 *xsph;               // XSPH mean-velocity output (general variant, ENABLE_XSPH), else NULL
+	// fused integration epilogue (gather kernel only; b200sph_forces_euler): eul_step 1 / 2 integrates the particle
+	// right after its forces are known — state n from eul_old_*, result to eul_new_* (0: forces only)
+	int eul_step;
+	float eul_dt;                          // dt of the sub-step unless eul_state is given
+	const StepState *eul_state;            // device-resident dt record
+	const float4 *eul_old_pos, *eul_old_vel;
+	float4 *eul_new_pos, *eul_new_vel;
+	const BodyData *eul_bodies;            // rigid motion of moving bodies (NULL: none)
 };
 
 __device__ __forceinline__ float finalize_particle(const DevParams &P, const int type, const int fnum, const float sspeed,

@@ -196,9 +196,11 @@ class ForcesEngine:
 
     def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, fromParticle: int,
                   toParticle: int, cflOffset: int = 0, compute_object_forces: bool = False,
-                  step: int = 0, dt: float = 0.0, dt_from_device: bool = False) -> int:
+                  step: int = 0, dt: float = 0.0, dt_from_device: bool = False, euler=None) -> int:
         """step / dt = the command's integrator step and dt (src/GPUWorker.cc:1931-1932), read by BREZZI diffusion only;
-        dt_from_device: take dt from the context's device-resident record instead."""
+        dt_from_device: take dt from the context's device-resident record instead.
+        euler = (old: BufferList, new: BufferList, step, dt | None): also integrate the same particles
+        (AbstractIntegrationEngine::basicstep) right behind their forces; dt None = from the device record."""
         nblocks = C.c_uint32()
         a = capi.ForcesArgs()
         a.pos, a.vel, a.info = bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO)
@@ -209,7 +211,16 @@ class ForcesEngine:
         a.xsph = bufwrite.ptr(BUFFER_XSPH, False)
         a.num_particles, a.from_particle, a.to_particle, a.cfl_offset = numParticles, fromParticle, toParticle, cflOffset
         a.dt, a.step, a.dt_from_device = dt, step, 1 if dt_from_device else 0
-        capi.check(self.lib.b200sph_forces_ex(self.ctx.handle, C.byref(a), C.byref(nblocks)))
+        if euler is None:
+            capi.check(self.lib.b200sph_forces_ex(self.ctx.handle, C.byref(a), C.byref(nblocks)))
+        else:
+            # forces + integration of the same particles in one call (b200sph_forces_euler: fused epilogue)
+            old, new, estep, edt = euler
+            e = capi.FusedEulerArgs()
+            e.old_pos, e.old_vel = old.ptr(BUFFER_POS), old.ptr(BUFFER_VEL)
+            e.new_pos, e.new_vel = new.ptr(BUFFER_POS), new.ptr(BUFFER_VEL)
+            e.step, e.dt, e.dt_from_device = estep, (0.0 if edt is None else edt), (1 if edt is None else 0)
+            capi.check(self.lib.b200sph_forces_euler(self.ctx.handle, C.byref(a), C.byref(e), C.byref(nblocks)))
         return nblocks.value
 
     # ---- moving / force-feedback bodies (src/engine_forces.h:62-74) ----

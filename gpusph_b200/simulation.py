@@ -101,6 +101,9 @@ class Worker:
         self.postproc = self.framework.newPostProcessEngine(TESTPOINTS)
         if planes:
             self.forces.setplanes(planes)
+        # integration fused into the forces kernel's epilogue (device-dt stepping without XSPH; B200SPH_FUSED_EULER=0: off)
+        self.fused = self.device_dt and self.xsph is None and n == self.particleRangeEnd and \
+            os.environ.get("B200SPH_FUSED_EULER", "1") != "0"
         self.graphs = bool(graphs) and self.device_dt
         self._graphs = {}                 # (state buffers, numParticles, range end) -> [eager runs so far, CUDAGraph | None]
         self.last_neibs_info = None
@@ -231,8 +234,11 @@ class Worker:
                 self._step_graph(cur, n, end)
             else:
                 self._enqueue_step(rd, wr, n, end)
-            self.launches += 2 * 3 + 1
+            fused = self.fused and n == end
+            self.launches += (2 * 2 if fused else 2 * 3) + 1
             self._stale = True
+            if fused:
+                oth = cur                 # state n+1 is in the buffers state n was in
         else:
             dt = self._dt
             # predictor: forces(n) -> euler step 1 with dt/2 writes n*
@@ -252,15 +258,25 @@ class Worker:
 
     def _enqueue_step(self, rd: BufferList, wr: BufferList, n: int, end: int) -> None:
         """Everything enqueued, nothing read back: forces(n) -> dt candidate 1 -> euler step 1 (dt/2) -> forces(n*) ->
-        dt candidate 2 -> euler step 2 (dt) -> t += dt, dt = min(candidates)."""
+        dt candidate 2 -> euler step 2 (dt) -> t += dt, dt = min(candidates).
+
+        Fused variant (self.fused): each integration runs in the epilogue of its forces kernel (b200sph_forces_euler),
+        the corrector IN PLACE into the state-n buffers (the pair loop still gathers n* from the other ones), so
+        state n+1 ends up where state n was and the two states do not swap."""
+        fused = self.fused and n == end
         for which, st in ((1, rd), (2, wr)):
             if self.clobber:
                 self.forces_buf.zero_()
             if self.xsph is not None:
                 self.xsph.zero_()
-            nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True)
-            self.forces.dtreduce_async(st, nblocks, which)
-            self.integration.basicstep_async(rd, wr, n, end, which)
+            if fused:
+                nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True,
+                                                euler=(rd, wr if which == 1 else rd, which, None))
+                self.forces.dtreduce_async(st, nblocks, which)
+            else:
+                nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True)
+                self.forces.dtreduce_async(st, nblocks, which)
+                self.integration.basicstep_async(rd, wr, n, end, which)
         self.forces.step_end()
 
     def _step_graph(self, cur: int, n: int, end: int) -> None:

@@ -307,6 +307,23 @@ typedef struct b200sph_forces_args {
 } b200sph_forces_args;
 int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks);
 
+/* b200sph_forces_ex immediately followed by b200sph_euler_ex for the same particles [from_particle, to_particle)
+ * (no reference counterpart: the reference runs forcesDevice, finalizeforcesDevice and eulerDevice as separate
+ * launches with FORCES round-tripping through memory, src/cuda/forces.cu:718-799, src/cuda/euler.cu:330-372).
+ * With the default pair kernel the integration runs in the kernel's epilogue while the particle's forces are still in
+ * registers; results are bitwise those of the two separate calls (same update code). old_* = state n (may be the
+ * buffers args->pos / args->vel: predictor), new_* receives the integrated state and may alias old_* (in place) but
+ * must not alias args->pos / args->vel, which other particles still gather from. forces is written as usual. */
+typedef struct b200sph_fused_euler_args {
+	const void *old_pos, *old_vel;
+	void *new_pos, *new_vel;
+	float dt;                 /* dt of the sub-step (dt/2 for step 1), unless dt_from_device */
+	int step;                 /* 1 predictor, 2 corrector */
+	int dt_from_device;       /* dt from the device-resident record (dt/2 for step 1) */
+} b200sph_fused_euler_args;
+int b200sph_forces_euler(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *euler,
+	uint32_t *num_cfl_blocks);
+
 /* AbstractForcesEngine::reduceRbForces (src/engine_forces.h:68-74; src/cuda/forces.cu:967-1003): in-place segmented
  * inclusive scan of rb_forces / rb_torques keyed by rb_keys, then the last element of each body's segment
  * (lastindex[b], host array) is copied to total_force / total_torque (host float[3*numbodies]). Synchronises. */

@@ -346,6 +346,61 @@ def test_chained_host_stepping_without_host_synchronisation(stripes):
     assert torch.equal(hp[:n].view(torch.int32), torch.from_numpy(exp.pos).view(torch.int32))
 
 
+@pytest.mark.parametrize("name", ["dambreak", "dambreak_ferrari", "poiseuille", "twofluid_laminar", "ragged"])
+def test_fused_forces_euler_equals_separate_launches_bitwise(name):
+    """b200sph_forces_euler (integration in the epilogue of the pair kernel) against b200sph_forces_ex followed by
+    b200sph_euler_ex: both sub-steps, a particle sub-range, the corrector in place."""
+    from gpusph_b200.engines import BufferList
+    params, parts = tg.get(name)
+    w = Worker(params, parts, 0, device_dt=False)
+    for _ in range(3):
+        w.step()
+    n = w.numParticles
+    st = w.state(w.cur)
+    lo, hi = n // 5, n - n // 7                          # not aligned to anything
+    for step, dt in ((1, 0.5 * w.dt), (2, w.dt)):
+        # separate launches
+        w.forces_buf.zero_()
+        nb_ref = w.forces.basicstep(st, st, n, lo, hi, 0)
+        f_ref = w.forces_buf.clone()
+        cfl_ref = w.cfl[:nb_ref].clone()
+        old = BufferList({BUFFER_POS: w.pos[w.cur].clone(), BUFFER_VEL: w.vel[w.cur].clone()})
+        exp_p, exp_v = torch.zeros_like(w.pos[0]), torch.zeros_like(w.vel[0])
+        sl = lambda t: t[lo:hi]
+        rd = BufferList({k: sl(v) for k, v in st.items() if k in ("BUFFER_INFO", "BUFFER_HASH", "BUFFER_FORCES")})
+        rd[BUFFER_POS], rd[BUFFER_VEL] = sl(old[BUFFER_POS]), sl(old[BUFFER_VEL])
+        w.integration.basicstep(rd, BufferList({BUFFER_POS: sl(exp_p), BUFFER_VEL: sl(exp_v)}), hi - lo, hi - lo, dt, step)
+        # one launch; the corrector writes in place over `old`
+        w.forces_buf.zero_()
+        w.cfl.zero_()
+        new = old if step == 2 else BufferList({BUFFER_POS: torch.zeros_like(w.pos[0]), BUFFER_VEL: torch.zeros_like(w.vel[0])})
+        nb = w.forces.basicstep(st, st, n, lo, hi, 0, euler=(old, new, step, dt))
+        torch.cuda.synchronize()
+        assert nb == nb_ref
+        assert torch.equal(w.forces_buf.view(torch.int32), f_ref.view(torch.int32))
+        assert torch.equal(w.cfl[:nb].view(torch.int32), cfl_ref.view(torch.int32))
+        assert torch.equal(new[BUFFER_POS][lo:hi].view(torch.int32), exp_p[lo:hi].view(torch.int32)), f"pos, step {step}"
+        assert torch.equal(new[BUFFER_VEL][lo:hi].view(torch.int32), exp_v[lo:hi].view(torch.int32)), f"vel, step {step}"
+    with pytest.raises(ValueError):                      # the integrated state must not overwrite the gathered one
+        w.forces.basicstep(st, st, n, lo, hi, 0, euler=(st, st, 1, 0.1))
+
+
+def test_fused_stepping_equals_unfused_stepping_bitwise():
+    params, parts = tg.get("dambreak")
+    a = Worker(params, parts, 0)
+    b = Worker(params, parts, 0)
+    assert a.fused
+    b.fused = False
+    for _ in range(23):
+        a.step()
+        b.step()
+    assert a.dt == b.dt and a.t == pytest.approx(b.t, rel=1e-15)
+    ga, gb = a.download(), b.download()
+    assert np.array_equal(ga.hash, gb.hash) and np.array_equal(ga.info, gb.info)
+    assert np.array_equal(ga.pos.view(np.uint32), gb.pos.view(np.uint32))
+    assert np.array_equal(ga.vel.view(np.uint32), gb.vel.view(np.uint32))
+
+
 def test_step_host_argument_checks():
     params, parts = tg.get("lattice")
     w = Worker(params, parts, 0)

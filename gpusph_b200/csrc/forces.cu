@@ -203,13 +203,16 @@ __device__ __forceinline__ float4 lds_f4(uint a)
 #define B200_HOIST 1
 #endif
 #ifndef B200_MIN_BLOCKS
-#define B200_MIN_BLOCKS 7
+#define B200_MIN_BLOCKS 8
 #endif
 // (the detour through shared memory is what stops ptxas from re-deriving the value from the constant bank)
 struct Pinned { float v[20]; };
 
+// 8 CTAs (32 warps) per SM for the lean variants: 64 registers (8 bytes of spill) measured 2.7 % faster than 7 CTAs at
+// 72 registers, 9 CTAs at 56 registers 15 % slower (dambreak2m; the kernel is latency-bound: 1.3 eligible warps per
+// cycle, profiles/r01_forces_gather_final_ncu.txt). The variants with more live state keep 7.
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, bool WIDE>
-__global__ void __launch_bounds__(BLOCK_FORCES, B200_MIN_BLOCKS)
+__global__ void __launch_bounds__(BLOCK_FORCES, (LAMINAR || MULTIFLUID || WIDE || RHODIFF == RHODIFF_RUNTIME) ? 7 : B200_MIN_BLOCKS)
 forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,

@@ -413,7 +413,7 @@ def main():
                                             "achieved": 88 * n / (t_euler / 1e3) / 1e9, "frac": 88 * n / (t_euler / 1e3) / 1e9 / peak},
                     "neighbour_rebuild_ms": t_rebuild,
                     "pair_rate_G_per_s": w.last_neibs_info.num_interactions / (t_kernel / 1e3) / 1e9,
-                    "note": "the pair kernel is instruction-issue / L1-gather bound (ncu: issue 76 %, L1TEX 87 %, DRAM 8 %; profiles/r01_forces_gather_dambreak2m_ncu.txt), not HBM bound (SURVEY.md 8d); the HBM fraction is reported because the contract asks for it"}
+                    "note": "the pair kernel is L1-gather / instruction-issue bound (ncu: L1TEX 81 %, issue 67 %, DRAM 8 %; profiles/r01_forces_gather_final_ncu.txt), not HBM bound (SURVEY.md 8d); the HBM fraction is reported because the contract asks for it"}
         tr = os.path.join(ROOT, "profiles", "forces_traffic.json")
         if os.path.exists(tr):
             try:

@@ -327,6 +327,39 @@ __device__ __forceinline__ bool too_many_neibs(const DevParams &P, uint nf, uint
 	}
 }
 
+
+// L2 policy of the list builder. Every list entry is written once and not read again by this kernel, while the
+// candidate positions of a cell are re-read by the particles of its 26 neighbours — two of them one whole plane of
+// cells later. At 8 M particles a plane's list section (180 MB) streams through the 126 MB L2 between those uses
+// and evicts the positions; B200_NL_STORE_CS stores the entries with the streaming (evict-first) policy and
+// B200_NL_LOAD_EL loads the candidates evict-last.
+#ifndef B200_NL_STORE_CS
+#define B200_NL_STORE_CS 0
+#endif
+#ifndef B200_NL_LOAD_EL
+#define B200_NL_LOAD_EL 0
+#endif
+__device__ __forceinline__ void st_list(ushort *p, const ushort v)
+{
+#if B200_NL_STORE_CS
+	asm volatile("st.global.cs.u16 [%0], %1;" :: "l"(p), "h"(v) : "memory");
+#else
+	*p = v;
+#endif
+}
+__device__ __forceinline__ float4 ld_cand(const float4 *p)
+{
+#if B200_NL_LOAD_EL
+	float4 v;
+	unsigned long long pol;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));       // loop-invariant: hoisted by ptxas
+	asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+	return v;
+#else
+	return __ldg(p);
+#endif
+}
+
 __global__ void __launch_bounds__(BLOCK_STREAM)
 build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
@@ -389,7 +422,7 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					if (nt == PT_FLUID) ++nf; else if (nt == PT_BOUNDARY) ++nb; else ++nv;
 					if (!too_many_neibs(P, nf, nb, nv, nt)) {                             // :626-634
 						const uint enc = encode_cell ? ((cell + 1) << CELLNUM_SHIFT) : 0u;
-						neibsList[offset * stride + index] = (ushort)((j - bucketStart) + enc);
+						st_list(neibsList + offset * stride + index, (ushort)((j - bucketStart) + enc));
 						encode_cell = false;
 					}
 				};
@@ -403,7 +436,7 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					const uint self = index - bucketStart;                              // >= count when in another cell
 #pragma unroll 2
 					for (uint k = 0; k < count; ++k) {
-						const float4 np = __ldg(cand + k);
+						const float4 np = ld_cand(cand + k);
 						const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);
 						// sqlength(relPos) = x*x + y*y + z*z as nvcc contracts it
 						const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
@@ -421,7 +454,7 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					if (!encode_cell && neib_type != nt) encode_cell = true;             // :588
 					neib_type = nt;
 					if (skip_bb && nt == PT_BOUNDARY) continue;                           // :591-602
-					const float4 np = __ldg(posArray + j);
+					const float4 np = ld_cand(posArray + j);
 					if (inactive_w(np.w)) continue;                                       // :612
 					const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);
 					// sqlength(relPos) = x*x + y*y + z*z as nvcc contracts it

@@ -20,5 +20,6 @@ for a, b in (("BENCH", "BENCH_ref"), ("BENCH_8m", "BENCH_ref_8m")):
         print(a, "failed", e)
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 11 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"forces_gather_kernel" -s 4 -c 1 -f -o gpurun_out/prof_forces python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full1.log 2>&1; tail -1 gpurun_out/ncu_full1.log | cut -c1-200
+B200SPH_FUSED_EULER=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"forces_gather_kernel" -s 4 -c 1 -f -o gpurun_out/prof_forces python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full1.log 2>&1; tail -1 gpurun_out/ncu_full1.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"build_neibs_kernel" -c 1 -f -o gpurun_out/prof_buildneibs python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1; tail -1 gpurun_out/ncu_full2.log | cut -c1-200
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_8m.csv python bench.py --workload dambreak8m --steps 11 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench8m.log 2>&1; tail -1 gpurun_out/ncu_bench8m.log | cut -c1-120

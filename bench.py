@@ -124,6 +124,11 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload}}
+    if args.gpus > 1:
+        # the reference's DamBreak3D has no option to widen the tank: its multi-GPU run splits the N = 1 problem
+        line["scaling"] = "strong"
+        line["config"]["note"] = ("reference at N > 1: the same (N = 1) DamBreak3D split over N devices by its own slab decomposition - "
+                                  "its problem file cannot widen the tank like our weak-scaling arm does")
     if kind != "dambreak" or not os.path.exists(binp):
         cb = cpu_baseline_port(20.0)
         line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,

@@ -33,7 +33,9 @@ def test_abi_version_and_struct_size():
     lib = capi.load()
     assert lib.b200sph_abi_version() == capi.ABI_VERSION
     # layout check: the C compiler and ctypes must agree on sizeof(b200sph_params)
-    src = '#include "b200sph.h"\n#include <stdio.h>\nint main(){printf("%zu %zu", sizeof(b200sph_params), sizeof(b200sph_neibs_info));return 0;}'
+    src = ('#include "b200sph.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(b200sph_params), '
+           'sizeof(b200sph_neibs_info), sizeof(b200sph_forces_args), sizeof(b200sph_fused_euler_args), '
+           'sizeof(b200sph_host_step_args), sizeof(b200sph_reorder_extra));return 0;}')
     import subprocess, tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
@@ -41,6 +43,11 @@ def test_abi_version_and_struct_size():
         out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()
     assert int(out[0]) == C.sizeof(capi.Params)
     assert int(out[1]) == C.sizeof(capi.NeibsInfo)
+    assert int(out[2]) == C.sizeof(capi.ForcesArgs)
+    assert int(out[3]) == C.sizeof(capi.FusedEulerArgs)
+    assert int(out[4]) == C.sizeof(capi.HostStepArgs)
+    assert int(out[5]) == C.sizeof(capi.ReorderExtra)
+    assert capi.MAX_STRIPES == int(re.search(r"#define B200SPH_MAX_STRIPES (\d+)", open(os.path.join(ROOT, "include", "b200sph.h")).read()).group(1))
 
 
 def test_validate_accepts_supported_and_rejects_unsupported():

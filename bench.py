@@ -34,6 +34,7 @@ WORKLOADS = {
     "lattice8m": ("lattice", dict(n=200)),           # configs[2]
     "lattice2m": ("lattice", dict(n=126)),
     "lattice85k": ("lattice", dict(n=44)),
+    "poiseuille1m": ("poiseuille", dict(ppH=100, ncell=38)),   # configs[4] geometry (lx = ly = lz cube) with DYN boundaries
 }
 FORCES_BYTES_PER_PARTICLE = 60      # R pos16+vel16+info8+hash4, W forces16
 L2_BYTES = 126 * 1024 * 1024
@@ -50,6 +51,11 @@ def make_problem(name, world=1):
     if kind == "dambreak":
         extra = dict(width_scale=world, coord=(0, 2, 1)) if world > 1 else {}
         return dambreak_problem(kw["dp"], densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1, **extra)
+    if kind == "poiseuille":
+        if world > 1:
+            raise SystemExit("poiseuille1m is a single-GPU workload (periodic along every slab axis)")
+        from gpusph_b200.problems import poiseuille_problem
+        return poiseuille_problem(kw["ppH"], ncell=kw["ncell"])
     if world > 1:
         return lattice_problem(kw["n"], ny=kw["n"] * world, coord=(0, 2, 1), densitydiffusion=capi.RHODIFF_NONE)
     return lattice_problem(kw["n"], densitydiffusion=capi.RHODIFF_NONE)
@@ -438,6 +444,7 @@ def main():
             "config": {"workload": args.workload, "particles": n_global,
                        "neibs_per_particle": w.last_neibs_info.num_interactions / max(w.numOwn if world > 1 else w.numParticles, 1),
                        "buildneibsfreq": 10, "density_diffusion": "ferrari" if "dambreak" in args.workload else "none",
+                       "viscosity": "laminar (Morris)" if "poiseuille" in args.workload else "artificial",
                        "l2": f"inputs larger than L2 (working set {working_set / 1e6:.0f} MB vs 126 MB)" if working_set > L2_BYTES
                              else "working set fits L2 (small reference config)",
                        "parallelism": f"slab{world} (1-D slabs along y, tank widened x{world}, NCCL halo exchange)" if world > 1 else "single"},

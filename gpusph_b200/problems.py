@@ -275,20 +275,19 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
 
 def poiseuille_problem(ppH: int = 32, *, lz: float = 1.0, kinvisc: float = 0.1, driving_force: float = 0.05,
                        rho0: float = 1.0, viscavgop: int = capi.AVG_ARITHMETIC, steady_init: bool = True,
-                       layers: int = 3, alloc_extra: float = 0.0, **kw):
+                       layers: int = 3, alloc_extra: float = 0.0, ncell: int = 4, **kw):
     """Plane Poiseuille flow like src/problems/Poiseuille.inc:60-232: fluid between two DYN-boundary plates at
     z = +-lz/2, periodic in x and y, Newtonian laminar (Morris) viscosity with constant kinematic viscosity,
     driven by a body force along x. Analytic steady profile (Poiseuille.inc:187-232, scripts/validate-poiseuille.py:32-37):
         v_x(z) = F/(2 nu) ((lz/2)^2 - z^2).
-    Sizes follow the reference: lx = ly = 12 h? — here a thin periodic box of 6 x 6 cells is enough because the flow
-    is invariant in x and y."""
+    The flow is invariant in x and y: a thin periodic box of ncell x ncell cells (default 4) is enough for validation;
+    the reference's lx = ly = lz cube (Poiseuille.inc:120-130; ~1 M particles at --ppH 100) is ncell ~ lz / (2.6 dp)."""
     dp = lz / ppH
     max_vel = driving_force / (2 * kinvisc) * (lz / 2) ** 2
     hydro = math.sqrt(2 * driving_force * lz)
     c0 = 20 * max(hydro, max_vel)                                  # Poiseuille.inc:147
     h = 1.3 * dp
     cell = 2 * h
-    ncell = 4
     lx = ly = round(ncell * cell / dp) * dp                         # multiple of dp (periodicity, ProblemCore.cc:1436-1456)
     zpad = (layers - 0.5) * dp
     origin = np.array([-lx / 2, -ly / 2, -lz / 2 - zpad])

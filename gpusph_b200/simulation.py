@@ -91,6 +91,7 @@ class Worker:
         # blocking 4-byte readbacks per step); `dt` and `t` are fetched on demand
         self.device_dt = device_dt and fixed_dt is None
         self._t = 0.0
+        self._t_offset = 0.0
         self._dt = float(fixed_dt) if fixed_dt is not None else (float(dt) if dt is not None else initial_dt(self.params))
         self._stale = False
         if self.device_dt:
@@ -112,7 +113,8 @@ class Worker:
 
     def _sync_time(self) -> None:
         if self._stale:
-            self._t, self._dt, _ = self.forces.step_query()
+            t_dev, self._dt, _ = self.forces.step_query()
+            self._t = self._t_offset + t_dev       # the device record counts from 0; a resumed run starts later
             self._stale = False
 
     @property
@@ -134,6 +136,9 @@ class Worker:
 
     @t.setter
     def t(self, v: float) -> None:
+        if self.device_dt:
+            t_dev = self.forces.step_query()[0]
+            self._t_offset = float(v) - t_dev
         self._t = float(v)
 
     # ---- buffer lists ----
@@ -411,6 +416,27 @@ class Worker:
         """One predictor sub-step into the scratch state (bench.py: streaming-kernel reference point)."""
         rd, wr = self.state(self.cur), self.state(1 - self.cur)
         self.integration.basicstep(rd, wr, self.numParticles, self.particleRangeEnd, 0.0, 1)
+
+    # ---- checkpoints in the reference's own format (src/writers/HotFile.cc) ----
+    def save_hotfile(self, path: str, **layout) -> None:
+        """HotWriter equivalent: the current state, iteration count, t and dt; `DamBreak3D --resume <path>` and
+        Worker.from_hotfile() both continue from it. layout: buffer_count / order / num_open_boundaries overrides
+        (gpusph_b200.hotfile.write_hotfile) for simulations whose host buffer list differs from the plain one."""
+        from .hotfile import write_hotfile
+        st = self.download()
+        write_hotfile(path, st.pos, st.vel, st.info, st.hash, iterations=self.iterations, t=self.t, dt=self.dt, **layout)
+
+    @classmethod
+    def from_hotfile(cls, params: capi.Params, path: str, device=None, **kw) -> "Worker":
+        """Resume like GPUSPH --resume (src/GPUSPH.cc:393-453): particles, iteration count, t and dt from the file;
+        the first step rebuilds the neighbour list with calcHash (iterations > 0)."""
+        from .hotfile import particle_arrays, read_hotfile
+        hf = read_hotfile(path)
+        pos, vel, info, hashv = particle_arrays(hf)
+        w = cls(params, ParticleArrays(pos, vel, info, hashv), device, start_iteration=int(hf["iterations"]),
+                dt=float(hf["dt"]), **kw)
+        w.t = float(hf["t"])
+        return w
 
     # ---- host copies ----
     def download(self) -> ParticleArrays:

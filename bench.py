@@ -124,7 +124,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    binp = os.path.join(ROOT, "oracle", "_ref", "DamBreak3D")
+    binp = os.environ.get("B200SPH_REF_BIN") or os.path.join(ROOT, "oracle", "_ref", "DamBreak3D")
     kind, kw = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "particle_interactions_per_second", "unit": "M interactions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,

@@ -339,6 +339,11 @@ __device__ __forceinline__ bool too_many_neibs(const DevParams &P, uint nf, uint
 #ifndef B200_NL_LOAD_EL
 #define B200_NL_LOAD_EL 0
 #endif
+// B200_NL_GROUP4: distance tests four candidates at a time in the uniform-cell fast path (written at the end of round 1,
+// not yet measured on a GPU: off)
+#ifndef B200_NL_GROUP4
+#define B200_NL_GROUP4 0
+#endif
 __device__ __forceinline__ void st_list(ushort *p, const ushort v)
 {
 #if B200_NL_STORE_CS
@@ -434,8 +439,26 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					asm volatile("" : "+l"(cand));
 					const uint count = bucketEnd - bucketStart;
 					const uint self = index - bucketStart;                              // >= count when in another cell
+					uint k = 0;
+#if B200_NL_GROUP4
+					// four candidates per trip: four loads in flight, one branch for the (52 % likely) case that none of
+					// them is inside the search radius; accepted candidates are appended in index order like below
+					auto sq = [&](const float4 c) {
+						const float rx = __fsub_rn(px, c.x), ry = __fsub_rn(py, c.y), rz = __fsub_rn(pz, c.z);
+						return __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
+					};
+					for (; k + 4 <= count; k += 4) {
+						const float4 c0 = ld_cand(cand + k), c1 = ld_cand(cand + k + 1), c2 = ld_cand(cand + k + 2), c3 = ld_cand(cand + k + 3);
+						const bool a0 = sq(c0) < R2, a1 = sq(c1) < R2, a2 = sq(c2) < R2, a3 = sq(c3) < R2;
+						if (!(a0 | a1 | a2 | a3)) continue;
+						if (a0 && k != self && !inactive_w(c0.w)) append(bucketStart + k, t_first);
+						if (a1 && k + 1 != self && !inactive_w(c1.w)) append(bucketStart + k + 1, t_first);
+						if (a2 && k + 2 != self && !inactive_w(c2.w)) append(bucketStart + k + 2, t_first);
+						if (a3 && k + 3 != self && !inactive_w(c3.w)) append(bucketStart + k + 3, t_first);
+					}
+#endif
 #pragma unroll 2
-					for (uint k = 0; k < count; ++k) {
+					for (; k < count; ++k) {
 						const float4 np = ld_cand(cand + k);
 						const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);
 						// sqlength(relPos) = x*x + y*y + z*z as nvcc contracts it

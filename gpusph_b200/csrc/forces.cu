@@ -22,7 +22,12 @@
 #include "pair_physics.cuh"
 #include "euler_update.cuh"
 #include <stdlib.h>
+#include <mutex>
 #include <cub/device/device_scan.cuh>
+
+// the two per-kernel caches below are process-wide and the engines are shared by one host thread per device
+// (SURVEY.md section 8b "Threading"): one lock for both
+static std::mutex g_kernel_cache_lock;
 
 // list rows kept in flight by the gather kernel: measured on B200 at 2 M particles (dambreak2m / lattice2m):
 // 1 row 0.585 / 0.769 ms, 2 rows 0.535 / 0.805 ms, 4 rows 0.651 / 0.808 ms
@@ -683,7 +688,7 @@ static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather
 // rest of the 228 KB stays L1 for the neighbour gathers). Said explicitly because a host application may have set
 // a device-wide cache preference (GPUSPH sets cudaFuncCachePreferL1, src/cuda/cudautil.cc:71-79), which would
 // otherwise shrink the carve-out and cut the occupancy of this kernel several times over.
-static int gather_carveout(const void *kernel)
+static int gather_carveout(const void *kernel)      // caller holds g_kernel_cache_lock
 {
 	static const void *known[128]; static int pct[128]; static int nknown = 0;
 	for (int i = 0; i < nknown; ++i) if (known[i] == kernel) return pct[i];
@@ -709,6 +714,7 @@ static int gather_carveout(const void *kernel)
 static int set_carveout(const b200sph_ctx *ctx, const void *kernel)
 {
 	static const void *known[256]; static int dev[256]; static int nknown = 0;
+	std::lock_guard<std::mutex> guard(g_kernel_cache_lock);
 	for (int i = 0; i < nknown; ++i) if (known[i] == kernel && dev[i] == ctx->device) return B200SPH_OK;
 	CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, gather_carveout(kernel)));
 	if (nknown < 256) { known[nknown] = kernel; dev[nknown] = ctx->device; ++nknown; }

@@ -150,6 +150,8 @@ struct b200sph_ctx {
 	const void *host_pos_last, *host_vel_last, *dev_pos_last, *dev_vel_last;
 	int host_pending;
 	cudaEvent_t *trace_ev; int trace_resident;      // B200SPH_HOST_TRACE diagnostics
+	// zero-copy downloads (B200_HOST_ZEROCOPY builds + B200SPH_HOST_ZEROCOPY=1): host mirrors the next fused launch writes to
+	void *zc_host_pos, *zc_host_vel; int host_zerocopy;
 };
 
 // ---- error plumbing ----
@@ -202,3 +204,4 @@ int b200_coop_list(b200sph_ctx *ctx, const void *info, const void *pos, const ui
 void b200_invalidate_coop(b200sph_ctx *ctx);
 void b200_invalidate_tiles(b200sph_ctx *ctx);
 void b200_hoststep_destroy(b200sph_ctx *ctx);
+int b200_zero_copy_supported(void);   // forces.cu: was the pair kernel compiled with the zero-copy epilogue?

@@ -299,6 +299,15 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 				euler_update<2>(P, p, v, acc, info, particleHash, index, euler_dt<2>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
 			bo.eul_new_pos[index] = p;
 			bo.eul_new_vel[index] = v;
+#if B200_HOST_ZEROCOPY
+			// B200_HOST_ZEROCOPY (experimental, off): the integrated state also goes straight to the caller's mapped host
+			// buffers — a warp writes 512 contiguous bytes per array over PCIe — so that b200sph_step_host needs no
+			// device-to-host copy (and no copy-engine hand-over) behind the corrector
+			if (bo.eul_host_pos) {
+				__stcs(bo.eul_host_pos + index, p);
+				__stcs(bo.eul_host_vel + index, v);
+			}
+#endif
 		}
 	}
 
@@ -744,6 +753,7 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 }
 
 static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *eul, uint32_t *num_cfl_blocks);
+int b200_zero_copy_supported(void) { return B200_HOST_ZEROCOPY; }
 
 extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks)
 {
@@ -825,6 +835,12 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 		bo.eul_new_pos = (float4 *)eul->new_pos; bo.eul_new_vel = (float4 *)eul->new_vel;
 		bo.eul_bodies = ctx->have_bodies ? ctx->d_bodies : NULL;
 	}
+#if B200_HOST_ZEROCOPY
+	bo.eul_host_pos = fuse ? (float4 *)ctx->zc_host_pos : NULL;
+	bo.eul_host_vel = fuse ? (float4 *)ctx->zc_host_vel : NULL;
+	if (ctx->zc_host_pos && !fuse) { b200_set_error("forces_euler: zero-copy mirror requested but the launch is not fused"); return B200SPH_EINVAL; }
+#endif
+	ctx->zc_host_pos = ctx->zc_host_vel = NULL;      // one launch only
 	auto integrate_unfused = [&]() -> int {
 		if (!eul || fuse) return B200SPH_OK;
 		const size_t o = (size_t)from * 16;

@@ -1,6 +1,6 @@
 """HotFile compatibility with the REAL reference binary (oracle/_ref/DamBreak3D, GPU box only):
 * a HotFile the reference wrote, decoded and re-encoded by gpusph_b200/hotfile.py, is byte-identical;
-* Worker.from_hotfile continues the reference's run (reference 0..10, ours 10..15 against the reference's own 15);
+* Worker.from_hotfile continues the reference's run (reference 0..10, ours 10..20 against the reference's own 20);
 * Worker.save_hotfile writes a file the reference `--resume`s from (relay: reference 0..10, ours 10..20, reference
   20..30, against the reference's own uninterrupted 0..30).
 
@@ -71,16 +71,16 @@ def test_reencoded_hotfile_is_byte_identical_and_our_run_continues_the_reference
     params = params_for(pos.shape[0])
     w = Worker.from_hotfile(params, hot[10], 0, clobber=True)
     assert w.iterations == 10 and w.t == pytest.approx(hf["t"]) and w.dt == pytest.approx(hf["dt"])
-    for _ in range(5):
+    for _ in range(10):
         w.step()
-    mine = str(tmp_path / "hot_ours_00015.bin")
+    mine = str(tmp_path / "hot_ours_00020.bin")
     w.save_hotfile(mine)
-    h15 = read_hotfile(mine)
-    assert h15["iterations"] == 15 and h15["t"] > hf["t"] and h15["buffer_count"] == hf["buffer_count"]
-    assert 15 in hot
-    r15 = read_hotfile(hot[15])
-    assert h15["t"] == pytest.approx(r15["t"], rel=5e-5)
-    tg.compare(params, w.download(), ParticleArrays(*particle_arrays(r15)), pos_tol_dp=1e-4, vel_tol=1e-3, exact_order=False, rho_tol=5e-5)
+    h20 = read_hotfile(mine)
+    assert h20["iterations"] == 20 and h20["t"] > hf["t"] and h20["buffer_count"] == hf["buffer_count"]
+    # the reference checkpoints at its neighbour-rebuild iterations (and at the end): its own state at 20
+    r20 = read_hotfile(hot[20])
+    assert h20["t"] == pytest.approx(r20["t"], rel=5e-5)
+    tg.compare(params, w.download(), ParticleArrays(*particle_arrays(r20)), pos_tol_dp=1e-4, vel_tol=1e-3, exact_order=False, rho_tol=5e-5)
 
 
 @pytest.mark.timeout(600)

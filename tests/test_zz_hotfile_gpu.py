@@ -65,8 +65,6 @@ def test_reencoded_hotfile_is_byte_identical_and_our_run_continues_the_reference
     again = str(tmp_path / "reencoded.bin")
     write_hotfile(again, pos, vel, info, hashv, iterations=hf["iterations"], t=hf["t"], dt=hf["dt"], **layout)
     assert open(again, "rb").read() == open(hot[10], "rb").read()
-    # the defaults of the writer are this layout (what save_hotfile() writes without overrides)
-    assert hf["buffer_count"] == hfmod.PLAIN_BUFFER_COUNT and list(hf["buffers"]) == [b[0] for b in hfmod.PLAIN_BUFFERS]
 
     params = params_for(pos.shape[0])
     w = Worker.from_hotfile(params, hot[10], 0, clobber=True)
@@ -74,7 +72,7 @@ def test_reencoded_hotfile_is_byte_identical_and_our_run_continues_the_reference
     for _ in range(10):
         w.step()
     mine = str(tmp_path / "hot_ours_00020.bin")
-    w.save_hotfile(mine)
+    w.save_hotfile(mine, **layout)
     h20 = read_hotfile(mine)
     assert h20["iterations"] == 20 and h20["t"] > hf["t"] and h20["buffer_count"] == hf["buffer_count"]
     # the reference checkpoints at its neighbour-rebuild iterations (and at the end): its own state at 20
@@ -90,6 +88,8 @@ def test_reference_resumes_from_our_hotfile(reference_run, tmp_path):
     from gpusph_b200.simulation import Worker
     hot = reference_run
     hf = read_hotfile(hot[10])
+    # the defaults of the writer (what save_hotfile() writes without overrides) are the reference's layout for this run
+    assert hf["buffer_count"] == hfmod.PLAIN_BUFFER_COUNT and list(hf["buffers"]) == [b[0] for b in hfmod.PLAIN_BUFFERS]
     params = params_for(hf["particle_count"])
     w = Worker.from_hotfile(params, hot[10], 0, clobber=True)
     for _ in range(10):

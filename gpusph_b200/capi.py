@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SPH_LIB: alternative build of the same library (kernel tuning experiments, tools/build_variants.sh)
 LIB_PATH = os.environ.get("B200SPH_LIB") or os.path.join(_HERE, "libb200sph.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_FLUIDS = 4
 MAX_PLANES = 8
 
@@ -31,6 +31,8 @@ COMPVISC_KINEMATIC, COMPVISC_DYNAMIC = 0, 1
 VISCMODEL_MORRIS, VISCMODEL_MONAGHAN, VISCMODEL_ESPANOL_REVENGA = 0, 1, 2
 # simulation flags (src/simflags.h:71-86)
 ENABLE_DTADAPT, ENABLE_XSPH, ENABLE_PLANES, ENABLE_DEM = 1, 2, 4, 8
+ENABLE_MOVING_BODIES, ENABLE_INLET_OUTLET, ENABLE_WATER_DEPTH, ENABLE_DENSITY_SUM = 16, 32, 64, 128
+ENABLE_GAMMA_QUADRATURE, ENABLE_REPACKING, ENABLE_INTERNAL_ENERGY, ENABLE_MULTIFLUID = 256, 512, 1024, 2048
 AVG_ARITHMETIC, AVG_HARMONIC, AVG_GEOMETRIC = 0, 1, 2
 
 PT_FLUID, PT_BOUNDARY, PT_VERTEX, PT_TESTPOINT = 0, 1, 2, 3
@@ -108,6 +110,7 @@ class ForcesArgs(C.Structure):
         ("rb_forces", C.c_void_p), ("rb_torques", C.c_void_p), ("xsph", C.c_void_p),
         ("num_particles", C.c_uint32), ("from_particle", C.c_uint32), ("to_particle", C.c_uint32), ("cfl_offset", C.c_uint32),
         ("dt", C.c_float), ("step", C.c_int), ("dt_from_device", C.c_int),
+        ("packed", C.c_void_p),
     ]
 
 
@@ -116,6 +119,7 @@ class FusedEulerArgs(C.Structure):
     _fields_ = [
         ("old_pos", C.c_void_p), ("old_vel", C.c_void_p), ("new_pos", C.c_void_p), ("new_vel", C.c_void_p),
         ("dt", C.c_float), ("step", C.c_int), ("dt_from_device", C.c_int),
+        ("new_packed", C.c_void_p),
     ]
 
 
@@ -169,15 +173,18 @@ PROTOTYPES = {
     "b200sph_round_particles": (_U, [_U]),
     "b200sph_forces": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, C.POINTER(_U)]),
     "b200sph_set_rbcg": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
+    "b200sph_set_rbcg_euler": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
     "b200sph_set_rbstart": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     "b200sph_set_rbtrans": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200sph_set_rbsteprot": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200sph_set_rblinearvel": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200sph_set_rbangularvel": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200sph_forces_bodies": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, C.POINTER(_U)]),
+    "b200sph_pack_state": (C.c_int, [_P, _P, _P, _P, _U, _U]),
     "b200sph_reduce_rb_forces": (C.c_int, [_P, _P, _P, _P, C.POINTER(_U), C.POINTER(C.c_float), C.POINTER(C.c_float), _U, _U]),
     "b200sph_eos_probe": (C.c_int, [_P, _P, _P, _P, _U]),
     "b200sph_dtreduce": (C.c_int, [_P, _P, _P, _U, C.POINTER(C.c_float)]),
+    "b200sph_dtreduce_ex": (C.c_int, [_P, _P, _P, _U, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]),
     "b200sph_cflmax": (C.c_int, [_P, _P, _U, _P]),
     "b200sph_dt_from_cfl": (C.c_int, [_P, C.c_float, C.POINTER(C.c_float)]),
     "b200sph_step_set_dt": (C.c_int, [_P, C.c_float]),

@@ -50,7 +50,17 @@ extern "C" int b200sph_validate(const b200sph_params *p)
 	if (p->rheologytype > B200SPH_RHEOLOGY_NEWTONIAN) { b200_set_error("unsupported rheology %u", p->rheologytype); return B200SPH_EUNSUP; }
 	if (p->turbmodel > B200SPH_TURB_ARTIFICIAL) { b200_set_error("unsupported turbulence model %u", p->turbmodel); return B200SPH_EUNSUP; }
 	if (p->rheologytype == B200SPH_RHEOLOGY_NEWTONIAN && p->viscmodel > B200SPH_VISCMODEL_ESPANOL_REVENGA) { b200_set_error("unknown viscous model %u", p->viscmodel); return B200SPH_EINVAL; }
-	if (p->simflags & B200SPH_ENABLE_DEM) { b200_set_error("unsupported simulation flag ENABLE_DEM (out of scope, SURVEY.md section 8)"); return B200SPH_EUNSUP; }
+	if (p->simflags & ~B200SPH_SUPPORTED_SIMFLAGS) {
+		// the whole of SimParams::simflags arrives here: anything outside the allow-list is refused, never ignored
+		static const char *names[] = { "ENABLE_DTADAPT", "ENABLE_XSPH", "ENABLE_PLANES", "ENABLE_DEM", "ENABLE_MOVING_BODIES",
+			"ENABLE_INLET_OUTLET", "ENABLE_WATER_DEPTH", "ENABLE_DENSITY_SUM", "ENABLE_GAMMA_QUADRATURE", "ENABLE_REPACKING",
+			"ENABLE_INTERNAL_ENERGY", "ENABLE_MULTIFLUID" };
+		const uint32_t bad = p->simflags & ~B200SPH_SUPPORTED_SIMFLAGS;
+		int bit = 0; while (!((bad >> bit) & 1u)) ++bit;
+		b200_set_error("unsupported simulation flag %s (0x%x; out of scope, SURVEY.md section 8)", bit < 12 ? names[bit] : "(unknown)", bad);
+		return B200SPH_EUNSUP;
+	}
+	if ((p->simflags & B200SPH_ENABLE_MULTIFLUID) == 0 && p->num_fluids > 1) { b200_set_error("%u fluids without ENABLE_MULTIFLUID", p->num_fluids); return B200SPH_EINVAL; }
 	if ((p->simflags & B200SPH_ENABLE_PLANES) && !(p->r0 > 0)) { b200_set_error("ENABLE_PLANES needs the Lennard-Jones radius r0 > 0"); return B200SPH_EINVAL; }
 	if (p->viscavgop > B200SPH_AVG_GEOMETRIC || p->compvisc > B200SPH_COMPVISC_DYNAMIC) { b200_set_error("bad viscous averaging / computational viscosity"); return B200SPH_EINVAL; }
 	if (!(p->slength > 0) || !(p->influenceradius > 0)) { b200_set_error("non-positive smoothing length"); return B200SPH_EINVAL; }
@@ -114,9 +124,6 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	fill_devparams(p, &ctx->dp);
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
-	{ const char *e = getenv("B200SPH_FORCES_COOP"); ctx->use_coop = e ? atoi(e) : 0; }     // cooperative kernel is opt-in: measured slower (788 vs 553 us, profiles/r01_forces_coop_experiment_ncu.txt)
-	{ const char *e = getenv("B200SPH_FORCES_TILES"); ctx->use_tiles = e ? atoi(e) : 0; }   // staged kernel is opt-in: measured slower than the gather kernel
-	ctx->tile_cfg = 0; ctx->tile_p = TILE_P; ctx->tile_s = TILE_S;
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
 	CUDA_TRY(cudaMalloc(&ctx->d_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));
@@ -130,9 +137,6 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	CUDA_TRY(cudaMalloc(&ctx->d_step, sizeof(StepState)));
 	CUDA_TRY(cudaMemset(ctx->d_step, 0, sizeof(StepState)));
 	CUDA_TRY(cudaMallocHost(&ctx->h_step, sizeof(StepState)));
-	CUDA_TRY(cudaMalloc(&ctx->d_tile_info, 4 * sizeof(uint)));
-	CUDA_TRY(cudaMallocHost(&ctx->h_tile_info, 4 * sizeof(uint)));
-	CUDA_TRY(cudaEventCreateWithFlags(&ctx->tiles_event, cudaEventDisableTiming));
 	*out = ctx;
 	return B200SPH_OK;
 }
@@ -143,7 +147,9 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	b200_hoststep_destroy(ctx);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
-	cudaFree(ctx->info_tmp); cudaFree(ctx->aux); cudaFree(ctx->plist); cudaFree(ctx->pcount); cudaFree(ctx->tiles); cudaFree(ctx->row_tiles); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies); cudaFreeHost(ctx->h_tile_info); if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event); cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->pv[0]); cudaFree(ctx->pv[1]);
+	cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies);
+	cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);
 	free(ctx);
 	return B200SPH_OK;
@@ -210,40 +216,80 @@ static int push_bodies(b200sph_ctx *ctx)
 #define CHECK_BODIES(n, p) do { CHECK_CTX(ctx); if ((n) < 0 || (n) > B200SPH_MAX_BODIES) { b200_set_error("too many bodies (%d > %d)", (n), B200SPH_MAX_BODIES); return B200SPH_EINVAL; } \
 	if ((n) && !(p)) { b200_set_error("null body array"); return B200SPH_EINVAL; } if ((n) == 0) return B200SPH_OK; } while (0)
 
+// the FORCES engine's copy of the centres of gravity (torque arm, finalize_particle)
 extern "C" int b200sph_set_rbcg(b200sph_ctx *ctx, const int *g, const float *c, int n)
 {
 	CHECK_BODIES(n, g);
 	if (!c) { b200_set_error("null body array"); return B200SPH_EINVAL; }
 	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) { ctx->h_bodies->cgGridPos[b][a] = g[3 * b + a]; ctx->h_bodies->cgPos[b][a] = c[3 * b + a]; }
+	ctx->bodies_set |= BODY_SET_CG_FORCES;
+	return push_bodies(ctx);
+}
+// the INTEGRATION engine's copy (rigid motion, euler_update): stays at cg(n) while the forces copy moves on
+extern "C" int b200sph_set_rbcg_euler(b200sph_ctx *ctx, const int *g, const float *c, int n)
+{
+	CHECK_BODIES(n, g);
+	if (!c) { b200_set_error("null body array"); return B200SPH_EINVAL; }
+	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) { ctx->h_bodies->eulCgGridPos[b][a] = g[3 * b + a]; ctx->h_bodies->eulCgPos[b][a] = c[3 * b + a]; }
+	ctx->bodies_set |= BODY_SET_CG_EULER;
 	return push_bodies(ctx);
 }
 extern "C" int b200sph_set_rbstart(b200sph_ctx *ctx, const int *first, int n)
 {
 	CHECK_BODIES(n, first);
 	for (int b = 0; b < n; ++b) ctx->h_bodies->startIndex[b] = first[b];
+	ctx->bodies_set |= BODY_SET_START;
 	return push_bodies(ctx);
 }
 extern "C" int b200sph_set_rbtrans(b200sph_ctx *ctx, const float *t, int n)
 {
 	CHECK_BODIES(n, t);
 	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) ctx->h_bodies->trans[b][a] = t[3 * b + a];
+	ctx->bodies_set |= BODY_SET_TRANS;
 	return push_bodies(ctx);
 }
 extern "C" int b200sph_set_rbsteprot(b200sph_ctx *ctx, const float *r, int n)
 {
 	CHECK_BODIES(n, r);
 	for (int b = 0; b < n; ++b) for (int a = 0; a < 9; ++a) ctx->h_bodies->steprot[b][a] = r[9 * b + a];
+	ctx->bodies_set |= BODY_SET_STEPROT;
 	return push_bodies(ctx);
 }
 extern "C" int b200sph_set_rblinearvel(b200sph_ctx *ctx, const float *v, int n)
 {
 	CHECK_BODIES(n, v);
 	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) ctx->h_bodies->linearvel[b][a] = v[3 * b + a];
+	ctx->bodies_set |= BODY_SET_LINVEL;
 	return push_bodies(ctx);
 }
 extern "C" int b200sph_set_rbangularvel(b200sph_ctx *ctx, const float *v, int n)
 {
 	CHECK_BODIES(n, v);
 	for (int b = 0; b < n; ++b) for (int a = 0; a < 3; ++a) ctx->h_bodies->angularvel[b][a] = v[3 * b + a];
+	ctx->bodies_set |= BODY_SET_ANGVEL;
 	return push_bodies(ctx);
+}
+
+// The integration moves FG_MOVING_BOUNDARY particles with the body data; it must never skip that silently. Called by
+// both integration paths (stand-alone kernel, fused epilogue). Returns the device record, or NULL when no body was
+// ever described (then the caller's particles must not contain moving ones: that is the contract the reference's
+// GPUWorker fulfils by uploading all five arrays whenever numbodies > 0, src/GPUWorker.cc:1749, 3128-3160).
+int b200_euler_bodies(b200sph_ctx *ctx, const uint32_t *hash, const BodyData **out)
+{
+	*out = NULL;
+	const unsigned eul = ctx->bodies_set & BODY_SET_EULER_ALL;
+	if (!eul) {
+		if (ctx->hp.simflags & B200SPH_ENABLE_MOVING_BODIES) {
+			b200_set_error("euler: ENABLE_MOVING_BODIES is set but no setrbcg/setrbtrans/setrbsteprot/setrblinearvel/setrbangularvel call was made");
+			return B200SPH_EINVAL;
+		}
+		return B200SPH_OK;
+	}
+	if (eul != BODY_SET_EULER_ALL) {
+		b200_set_error("euler: incomplete body description (setrb* calls made: mask 0x%x, needed 0x%x)", eul, BODY_SET_EULER_ALL);
+		return B200SPH_EINVAL;
+	}
+	if (!hash) { b200_set_error("euler: moving bodies need the particle hash (cell of each particle)"); return B200SPH_EINVAL; }
+	*out = ctx->d_bodies;
+	return B200SPH_OK;
 }

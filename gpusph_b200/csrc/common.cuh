@@ -70,18 +70,9 @@ struct DevParams {
 	const struct StepState *dev_state;   // non-NULL: dt from the device-resident record (dt/2 for step 1)
 };
 
-// One CTA of the staged forces kernel: a run of consecutive non-empty cells along COORD1 inside one
-// (COORD2, COORD3) row, plus the particle ranges of the 9 neighbouring rows that cover its 27-cell
-// neighbourhood (each row of cells is one contiguous particle range because COORD1 is the fastest hash digit).
-// tile shape of the opt-in staged kernel: 128 threads, 1152 staged particles (3 x 16 B x 1152 = 54 KB + 14 KB of cell
-// bases -> 3 CTAs per SM); the best of (128,1536) (128,1152) (64,1024) (64,768) measured on B200
-#define TILE_P 128
-#define TILE_S 1152
-struct Tile {
-	uint first, count;      // central particles [first, first+count)
-	uint row_start[9];      // first staged particle of neighbour row r = (d2+1) + 3*(d3+1)
-	uint row_count[9];      // staged particles of that row (0 = none)
-};
+// One neighbour record of the pair kernel: the particle's pos and vel entries side by side, so that a gather is ONE
+// 256-bit load touching one 32-byte sector (forces.cu)
+struct __align__(32) PosVel { float4 pos, vel; };
 
 struct NeibsCounters {     // mirrors the reference's device counters, src/cuda/buildneibs_kernel.cu:108-112
 	int numInteractions;
@@ -94,15 +85,30 @@ struct NeibsCounters {     // mirrors the reference's device counters, src/cuda/
 
 // moving / force-feedback bodies: device copy of what the reference keeps in __constant__ arrays
 // (src/cuda/forces_kernel.cu:81-83, src/cuda/euler_kernel.cu:45-50)
+// The centre of gravity exists TWICE on purpose, like the reference's two __constant__ copies: the integrator uploads
+// cg(n+1) to the forces engine right after MOVE_BODIES (FORCES_UPLOAD_OBJECTS_CG) while the integration keeps
+// rotating about cg(n) until the end of the step (EULER_UPLOAD_OBJECTS_CG;
+// src/integrators/PredictorCorrectorIntegrator.cc:332,556-587, "We always have cg = cg(n)" src/cuda/euler_kernel.def:488).
 struct BodyData {
-	int cgGridPos[B200SPH_MAX_BODIES][3];
+	int cgGridPos[B200SPH_MAX_BODIES][3];      // forces engine copy: torque arm in finalize
 	float cgPos[B200SPH_MAX_BODIES][3];
+	int eulCgGridPos[B200SPH_MAX_BODIES][3];   // integration engine copy: rigid motion in euler
+	float eulCgPos[B200SPH_MAX_BODIES][3];
 	int startIndex[B200SPH_MAX_BODIES];
 	float trans[B200SPH_MAX_BODIES][3];
 	float steprot[B200SPH_MAX_BODIES][9];
 	float linearvel[B200SPH_MAX_BODIES][3];
 	float angularvel[B200SPH_MAX_BODIES][3];
 };
+
+#define BODY_SET_CG_FORCES 1u
+#define BODY_SET_START     2u
+#define BODY_SET_CG_EULER  4u
+#define BODY_SET_TRANS     8u
+#define BODY_SET_STEPROT   16u
+#define BODY_SET_LINVEL    32u
+#define BODY_SET_ANGVEL    64u
+#define BODY_SET_EULER_ALL (BODY_SET_CG_EULER | BODY_SET_TRANS | BODY_SET_STEPROT | BODY_SET_LINVEL | BODY_SET_ANGVEL)
 
 // device-resident time-stepping record (b200sph_step_* entry points)
 struct StepState {
@@ -120,25 +126,14 @@ struct b200sph_ctx {
 	// scratch (grown on demand)
 	void *sort_tmp; size_t sort_tmp_bytes;
 	uint64_t *keys_in, *keys_out; uint32_t *vals_out; void *info_tmp; size_t sort_cap;
-	float4 *aux; size_t aux_cap;           // per-particle {P/rho^2, sound speed, density, fluid#} (forces.cu aux_kernel)
-	// tiles of the staged forces kernel, rebuilt with the neighbour list
-	Tile *tiles; size_t tiles_cap; uint *row_tiles; size_t row_tiles_cap;
-	uint *d_tile_info; uint *h_tile_info;   // {numTiles, overflow flag}
-	cudaEvent_t tiles_event; int tiles_state;   // 0 none, 1 copy in flight, 2 valid
-	uint num_tiles; uint tiles_range_end; const uint32_t *tiles_cellstart;
-	int use_tiles;                          // env B200SPH_FORCES_TILES (default 0)
-	// cooperative forces kernel: private transposed copy of the neighbour list (forces.cu, b200_coop_list)
-	uint *plist; size_t plist_cap;          // entries, see coop_slot()
-	ushort2 *pcount; size_t pcount_cap;     // per particle {fluid neighbours, boundary neighbours}
-	const void *coop_src; uint coop_n;      // list buffer / particle count the copy was made from (NULL: none)
-	int use_coop;                           // env B200SPH_FORCES_COOP (default 0)
-	int tile_cfg, tile_p, tile_s;           // tile shape handed to the tile builder
+	PosVel *pv[2]; size_t pv_cap[2];        // context-owned neighbour records (forces.cu b200_packed_scratch)
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions
 	float *h_scalar;                        // pinned host scalar
 	int *d_flag; int *h_flag;
 	StepState *d_step; StepState *h_step;
 	BodyData *d_bodies; BodyData *h_bodies; int have_bodies;
+	unsigned bodies_set;                    // BODY_SET_* bits: which setrb* calls were made
 	// pipelined stepping of a host-resident state (hoststep.cu): copy streams, per-stripe events, and what the
 	// previous call left in flight (the next call chains on it stripe by stripe)
 	cudaStream_t up_stream, down_stream;
@@ -167,6 +162,16 @@ static inline uint div_up(uint a, uint b) { return (a + b - 1) / b; }
 
 // ---- device helpers ----
 #ifdef __CUDACC__
+__device__ __forceinline__ void ld_posvel(const PosVel *p, float4 &a, float4 &b)
+{
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st_posvel(PosVel *p, const float4 a, const float4 b)
+{
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 __device__ __forceinline__ int ptype_of(ushort4 info) { return info.x & 7; }
 __device__ __forceinline__ uint id_of(ushort4 info) { return (uint)info.z | ((uint)info.w << 16); }
 __device__ __forceinline__ int fluid_num_of(ushort4 info) { return info.y >> 12; }
@@ -198,10 +203,7 @@ __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
 #endif
 
 // ---- internal launchers implemented in the .cu files ----
-int b200_build_tiles(b200sph_ctx *ctx, const uint32_t *cell_start, const uint32_t *cell_end, uint range_end);
-int b200_coop_list(b200sph_ctx *ctx, const void *info, const void *pos, const uint32_t *hash, const uint32_t *cell_start,
-	const uint16_t *neibs_list, uint n);
-void b200_invalidate_coop(b200sph_ctx *ctx);
-void b200_invalidate_tiles(b200sph_ctx *ctx);
+int b200_packed_scratch(b200sph_ctx *ctx, int which, uint32_t n, PosVel **out);   // forces.cu
 void b200_hoststep_destroy(b200sph_ctx *ctx);
+int b200_euler_bodies(b200sph_ctx *ctx, const uint32_t *hash, const BodyData **out);   // api.cu
 int b200_zero_copy_supported(void);   // forces.cu: was the pair kernel compiled with the zero-copy epilogue?

@@ -30,8 +30,9 @@ static int launch_euler(b200sph_ctx *ctx, const void *old_pos, const void *old_v
 {
 	CHECK_CTX(ctx);
 	if (step != 1 && step != 2) { b200_set_error("unsupported predcorr timestep %d", step); return B200SPH_EINVAL; }   // euler.cu:361-362
-	const BodyData *bodies = (ctx->have_bodies && hash) ? ctx->d_bodies : NULL;
 	if (particle_range_end == 0) return B200SPH_OK;
+	const BodyData *bodies = NULL;
+	{ const int rc = b200_euler_bodies(ctx, hash, &bodies); if (rc) return rc; }
 	if (!old_pos || !old_vel || !info || !forces || !new_pos || !new_vel) { b200_set_error("euler: null buffer"); return B200SPH_EINVAL; }
 	if ((ctx->hp.simflags & B200SPH_ENABLE_XSPH) && !xsph) { b200_set_error("euler: ENABLE_XSPH needs the xsph buffer"); return B200SPH_EINVAL; }
 	if (!(ctx->hp.simflags & B200SPH_ENABLE_XSPH)) xsph = NULL;

@@ -34,9 +34,9 @@ euler_update(const DevParams &P, float4 &pos, float4 &vel, const float4 force, c
 				const int obj = object_of_y(info.y);
 				const int3 gp = grid_pos(P, particleHash[index] & CELLTYPE_BITMASK);
 				// relPos = x - x_cg (globalDistance, cellgrid.cuh:152-160)
-				const float rx = (float)(gp.x - bodies->cgGridPos[obj][0]) * P.cellSize[0] + (pos.x - bodies->cgPos[obj][0]);
-				const float ry = (float)(gp.y - bodies->cgGridPos[obj][1]) * P.cellSize[1] + (pos.y - bodies->cgPos[obj][1]);
-				const float rz = (float)(gp.z - bodies->cgGridPos[obj][2]) * P.cellSize[2] + (pos.z - bodies->cgPos[obj][2]);
+				const float rx = (float)(gp.x - bodies->eulCgGridPos[obj][0]) * P.cellSize[0] + (pos.x - bodies->eulCgPos[obj][0]);
+				const float ry = (float)(gp.y - bodies->eulCgGridPos[obj][1]) * P.cellSize[1] + (pos.y - bodies->eulCgPos[obj][1]);
+				const float rz = (float)(gp.z - bodies->eulCgGridPos[obj][2]) * P.cellSize[2] + (pos.z - bodies->eulCgPos[obj][2]);
 				const float *rot = bodies->steprot[obj];
 				// applyrot, euler_kernel.cu:67-74
 				pos.x += (rot[0] - 1.0f) * rx + rot[1] * ry + rot[2] * rz;

@@ -1,22 +1,20 @@
-// forces.cu — forces engine: fused pair-interaction kernels, CFL reduction, dt.
+// forces.cu — forces engine: the fused pair-interaction kernel, CFL reduction, dt.
 //
 // Behavioural specification: GPUSPH src/cuda/forces.cu + forces_kernel.def (cited inline and in pair_physics.cuh).
 // The reference evaluates one half-step with FOUR launches (forcesDevice<fluid,fluid>, <fluid,boundary>,
 // <boundary,fluid>, finalizeforcesDevice), each re-reading the particle and read-modify-writing forces[] in
-// global memory, gathers every neighbour through the texture path and re-evaluates the equation of state
-// (two __powf = 4 MUFU + an IEEE division) for BOTH particles of every pair. Here:
-//  * `aux_kernel` evaluates P/rho^2, the sound speed and the density ONCE per particle (same __powf expressions,
-//    so the values are the ones the reference recomputes per pair);
-//  * ONE launch walks both neighbour-list sections of a particle with the accumulator in registers, applies the
-//    finalize step and reduces the CFL term — forces[] is written exactly once;
+// global memory, and gathers every neighbour's position, velocity and info through three texture fetches. Here:
+//  * ONE launch (`forces_gather_kernel`) walks both neighbour-list sections of a particle with the accumulator in
+//    registers, applies the finalize step, reduces the CFL term and (b200sph_forces_euler) integrates the particle in
+//    its epilogue — forces[] is written exactly once and never read back;
+//  * neighbours are gathered as ONE 32-byte record {pos.xyz, mass, vel.xyz, rho~} with one 256-bit load
+//    (ld.global.nc.v8.f32 -> LDG.E.256, sm_100): one sector in one line per neighbour instead of two sectors in two
+//    lines. The records are an interleaved copy of the reference's pos / vel buffers, made by a streaming pre-pass
+//    (`pack_state_kernel`, 64 B per particle) or handed from launch to launch by the fused integration epilogue;
+//  * the neighbour's P/rho^2 and sound speed are re-evaluated per pair from rho~ with the reference's __powf
+//    expressions sharing one logarithm (12 ALU/MUFU instructions instead of a third gather);
 //  * physics options are template parameters, per-pair divisions/roots are MUFU approximations (the bit-exact
-//    distance test belongs to the list builder);
-//  * two kernels share that physics:
-//      - forces_tile_kernel  (default): one CTA per *tile* (tiles.cu); the tile's 9 neighbouring particle ranges
-//        (pos, vel, aux) are staged into shared memory with TMA bulk copies (cp.async.bulk + mbarrier) while the
-//        threads compute their 27 cell bases; every per-pair gather is then an LDS;
-//      - forces_gather_kernel (fallback: periodic COORD1, tiles that do not fit, no tiles built): gathers through
-//        L1/L2 like the reference, still single-pass and fused.
+//    distance test belongs to the list builder).
 // Summation order inside each list section is the reference's (list order); the fluid and boundary partial sums
 // are combined as (0 + sum_fluid) + sum_boundary like the reference's RMW sequence.
 #include "pair_physics.cuh"
@@ -25,27 +23,19 @@
 #include <mutex>
 #include <cub/device/device_scan.cuh>
 
-// the two per-kernel caches below are process-wide and the engines are shared by one host thread per device
-// (SURVEY.md section 8b "Threading"): one lock for both
+// the per-kernel caches below are process-wide and the engines are shared by one host thread per device
+// (SURVEY.md section 8b "Threading")
 static std::mutex g_kernel_cache_lock;
 
 // list rows kept in flight by the gather kernel: measured on B200 at 2 M particles (dambreak2m / lattice2m):
 // 1 row 0.585 / 0.769 ms, 2 rows 0.535 / 0.805 ms, 4 rows 0.651 / 0.808 ms
+#ifndef GATHER_PF
 #define GATHER_PF 2
+#endif
 
 // ---------------------------------------------------------------------------
-// per-particle pre-pass
+// per-particle pre-passes
 // ---------------------------------------------------------------------------
-// x = P/rho^2 (precalc_pressure<SPH_F1>, forces_kernel.def:419-429), y = sound speed, z = physical density, w = fluid#
-__global__ void __launch_bounds__(BLOCK_STREAM)
-aux_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ vel, const ushort4 *__restrict__ info,
-	float4 *__restrict__ aux, const uint n)
-{
-	const uint i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	aux[i] = eos_from_density(P, vel[i].w, fluid_num_of(info[i]));
-}
-
 __global__ void __launch_bounds__(BLOCK_STREAM)
 eos_probe_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ vel, const ushort4 *__restrict__ info,
 	float2 *__restrict__ out, const uint n)
@@ -54,19 +44,6 @@ eos_probe_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__
 	if (i >= n) return;
 	const float4 e = eos_from_density(P, vel[i].w, fluid_num_of(info[i]));
 	out[i] = make_float2(e.x, e.y);
-}
-
-static int aux_precompute(b200sph_ctx *ctx, const float4 *vel, const ushort4 *info, uint n)
-{
-	if (ctx->aux_cap < n) {
-		cudaFree(ctx->aux); ctx->aux = NULL; ctx->aux_cap = 0;
-		const size_t cap = (size_t)n + (n >> 3) + 1024;
-		CUDA_TRY(cudaMalloc(&ctx->aux, cap * sizeof(float4)));
-		ctx->aux_cap = cap;
-	}
-	aux_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, vel, info, ctx->aux, n);
-	KERNEL_TRY();
-	return B200SPH_OK;
 }
 
 extern "C" int b200sph_eos_probe(b200sph_ctx *ctx, const void *vel, const void *info, void *out, uint32_t n)
@@ -79,8 +56,44 @@ extern "C" int b200sph_eos_probe(b200sph_ctx *ctx, const void *vel, const void *
 	return B200SPH_OK;
 }
 
+// interleave pos / vel into the 32-byte records the pair kernel gathers (streaming: R 32 + W 32 per particle)
+__global__ void __launch_bounds__(BLOCK_STREAM)
+pack_state_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel, PosVel *__restrict__ pv, const uint from, const uint to)
+{
+	const uint i = from + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= to) return;
+	st_posvel(pv + i, pos[i], vel[i]);
+}
+
+extern "C" int b200sph_pack_state(b200sph_ctx *ctx, const void *pos, const void *vel, void *packed, uint32_t from, uint32_t to)
+{
+	CHECK_CTX(ctx);
+	if (to <= from) return B200SPH_OK;
+	if (!pos || !vel || !packed) { b200_set_error("pack_state: null buffer"); return B200SPH_EINVAL; }
+	if ((uintptr_t)packed & 31u) { b200_set_error("pack_state: the record buffer must be 32-byte aligned"); return B200SPH_EINVAL; }
+	pack_state_kernel<<<div_up(to - from, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>((const float4 *)pos, (const float4 *)vel,
+		(PosVel *)packed, from, to);
+	KERNEL_TRY();
+	return B200SPH_OK;
+}
+
+// context-owned record buffers (which = 0, 1): the pre-pass target of reference-style calls, and the two state copies of
+// the host-buffer step (hoststep.cu)
+int b200_packed_scratch(b200sph_ctx *ctx, int which, uint32_t n, PosVel **out)
+{
+	if (ctx->pv_cap[which] < n) {
+		// the buffer may still be read by work in flight on another lane of this context
+		CUDA_TRY(cudaDeviceSynchronize());
+		cudaFree(ctx->pv[which]); ctx->pv[which] = NULL; ctx->pv_cap[which] = 0;
+		const size_t cap = (size_t)n + (n >> 3) + 1024;
+		CUDA_TRY(cudaMalloc(&ctx->pv[which], cap * sizeof(PosVel)));
+		ctx->pv_cap[which] = cap;
+	}
+	*out = ctx->pv[which];
+	return B200SPH_OK;
+}
 // ---------------------------------------------------------------------------
-// shared pieces of the two kernels
+// pieces of the pair kernel
 // ---------------------------------------------------------------------------
 // cellStart of the 27 neighbouring cells of a particle in cell h0 -> out[cell * stride_out] (27 independent loads).
 // calcGridHashPeriodic, cellgrid.cuh:174-185 (cells outside a non-periodic domain are never listed, the wrapped
@@ -107,8 +120,7 @@ __device__ __forceinline__ float4 cell_offset(const DevParams &P, const int c)
 }
 
 // Walk one section of a particle's neighbour-list column. fetch(slot, np, nv, ne) loads the neighbour record
-// `slot` = base-of-its-cell + offset-in-cell (global index for the gather kernel, shared-memory slot for the
-// staged kernel); lut(cell, base, ox, oy, oz) returns the first slot of neighbour cell `cell` and its offset times
+// `slot` = base-of-its-cell + offset-in-cell (global particle index); lut(cell, base, ox, oy, oz) returns the first slot of neighbour cell `cell` and its offset times
 // the cell size. PF list rows are read ahead of use; the read-ahead offset is clamped to the list.
 // WIDE: 64-bit list offsets (lists of 2^31 entries or more), else 32-bit (one VIADDMNMX per row).
 // Accumulation order = list order, as in the reference (neibs_iteration.cuh:56-200).
@@ -172,6 +184,8 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 	c.pos = pos; c.vel = vel;
 	c.p_precalc = e.x; c.sspeed = e.y; c.rho = e.z;
 	c.fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
+	// the Molteni-Colagrossi switch compares raw pressures (forces_kernel.def:1925-1928)
+	c.press = (RHODIFF == B200SPH_RHODIFF_COLAGROSSI || RHODIFF == RHODIFF_RUNTIME) ? eos_pressure(P, vel.w, c.fnum) : 0.0f;
 	c.xsph = false;
 	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 	float3 xs = make_float3(0.f, 0.f, 0.f);
@@ -211,14 +225,14 @@ __device__ __forceinline__ float4 lds_f4(uint a)
 #define B200_MIN_BLOCKS 8
 #endif
 // (the detour through shared memory is what stops ptxas from re-deriving the value from the constant bank)
-struct Pinned { float v[20]; };
+struct Pinned { float v[24]; };
 
 // 8 CTAs (32 warps) per SM for the lean variants: 64 registers (8 bytes of spill) measured 2.7 % faster than 7 CTAs at
 // 72 registers, 9 CTAs at 56 registers 15 % slower (dambreak2m; the kernel is latency-bound: 1.3 eligible warps per
 // cycle, profiles/r01_forces_gather_final_ncu.txt). The variants with more live state keep 7.
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, bool WIDE>
 __global__ void __launch_bounds__(BLOCK_FORCES, (LAMINAR || MULTIFLUID || WIDE || RHODIFF == RHODIFF_RUNTIME) ? 7 : B200_MIN_BLOCKS)
-forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
+forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restrict__ pvArray,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
 	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
@@ -234,6 +248,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 	EosConsts E;
 	E.gamma = P.gammacoeff[0]; E.sspow = P.sspowercoeff[0]; E.b = P.bcoeff[0]; E.ss = P.sscoeff[0]; E.rho0 = P.rho0[0];
 	uint a_off = smem_u32(s_celloff);
+	const PosVel *pv = pvArray;       // pinned below: the record base is used by every gather
 	ListGeom L;
 	L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos;
 #if B200_HOIST
@@ -244,6 +259,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 		v[8] = k.diff; v[9] = k.grav_scale; v[10] = E.gamma; v[11] = E.sspow; v[12] = E.b; v[13] = E.ss; v[14] = E.rho0;
 		v[15] = __uint_as_float(a_off); v[16] = k.h; v[17] = __uint_as_float(L.stride);
 		v[18] = __uint_as_float((uint)(uintptr_t)neibsList); v[19] = __uint_as_float((uint)((uintptr_t)neibsList >> 32));
+		v[20] = __uint_as_float((uint)(uintptr_t)pvArray); v[21] = __uint_as_float((uint)((uintptr_t)pvArray >> 32));
 	}
 	__syncthreads();
 	{
@@ -253,6 +269,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 		k.diff = ld(8); k.grav_scale = ld(9); E.gamma = ld(10); E.sspow = ld(11); E.b = ld(12); E.ss = ld(13); E.rho0 = ld(14);
 		a_off = __float_as_uint(ld(15)); k.h = ld(16); L.stride = __float_as_uint(ld(17));
 		L.list = (const ushort *)((uintptr_t)__float_as_uint(ld(18)) | ((uintptr_t)__float_as_uint(ld(19)) << 32));
+		pv = (const PosVel *)((uintptr_t)__float_as_uint(ld(20)) | ((uintptr_t)__float_as_uint(ld(21)) << 32));
 	}
 #else
 	__syncthreads();
@@ -261,7 +278,8 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 	if (index < toParticle) {
 		const ushort4 info = infoArray[index];
 		const int type = ptype_of(info);
-		const float4 pos = posArray[index];
+		float4 pos, vel;
+		ld_posvel(pv + index, pos, vel);
 		float4 acc;
 		bool have_acc = false;
 		if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000)) {
@@ -276,13 +294,11 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 				const float4 o = lds_f4(a_off + cell * 16u);
 				ox = o.x; oy = o.y; oz = o.z;
 			};
-			// neighbour data straight from the reference's own pos / vel buffers (two 128-bit gathers); EOS terms from
-			// rho~ on the fly
+			// one 256-bit gather per neighbour: its {pos, mass, vel, rho~} record; EOS terms from rho~ on the fly
 			auto fetch = [&](const uint j, float4 &np, float4 &nv, float4 &ne) {
-				np = ld_gather(posArray + j); nv = ld_gather(velArray + j);
+				ld_posvel(pv + j, np, nv);
 				ne = MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
 			};
-			const float4 vel = velArray[index];
 			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE>(P, k, index, info, type, pos,
 				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, forces,
 				GEN ? bo.xsph : NULL, &acc);
@@ -291,7 +307,8 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 		// with the forces still in registers. A particle the pair loop skips integrates with its FORCES entry as is.
 		if (bo.eul_step) {
 			if (!have_acc) acc = forces[index];
-			float4 p = bo.eul_old_pos[index], v = bo.eul_old_vel[index];
+			float4 p = pos, v = vel;
+			if (bo.eul_old_pos) { p = bo.eul_old_pos[index]; v = bo.eul_old_vel[index]; }
 			const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (bo.eul_step == 1)
 				euler_update<1>(P, p, v, acc, info, particleHash, index, euler_dt<1>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
@@ -299,6 +316,8 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 				euler_update<2>(P, p, v, acc, info, particleHash, index, euler_dt<2>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
 			bo.eul_new_pos[index] = p;
 			bo.eul_new_vel[index] = v;
+			// the integrated state as the record the NEXT force evaluation gathers (no pack pre-pass between launches)
+			if (bo.eul_new_packed) st_posvel(bo.eul_new_packed + index, p, v);
 #if B200_HOST_ZEROCOPY
 			// B200_HOST_ZEROCOPY (experimental, off): the integrated state also goes straight to the caller's mapped host
 			// buffers — a warp writes 512 contiguous bytes per array over PCIe — so that b200sph_step_host needs no
@@ -328,361 +347,15 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const float4 *__restri
 }
 
 // ---------------------------------------------------------------------------
-// cooperative kernel: COOP_LPP lanes per particle
-// ---------------------------------------------------------------------------
-// The gather kernel above gives every thread its own list column: at a given row the 8 threads of a quarter-warp
-// fetch the k-th neighbours of 8 different particles, which on a dam break fall on ~5.6 different 128-byte lines —
-// and the L1 data pipe, at one line per quarter-warp per cycle, is what bounds that kernel (ncu: lsu wavefronts 87 %).
-// Here COOP_LPP (8) lanes share ONE particle and fetch COOP_LPP *consecutive* entries of its list. The list is
-// ordered by cell and, inside a cell, by particle index, so those entries are neighbours in memory too: ~3.2 lines
-// per quarter-warp on the same data (counted on the host from a dam-break list). The price is a transposed private
-// copy of the list (b200_coop_list, made once per neighbour-list build) with absolute particle indices, a shuffle
-// reduction per particle, and the central-particle work being done by every lane of the group.
-// Summation order: lane-strided partial sums combined by a butterfly (the reference sums in list order); the
-// difference is rounding-level and covered by the parity tolerance.
-#ifndef COOP_LPP
-#define COOP_LPP 8
-#endif
-#define COOP_PPW (32 / COOP_LPP)             // particles per warp
-#define COOP_BLOCK 128
-#define COOP_INDEX_BITS 27                   // entry = cell code (5 bits) << 27 | absolute particle index
-#define COOP_INDEX_MASK ((1u << COOP_INDEX_BITS) - 1u)
-#ifndef COOP_MIN_BLOCKS
-#define COOP_MIN_BLOCKS 7
-#endif
-
-// slot of entry k of particle i: the COOP_LPP entries a lane group reads in one step are contiguous, and so are the
-// groups of one warp (one 128-byte line per warp per step)
-__host__ __device__ __forceinline__ size_t coop_slot(const uint i, const uint k, const uint nchunks)
-{
-	return ((size_t)(i / COOP_PPW) * nchunks + k / COOP_LPP) * 32u + (i % COOP_PPW) * COOP_LPP + k % COOP_LPP;
-}
-
-// reference-format list -> private list. One thread per particle walks its column like forcesDevice would
-// (neibs_iteration.cuh:56-200, getNeibIndex cellgrid.cuh:198-226): fluid section up from row 0, boundary section down
-// from neibboundpos (only fluid particles use it, forces_kernel.def:3634-3726).
-__global__ void __launch_bounds__(BLOCK_STREAM)
-coop_list_kernel(const __grid_constant__ DevParams P, const ushort4 *__restrict__ infoArray, const float4 *__restrict__ posArray,
-	const uint *__restrict__ particleHash, const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
-	uint *__restrict__ plist, ushort2 *__restrict__ pcount, const uint n, const uint nchunks)
-{
-	const uint i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const ushort4 info = infoArray[i];
-	const int type = ptype_of(info);
-	uint cf = 0, cb = 0;
-	if ((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(posArray[i].w) < __int_as_float(0x7f800000)) {
-		const int h0 = (int)(particleHash[i] & CELLTYPE_BITMASK);
-		const int3 gp = grid_pos(P, (uint)h0);
-		const int sx = P.hstride[0], sy = P.hstride[1], sz = P.hstride[2];
-		const int Gx = P.gridSize[0], Gy = P.gridSize[1], Gz = P.gridSize[2];
-		const int dx[3] = { gp.x == 0 ? (Gx - 1) * sx : -sx, 0, gp.x == Gx - 1 ? -(Gx - 1) * sx : sx };
-		const int dy[3] = { gp.y == 0 ? (Gy - 1) * sy : -sy, 0, gp.y == Gy - 1 ? -(Gy - 1) * sy : sy };
-		const int dz[3] = { gp.z == 0 ? (Gz - 1) * sz : -sz, 0, gp.z == Gz - 1 ? -(Gz - 1) * sz : sz };
-		const size_t stride = P.stride;
-		const ushort *col = neibsList + i;
-		uint k = 0;
-		for (int section = 0; section < (type == PT_FLUID ? 2 : 1); ++section) {
-			uint base = 0, code = 0;
-			int row = section == 0 ? 0 : (int)P.neibboundpos;
-			const int step = section == 0 ? 1 : -1;
-			while (row >= 0 && row < (int)P.neiblistsize && k < nchunks * COOP_LPP) {
-				uint nd = ld_neib(col + (size_t)row * stride);
-				if (nd == NEIBS_END) break;
-				if (nd >= CELLNUM_ENCODED) {
-					code = (nd >> CELLNUM_SHIFT) - 1;
-					if (code >= 27) break;                       // not a list column (never built for this particle)
-					nd &= NEIBINDEX_MASK;
-					base = __ldg(cellStart + (h0 + dx[code % 3] + dy[(code / 3) % 3] + dz[code / 9]));
-				}
-				plist[coop_slot(i, k, nchunks)] = (code << COOP_INDEX_BITS) | ((base + nd) & COOP_INDEX_MASK);
-				++k; row += step;
-			}
-			if (section == 0) cf = k; else cb = k - cf;
-		}
-	}
-	pcount[i] = make_ushort2((ushort)cf, (ushort)cb);
-}
-
-void b200_invalidate_coop(b200sph_ctx *ctx) { ctx->coop_src = NULL; ctx->coop_n = 0; }
-
-int b200_coop_list(b200sph_ctx *ctx, const void *info, const void *pos, const uint32_t *hash, const uint32_t *cell_start,
-	const uint16_t *neibs_list, uint n)
-{
-	b200_invalidate_coop(ctx);
-	if (!ctx->use_coop || n == 0 || n > COOP_INDEX_MASK) return B200SPH_OK;
-	const uint nchunks = div_up(ctx->dp.neiblistsize, COOP_LPP);
-	const size_t groups = div_up(n, COOP_PPW);
-	const size_t need = groups * nchunks * 32;
-	if (ctx->plist_cap < need) {
-		cudaFree(ctx->plist); ctx->plist = NULL; ctx->plist_cap = 0;
-		const size_t cap = need + need / 8 + 4096;
-		CUDA_TRY(cudaMalloc(&ctx->plist, cap * sizeof(uint)));
-		ctx->plist_cap = cap;
-	}
-	if (ctx->pcount_cap < n) {
-		cudaFree(ctx->pcount); ctx->pcount = NULL; ctx->pcount_cap = 0;
-		const size_t cap = (size_t)n + n / 8 + 4096;
-		CUDA_TRY(cudaMalloc(&ctx->pcount, cap * sizeof(ushort2)));
-		ctx->pcount_cap = cap;
-	}
-	coop_list_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (const ushort4 *)info, (const float4 *)pos,
-		hash, cell_start, neibs_list, ctx->plist, ctx->pcount, n, nchunks);
-	KERNEL_TRY();
-	ctx->coop_src = neibs_list; ctx->coop_n = n;
-	return B200SPH_OK;
-}
-
-template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
-__global__ void __launch_bounds__(COOP_BLOCK, COOP_MIN_BLOCKS)
-forces_coop_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray, const float4 *__restrict__ velArray,
-	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
-	const uint *__restrict__ plist, const ushort2 *__restrict__ pcount, const uint nchunks,
-	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
-	const uint fromParticle, const uint toParticle, const uint cflOffset)
-{
-	__shared__ float4 s_celloff[32];
-	if (threadIdx.x < 27) s_celloff[threadIdx.x] = cell_offset(P, threadIdx.x);
-	PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
-	EosConsts E;
-	E.gamma = P.gammacoeff[0]; E.sspow = P.sspowercoeff[0]; E.b = P.bcoeff[0]; E.ss = P.sscoeff[0]; E.rho0 = P.rho0[0];
-	uint a_off = smem_u32(s_celloff);
-#if B200_HOIST
-	__shared__ Pinned s_pin;
-	if (threadIdx.x == 0) {
-		float *v = s_pin.v;
-		v[0] = k.inv_h; v[1] = k.fc; v[2] = k.R2; v[3] = k.h_alpha; v[4] = k.eps; v[5] = k.g0; v[6] = k.g1; v[7] = k.g2;
-		v[8] = k.diff; v[9] = k.grav_scale; v[10] = E.gamma; v[11] = E.sspow; v[12] = E.b; v[13] = E.ss; v[14] = E.rho0;
-		v[15] = __uint_as_float(a_off); v[16] = k.h;
-	}
-	__syncthreads();
-	{
-		const uint a = smem_u32(s_pin.v);
-		auto ld = [&](int i) { float x; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a + 4u * i)); return x; };
-		k.inv_h = ld(0); k.fc = ld(1); k.R2 = ld(2); k.h_alpha = ld(3); k.eps = ld(4); k.g0 = ld(5); k.g1 = ld(6); k.g2 = ld(7);
-		k.diff = ld(8); k.grav_scale = ld(9); E.gamma = ld(10); E.sspow = ld(11); E.b = ld(12); E.ss = ld(13); E.rho0 = ld(14);
-		a_off = __float_as_uint(ld(15)); k.h = ld(16);
-	}
-#else
-	__syncthreads();
-#endif
-
-	const uint lane = threadIdx.x & 31u, sub = lane % COOP_LPP;
-	// warp w handles particles [COOP_PPW*w, COOP_PPW*(w+1)) so that its list lines are the ones coop_slot laid out
-	const uint warp = fromParticle / COOP_PPW + blockIdx.x * (COOP_BLOCK / 32) + (threadIdx.x >> 5);
-	const uint index = warp * COOP_PPW + lane / COOP_LPP;
-	bool active = index >= fromParticle && index < toParticle;
-	ushort4 info = make_ushort4(0, 0, 0, 0);
-	float4 pos = make_float4(0.f, 0.f, 0.f, 0.f), vel = pos;
-	int type = -1;
-	uint cf = 0, ntot = 0;
-	if (active) {
-		info = infoArray[index];
-		type = ptype_of(info);
-		pos = posArray[index];
-		active = (type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000);
-	}
-	Central c;
-	c.pos = pos; c.vel = vel; c.rho = 1.f; c.p_precalc = 0.f; c.sspeed = 0.f; c.fnum = 0; c.momentum = false; c.xsph = false;
-	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-	if (active) {
-		vel = velArray[index];
-		const ushort2 cnt = pcount[index];
-		cf = cnt.x;
-		// fluid<-fluid, fluid<-boundary (DYN boundary neighbours interact like fluid ones, forces_kernel.def:3717-3726);
-		// boundary<-fluid: density always, momentum only with force feedback (:3634-3667)
-		ntot = type == PT_FLUID ? (uint)cnt.x + cnt.y : (uint)cnt.x;
-		const float4 e = MULTIFLUID ? eos_from_density(P, vel.w, fluid_num_of(info)) : eos_from_density(E, vel.w);
-		c.pos = pos; c.vel = vel;
-		c.p_precalc = e.x; c.sspeed = e.y; c.rho = e.z;
-		c.fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
-		c.momentum = type == PT_FLUID || (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
-	}
-
-	// lane `sub` takes entries sub, sub + LPP, ...; the next chunk's entry is loaded one step ahead
-	const uint *pl = plist + (size_t)warp * nchunks * 32u + lane;
-	const uint steps = (ntot + COOP_LPP - 1) / COOP_LPP;
-	uint e_next = steps ? __ldg(pl) : 0u;
-	for (uint s = 0; s < steps; ++s) {
-		const uint e = e_next;
-		if (s + 1 < steps) e_next = __ldg(pl + (size_t)(s + 1) * 32u);
-		const uint kk = s * COOP_LPP + sub;
-		if (kk >= ntot) continue;
-		const uint j = e & COOP_INDEX_MASK;
-		const float4 o = lds_f4(a_off + (e >> COOP_INDEX_BITS) * 16u);
-		const float4 np = __ldg(posArray + j), nv = __ldg(velArray + j);
-		const float4 ne = MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
-		const float rx = (c.pos.x - o.x) - np.x, ry = (c.pos.y - o.y) - np.y, rz = (c.pos.z - o.z) - np.z;
-		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
-		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
-		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
-		pair_interaction<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, kk < cf, acc);
-	}
-	// combine the partial sums of the lane group
-#pragma unroll
-	for (int o = COOP_LPP / 2; o > 0; o >>= 1) {
-		acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-		acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-	}
-	if (active && sub == 0) {
-		const uint cellHash = (bo.bodies || P.numplanes) ? particleHash[index] & CELLTYPE_BITMASK : 0u;
-		const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
-		forces[index] = acc;
-		// one CFL slot per 128 particles like the reference's per-block maxima (slots are zeroed by the launcher;
-		// non-negative floats order like their bit patterns)
-		if (cfl && cfl_term > 0.0f)
-			atomicMax(reinterpret_cast<unsigned int *>(cfl + cflOffset + (index - fromParticle) / BLOCK_FORCES), __float_as_uint(cfl_term));
-	}
-}
-
-// ---------------------------------------------------------------------------
-// staged kernel: one CTA per tile, neighbourhood in shared memory via TMA bulk copies
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint count)
-{ asm volatile("mbarrier.init.shared.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint parity)
-{
-	uint ok;
-	asm volatile("{\n\t.reg .pred P_OUT;\n\tmbarrier.try_wait.parity.shared::cta.b64 P_OUT, [%1], %2;\n\tselp.b32 %0, 1, 0, P_OUT;\n\t}"
-		: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-	return ok != 0;
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template<int TP, int TS>
-struct TileSmem {
-	float4 pos[TS];
-	float4 vel[TS];
-	float4 aux[TS];
-	uint cellbase[27 * TP];
-	float4 celloff[27];
-	uint row_off[9], row_start[9];
-	int rowof[27];            // neighbour cell code -> neighbour row index
-	unsigned long long bar;
-};
-
-template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int TP, int TS, int PF>
-__global__ void __launch_bounds__(TP)
-forces_tile_kernel(const __grid_constant__ DevParams P, const Tile *__restrict__ tiles,
-	const float4 *__restrict__ posArray, const float4 *__restrict__ velArray, const float4 *__restrict__ aux,
-	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
-	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
-	float4 *__restrict__ forces, float *__restrict__ cfl, const BodyOut bo,
-	const uint fromParticle, const uint toParticle, const uint cflOffset)
-{
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	typedef TileSmem<TP, TS> Smem;
-	Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-	const Tile &T = tiles[blockIdx.x];
-	const uint tid = threadIdx.x;
-	uint64_t *bar = reinterpret_cast<uint64_t *>(&S.bar);
-
-	if (tid == 0) {
-		mbar_init(bar, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		uint off = 0;
-#pragma unroll
-		for (int r = 0; r < 9; ++r) { S.row_off[r] = off; S.row_start[r] = T.row_start[r]; off += T.row_count[r]; }
-	}
-	if (tid < 27) {
-		S.celloff[tid] = cell_offset(P, tid);
-		// cell code = (x+1) + 3(y+1) + 9(z+1); the row of a neighbour is chosen by its COORD2 / COORD3 offsets
-		const int d[3] = { (int)tid % 3 - 1, ((int)tid / 3) % 3 - 1, (int)tid / 9 - 1 };
-		const int d2 = P.coord[1] == 0 ? d[0] : (P.coord[1] == 1 ? d[1] : d[2]);
-		const int d3 = P.coord[2] == 0 ? d[0] : (P.coord[2] == 1 ? d[1] : d[2]);
-		S.rowof[tid] = (d2 + 1) + 3 * (d3 + 1);
-	}
-	__syncthreads();
-	if (tid == 0) {
-		uint total = 0;
-#pragma unroll
-		for (int r = 0; r < 9; ++r) total += T.row_count[r];
-		mbar_expect_tx(bar, total * 48u);
-#pragma unroll
-		for (int r = 0; r < 9; ++r) {
-			const uint cnt = T.row_count[r];
-			if (cnt) {
-				const uint off = S.row_off[r], src = T.row_start[r];
-				bulk_g2s(&S.pos[off], posArray + src, cnt * 16u, bar);
-				bulk_g2s(&S.vel[off], velArray + src, cnt * 16u, bar);
-				bulk_g2s(&S.aux[off], aux + src, cnt * 16u, bar);
-			}
-		}
-	}
-
-	const PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
-	auto fetch = [&](const uint slot, float4 &np, float4 &nv, float4 &ne) {
-		np = S.pos[slot]; nv = S.vel[slot]; ne = S.aux[slot];
-	};
-	bool staged = false;
-	float cfl_term = 0.0f;
-	uint cfl_slot = 0xFFFFFFFFu;
-	const uint tend = T.first + T.count;
-	for (uint index = T.first + tid; index < tend; index += TP) {
-		if (index < fromParticle || index >= toParticle) continue;
-		const ushort4 info = infoArray[index];
-		const int type = ptype_of(info);
-		const float4 pos = posArray[index];
-		if (!((type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000))) continue;
-		const float4 vel = velArray[index];
-		const float4 e = aux[index];
-		// shared-memory slot of the first particle of each of the 27 neighbouring cells (while the copies fly)
-		uint *my_base = S.cellbase + tid;
-		const uint cellHash = particleHash[index] & CELLTYPE_BITMASK;
-		load_cell_starts(P, (int)cellHash, cellStart, my_base, TP);
-#pragma unroll
-		for (int cell = 0; cell < 27; ++cell) {
-			const int r = S.rowof[cell];
-			const uint cs = my_base[cell * TP];
-			my_base[cell * TP] = cs - S.row_start[r] + S.row_off[r];   // meaningless (and unused) for empty cells
-		}
-		if (!staged) { while (!mbar_try_wait(bar, 0)) { } staged = true; }
-		auto lut = [&](const uint cell, uint &base, float &ox, float &oy, float &oz) {
-			base = my_base[cell * TP];
-			const float4 o = S.celloff[cell];
-			ox = o.x; oy = o.y; oz = o.z;
-		};
-		ListGeom L;
-		L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos;
-		const float t = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, true>(P, k, index, info, type, pos, vel, e,
-			cellHash, bo, lut, L, fetch, forces);
-		cfl_term = fmaxf(cfl_term, t);
-		cfl_slot = (index - fromParticle) / BLOCK_FORCES;
-	}
-	// every thread must have observed the copies before the CTA (and its shared memory) may retire
-	if (!staged) { while (!mbar_try_wait(bar, 0)) { } }
-
-	// CFL: one slot per 128 particles like the reference's per-block maxima; tiles do not align with those blocks,
-	// so non-negative floats are max-combined with integer atomics (slots are zeroed by the launcher)
-	if (cfl && cfl_slot != 0xFFFFFFFFu)
-		atomicMax(reinterpret_cast<unsigned int *>(cfl + cflOffset + cfl_slot), __float_as_uint(cfl_term));
-}
-
-// ---------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------
-typedef void (*gather_kernel_t)(const DevParams, const float4 *, const float4 *, const ushort4 *, const uint *,
+typedef void (*gather_kernel_t)(const DevParams, const PosVel *, const ushort4 *, const uint *,
 	const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
-typedef void (*coop_kernel_t)(const DevParams, const float4 *, const float4 *, const ushort4 *, const uint *,
-	const uint *, const ushort2 *, const uint, float4 *, float *, const BodyOut, const uint, const uint, const uint);
-typedef void (*tile_kernel_t)(const DevParams, const Tile *, const float4 *, const float4 *, const float4 *, const ushort4 *,
-	const uint *, const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
 
 template<int RHODIFF>
-static void pick_kernels(bool artvisc, bool laminar, bool multi, int cfg, gather_kernel_t *g /* [wide] */, coop_kernel_t *cpk, tile_kernel_t *t, size_t *smem)
+static void pick_kernels(bool artvisc, bool laminar, bool multi, gather_kernel_t *g /* [wide] */)
 {
-	// the staged kernel's tile shape (TILE_P threads, TILE_S staged slots: common.cuh) is the best of the five measured
-#define PICK(A, L, M) do { g[0] = forces_gather_kernel<RHODIFF, A, L, M, false>; g[1] = forces_gather_kernel<RHODIFF, A, L, M, true>; \
-	*cpk = forces_coop_kernel<RHODIFF, A, L, M>; \
-	(void)cfg; *t = forces_tile_kernel<RHODIFF, A, L, M, TILE_P, TILE_S, 4>; *smem = sizeof(TileSmem<TILE_P, TILE_S>); \
-} while (0)
+#define PICK(A, L, M) do { g[0] = forces_gather_kernel<RHODIFF, A, L, M, false>; g[1] = forces_gather_kernel<RHODIFF, A, L, M, true>; } while (0)
 	if (multi) {
 		if (artvisc) { if (laminar) PICK(true, true, true); else PICK(true, false, true); }
 		else { if (laminar) PICK(false, true, true); else PICK(false, false, true); }
@@ -760,8 +433,8 @@ extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *ar
 	return forces_impl(ctx, args, NULL, num_cfl_blocks);
 }
 
-// forces of [from, to) followed by the integration of the same particles (b200sph_forces_ex + b200sph_euler_ex); the
-// default gather kernel does both in one launch (fused epilogue), every other kernel selection runs the two launches
+// forces of [from, to) followed by the integration of the same particles (b200sph_forces_ex + b200sph_euler_ex): one
+// launch (fused epilogue) unless ENABLE_XSPH is on, whose mean velocity the integration reads from the buffer
 extern "C" int b200sph_forces_euler(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *eul,
 	uint32_t *num_cfl_blocks)
 {
@@ -780,20 +453,34 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 	void *rb_forces = args->rb_forces, *rb_torques = args->rb_torques;
 	const uint32_t num_particles = args->num_particles, from = args->from_particle, to = args->to_particle, cfl_offset = args->cfl_offset;
 	BodyOut bo;
-	bo.bodies = NULL; bo.rb_forces = (float4 *)rb_forces; bo.rb_torques = (float4 *)rb_torques; bo.xsph = NULL;
-	bo.eul_step = 0; bo.eul_dt = 0.0f; bo.eul_state = NULL; bo.eul_old_pos = bo.eul_old_vel = NULL;
-	bo.eul_new_pos = bo.eul_new_vel = NULL; bo.eul_bodies = NULL;
+	memset(&bo, 0, sizeof(bo));
+	bo.rb_forces = (float4 *)rb_forces; bo.rb_torques = (float4 *)rb_torques;
 	if (eul) {
 		if (eul->step != 1 && eul->step != 2) { b200_set_error("unsupported predcorr timestep %d", eul->step); return B200SPH_EINVAL; }
-		if (args && args->to_particle > args->from_particle) {
+		if (args->to_particle > args->from_particle) {
 			if (!eul->old_pos || !eul->old_vel || !eul->new_pos || !eul->new_vel) { b200_set_error("forces_euler: null buffer"); return B200SPH_EINVAL; }
-			if (eul->new_pos == args->pos || eul->new_vel == args->vel) {
+			// [new + from, new + to) against [gathered, gathered + num_particles): any overlap, not just equal bases
+			auto overlaps = [&](const void *w, size_t wsz, const void *r, size_t rsz) {
+				if (!w || !r) return false;
+				const char *w0 = (const char *)w + (size_t)args->from_particle * wsz, *w1 = (const char *)w + (size_t)args->to_particle * wsz;
+				const char *r0 = (const char *)r, *r1 = r0 + (size_t)args->num_particles * rsz;
+				return w0 < r1 && r0 < w1;
+			};
+			// with caller-provided records the pair loop gathers from THEM, and pos / vel may be integrated in place
+			const bool own_records = args->packed != NULL;
+			if ((!own_records && (overlaps(eul->new_pos, 16, args->pos, 16) || overlaps(eul->new_pos, 16, args->vel, 16) ||
+					overlaps(eul->new_vel, 16, args->pos, 16) || overlaps(eul->new_vel, 16, args->vel, 16))) ||
+				overlaps(eul->new_pos, 16, args->packed, 32) || overlaps(eul->new_vel, 16, args->packed, 32) ||
+				overlaps(eul->new_packed, 32, args->packed, 32) || overlaps(eul->new_packed, 32, args->pos, 16) ||
+				overlaps(eul->new_packed, 32, args->vel, 16)) {
 				b200_set_error("forces_euler: the integrated state must not overwrite the state the pair loop reads"); return B200SPH_EINVAL; }
+			if ((uintptr_t)eul->new_packed & 31u) { b200_set_error("forces_euler: new_packed must be 32-byte aligned"); return B200SPH_EINVAL; }
 		}
 	}
 	if (rb_forces) {
 		if (!rb_torques) { b200_set_error("forces: rb_forces without rb_torques"); return B200SPH_EINVAL; }
-		if (!ctx->have_bodies) { b200_set_error("forces: body output requested before setrbcg/setrbstart"); return B200SPH_EINVAL; }
+		if ((ctx->bodies_set & (BODY_SET_CG_FORCES | BODY_SET_START)) != (BODY_SET_CG_FORCES | BODY_SET_START)) {
+			b200_set_error("forces: body output requested before setrbcg/setrbstart"); return B200SPH_EINVAL; }
 		bo.bodies = ctx->d_bodies;
 	}
 	const bool xsph = (ctx->hp.simflags & B200SPH_ENABLE_XSPH) != 0;
@@ -806,34 +493,40 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 	if (to <= from) return B200SPH_OK;
 	if (!pos || !vel || !info || !hash || !cell_start || !neibs_list || !forces) { b200_set_error("forces: null buffer"); return B200SPH_EINVAL; }
 	if (to > num_particles) { b200_set_error("forces: range end beyond numParticles"); return B200SPH_EINVAL; }
+	if ((uintptr_t)args->packed & 31u) { b200_set_error("forces: packed records must be 32-byte aligned"); return B200SPH_EINVAL; }
 	// CFL blocks: grid of the reference rounded to a multiple of 4 (forces.cu:741-744) so that the array can be
 	// reduced as float4
 	uint nblocks = div_up(to - from, BLOCK_FORCES);
 	nblocks = (nblocks + 3) / 4 * 4;
 	const DevParams &d = ctx->dp;
 	const bool artvisc = d.turbmodel == B200SPH_TURB_ARTIFICIAL, laminar = !d.inviscid, multi = d.numFluids > 1;
-	gather_kernel_t gks[2]; coop_kernel_t ck; tile_kernel_t tk; size_t smem = 0;
-	const int cfg = ctx->tile_cfg;
-	// options served by the general (run-time switched) variant of the gather kernel only
+	// options served by the general (run-time switched) variant of the kernel only
 	const bool general = brezzi || xsph || (laminar && d.viscmodel != B200SPH_VISCMODEL_MORRIS);
 	DevParams dp_launch = ctx->dp;
 	dp_launch.cmd_dt = args->dt; dp_launch.cmd_step = args->step;
 	dp_launch.dev_state = args->dt_from_device ? ctx->d_step : NULL;
-	// integration: fused into the gather kernel's epilogue, or a second launch behind the other kernels / with XSPH
-	// (whose mean velocity the integration reads from the buffer)
-	if (ctx->tiles_state == 1) {
-		CUDA_TRY(cudaEventSynchronize(ctx->tiles_event));
-		ctx->num_tiles = ctx->h_tile_info[0];
-		ctx->tiles_state = ctx->h_tile_info[1] ? 0 : 2;      // overflow: a tile does not fit in shared memory
+	// neighbour records: the caller's, or an interleaved copy of pos / vel made now (every neighbour of [from, to) can
+	// be anywhere in [0, num_particles))
+	const PosVel *pv = (const PosVel *)args->packed;
+	if (!pv) {
+		PosVel *scratch = NULL;
+		{ const int rc = b200_packed_scratch(ctx, 0, num_particles, &scratch); if (rc) return rc; }
+		pack_state_kernel<<<div_up(num_particles, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>((const float4 *)pos, (const float4 *)vel,
+			scratch, 0, num_particles);
+		KERNEL_TRY();
+		pv = scratch;
 	}
-	const bool use_tiles = !general && ctx->tiles_state == 2 && ctx->tiles_cellstart == cell_start && to <= ctx->tiles_range_end && ctx->num_tiles > 0;
-	const bool use_coop = !general && !use_tiles && ctx->use_coop && num_particles <= COOP_INDEX_MASK;
-	const bool fuse = eul && !xsph && !use_tiles && !use_coop;
+	// integration: fused into the kernel's epilogue, or a second launch with XSPH (whose mean velocity the integration
+	// reads from the buffer)
+	const bool fuse = eul && !xsph;
 	if (fuse) {
 		bo.eul_step = eul->step; bo.eul_dt = eul->dt; bo.eul_state = eul->dt_from_device ? ctx->d_step : NULL;
-		bo.eul_old_pos = (const float4 *)eul->old_pos; bo.eul_old_vel = (const float4 *)eul->old_vel;
+		const bool old_is_current = eul->old_pos == args->pos && eul->old_vel == args->vel;
+		bo.eul_old_pos = old_is_current ? NULL : (const float4 *)eul->old_pos;
+		bo.eul_old_vel = old_is_current ? NULL : (const float4 *)eul->old_vel;
 		bo.eul_new_pos = (float4 *)eul->new_pos; bo.eul_new_vel = (float4 *)eul->new_vel;
-		bo.eul_bodies = ctx->have_bodies ? ctx->d_bodies : NULL;
+		bo.eul_new_packed = (PosVel *)eul->new_packed;
+		{ const int rc = b200_euler_bodies(ctx, hash, &bo.eul_bodies); if (rc) return rc; }
 	}
 #if B200_HOST_ZEROCOPY
 	bo.eul_host_pos = fuse ? (float4 *)ctx->zc_host_pos : NULL;
@@ -841,61 +534,32 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 	if (ctx->zc_host_pos && !fuse) { b200_set_error("forces_euler: zero-copy mirror requested but the launch is not fused"); return B200SPH_EINVAL; }
 #endif
 	ctx->zc_host_pos = ctx->zc_host_vel = NULL;      // one launch only
-	auto integrate_unfused = [&]() -> int {
-		if (!eul || fuse) return B200SPH_OK;
-		const size_t o = (size_t)from * 16;
-		return b200sph_euler_ex(ctx, (const char *)eul->old_pos + o, (const char *)eul->old_vel + o, (const char *)info + (size_t)from * 8,
-			hash + from, (const char *)forces + o, args->xsph ? (const char *)args->xsph + o : NULL, (char *)eul->new_pos + o,
-			(char *)eul->new_vel + o, to - from, to - from, eul->dt, eul->step, eul->dt_from_device);
-	};
+	// 32-bit list offsets unless the list has 2^31 entries or more
+	const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
+	gather_kernel_t gks[2];
 	if (general) {
-		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
-		gather_kernel_t gk = wide ? forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, true>
-		                          : forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, false>;
-		{ const int rc = set_carveout(ctx, (const void *)gk); if (rc) return rc; }
-		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(dp_launch, (const float4 *)pos, (const float4 *)vel,
-			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
-		KERNEL_TRY();
-		if (num_cfl_blocks) *num_cfl_blocks = nblocks;
-		return integrate_unfused();
+		gks[0] = forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, false>;
+		gks[1] = forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, true>;
+	} else switch (d.densitydiffusiontype) {
+	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, gks); break;
+	case B200SPH_RHODIFF_COLAGROSSI: pick_kernels<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi, gks); break;
+	default: pick_kernels<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi, gks); break;
 	}
-	switch (d.densitydiffusiontype) {
-	case B200SPH_RHODIFF_FERRARI: pick_kernels<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
-	case B200SPH_RHODIFF_COLAGROSSI: pick_kernels<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
-	default: pick_kernels<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi, cfg, gks, &ck, &tk, &smem); break;
-	}
-	// tiles built by the last buildNeibsList for these cell ranges?
-	if (use_tiles) {
-		int rc = aux_precompute(ctx, (const float4 *)vel, (const ushort4 *)info, num_particles);
-		if (rc) return rc;
-		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
-		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CUDA_TRY(cudaFuncSetAttribute((const void *)tk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		tk<<<ctx->num_tiles, ctx->tile_p, smem, ctx->stream>>>(ctx->dp, ctx->tiles, (const float4 *)pos, (const float4 *)vel, ctx->aux,
-			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
-	} else if (use_coop) {
-		// private copy of the list: made by buildNeibsList for the list it wrote; a list from elsewhere is converted here
-		if (ctx->coop_src != (const void *)neibs_list || ctx->coop_n < to) {
-			int rc = b200_coop_list(ctx, info, pos, hash, cell_start, neibs_list, num_particles);
-			if (rc) return rc;
-		}
-		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
-		const uint first_warp = from / COOP_PPW, end_warp = div_up(to, COOP_PPW);
-		const uint grid = div_up(end_warp - first_warp, COOP_BLOCK / 32);
-		{ const int rc = set_carveout(ctx, (const void *)ck); if (rc) return rc; }
-		ck<<<grid, COOP_BLOCK, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel, (const ushort4 *)info, hash,
-			ctx->plist, ctx->pcount, div_up(d.neiblistsize, COOP_LPP), (float4 *)forces, cfl, bo, from, to, cfl_offset);
-	} else {
-		// 32-bit list offsets unless the list has 2^31 entries or more
-		const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
-		gather_kernel_t gk = gks[wide ? 1 : 0];
-		{ const int rc = set_carveout(ctx, (const void *)gk); if (rc) return rc; }
-		gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(ctx->dp, (const float4 *)pos, (const float4 *)vel,
-			(const ushort4 *)info, hash, cell_start, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset);
-	}
+	gather_kernel_t gk = gks[wide ? 1 : 0];
+	{ const int rc = set_carveout(ctx, (const void *)gk); if (rc) return rc; }
+	gk<<<nblocks, BLOCK_FORCES, 0, ctx->stream>>>(general ? dp_launch : ctx->dp, pv, (const ushort4 *)info, hash, cell_start, neibs_list,
+		(float4 *)forces, cfl, bo, from, to, cfl_offset);
 	KERNEL_TRY();
 	if (num_cfl_blocks) *num_cfl_blocks = nblocks;
-	return integrate_unfused();
+	if (eul && !fuse) {
+		const size_t o = (size_t)from * 16;
+		const int rc = b200sph_euler_ex(ctx, (const char *)eul->old_pos + o, (const char *)eul->old_vel + o, (const char *)info + (size_t)from * 8,
+			hash + from, (const char *)forces + o, args->xsph ? (const char *)args->xsph + o : NULL, (char *)eul->new_pos + o,
+			(char *)eul->new_vel + o, to - from, to - from, eul->dt, eul->step, eul->dt_from_device);
+		if (rc) return rc;
+		if (eul->new_packed) return b200sph_pack_state(ctx, eul->new_pos, eul->new_vel, eul->new_packed, from, to);
+	}
+	return B200SPH_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -986,19 +650,32 @@ extern "C" int b200sph_dt_from_cfl(const b200sph_ctx *ctx, float max_cfl, float 
 	return B200SPH_OK;
 }
 
-extern "C" int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl, uint32_t num_blocks, float *dt_out)
+static int dtreduce_impl(b200sph_ctx *ctx, const float *cfl, uint32_t num_blocks, const b200sph_params &hp, float *dt_out)
 {
-	CHECK_CTX(ctx);
-	(void)temp_cfl;
 	if (!cfl || !dt_out) { b200_set_error("dtreduce: null buffer"); return B200SPH_EINVAL; }
-	const b200sph_params &hp = ctx->hp;
 	max_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(cfl, num_blocks, ctx->d_scalar);
 	KERNEL_TRY();
 	CUDA_TRY(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-	const float dt = dt_from_cfl(hp, ctx->h_scalar[0]);
-	*dt_out = dt;
+	*dt_out = dt_from_cfl(hp, ctx->h_scalar[0]);
 	return B200SPH_OK;
+}
+
+extern "C" int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl, uint32_t num_blocks, float *dt_out)
+{
+	CHECK_CTX(ctx);
+	(void)temp_cfl;
+	return dtreduce_impl(ctx, cfl, num_blocks, ctx->hp, dt_out);
+}
+
+extern "C" int b200sph_dtreduce_ex(b200sph_ctx *ctx, const float *cfl, float *temp_cfl, uint32_t num_blocks,
+	float slength, float dtadaptfactor, float sspeed_cfl, float max_kinematic, float *dt_out)
+{
+	CHECK_CTX(ctx);
+	(void)temp_cfl;
+	b200sph_params hp = ctx->hp;
+	hp.slength = slength; hp.dtadaptfactor = dtadaptfactor; hp.max_sound_speed_cfl = sspeed_cfl; hp.max_kinvisc = max_kinematic;
+	return dtreduce_impl(ctx, cfl, num_blocks, hp, dt_out);
 }
 
 // ---------------------------------------------------------------------------

@@ -149,7 +149,7 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 
 	// experimental (B200_HOST_ZEROCOPY builds, B200SPH_HOST_ZEROCOPY=1): the corrector's epilogue writes state n+1 straight
 	// into the mapped host buffers, no download copies; only for fused launches and host pointers the device can address
-	bool zc = ctx->host_zerocopy && !xsph && !ctx->use_tiles && !ctx->use_coop;
+	bool zc = ctx->host_zerocopy && !xsph;
 	if (zc) {
 		cudaPointerAttributes pa, va;
 		zc = cudaPointerGetAttributes(&pa, a->host_pos) == cudaSuccess && cudaPointerGetAttributes(&va, a->host_vel) == cudaSuccess &&
@@ -167,6 +167,22 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		if (rc) return rc;
 	}
 
+	// neighbour records of the pair kernel (forces.cu): state n in the context's record buffer 0, interleaved stripe by
+	// stripe as the uploads land; n* in buffer 1, written by the predictor's epilogue
+	PosVel *pv_n = NULL, *pv_star = NULL;
+	rc = b200_packed_scratch(ctx, 0, n, &pv_n); if (rc) return rc;
+	rc = b200_packed_scratch(ctx, 1, n, &pv_star); if (rc) return rc;
+	uint32_t packed_upto = 0;                         // stripes [0, packed_upto) have their records
+	auto pack_upto = [&](uint32_t stripes) -> int {   // on P, after the caller made P wait for the uploads involved
+		if (stripes > ns) stripes = ns;
+		if (stripes <= packed_upto) return B200SPH_OK;
+		ctx->stream = P;
+		const int r = b200sph_pack_state(ctx, a->pos, a->vel, pv_n, B[packed_upto], B[stripes]);
+		packed_upto = stripes;
+		return r;
+	};
+	if (a->resident) { rc = pack_upto(ns); if (rc) return rc; }
+
 	b200sph_forces_args f;
 	memset(&f, 0, sizeof(f));
 	f.info = a->info; f.hash = a->hash; f.cell_start = a->cell_start; f.neibs_list = a->neibs_list;
@@ -181,13 +197,14 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		const size_t o16 = (size_t)s * 16;
 		ctx->stream = P;
 		if (!a->resident) CUDA_TRY(cudaStreamWaitEvent(P, ctx->up_ev[k + 1 < ns ? k + 1 : ns - 1], 0));
+		{ const int r = pack_upto(k + 2); if (r) return r; }
 		if (xsph) CUDA_TRY(cudaMemsetAsync((char *)a->xsph + o16, 0, (size_t)(e - s) * 16, P));
-		f.pos = a->pos; f.vel = a->vel; f.step = 1;
+		f.pos = a->pos; f.vel = a->vel; f.step = 1; f.packed = pv_n;
 		f.from_particle = s; f.to_particle = e; f.cfl_offset = offP;
 		// forces + euler step 1 (dt/2) of the stripe in one launch (fused epilogue)
 		b200sph_fused_euler_args eu;
 		eu.old_pos = a->pos; eu.old_vel = a->vel; eu.new_pos = a->pos_star; eu.new_vel = a->vel_star;
-		eu.dt = 0.0f; eu.step = 1; eu.dt_from_device = 1;
+		eu.dt = 0.0f; eu.step = 1; eu.dt_from_device = 1; eu.new_packed = pv_star;
 		int r = b200sph_forces_euler(ctx, &f, &eu, &nb);
 		if (r) return r;
 		offP += nb;
@@ -204,12 +221,12 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		ctx->stream = Q;
 		if (Q != P) CUDA_TRY(cudaStreamWaitEvent(Q, ctx->pred_ev[j + 1 < ns ? j + 1 : ns - 1], 0));
 		if (xsph) CUDA_TRY(cudaMemsetAsync((char *)a->xsph + o16, 0, (size_t)(e - s) * 16, Q));
-		f.pos = a->pos_star; f.vel = a->vel_star; f.step = 2;
+		f.pos = a->pos_star; f.vel = a->vel_star; f.step = 2; f.packed = pv_star;
 		f.from_particle = s; f.to_particle = e; f.cfl_offset = cflQ + offQ;
 		// forces + euler step 2 of the stripe, in place into the state-n buffers, in one launch
 		b200sph_fused_euler_args eu;
 		eu.old_pos = a->pos; eu.old_vel = a->vel; eu.new_pos = a->pos; eu.new_vel = a->vel;
-		eu.dt = 0.0f; eu.step = 2; eu.dt_from_device = 1;
+		eu.dt = 0.0f; eu.step = 2; eu.dt_from_device = 1; eu.new_packed = NULL;
 		if (zc) { ctx->zc_host_pos = a->host_pos; ctx->zc_host_vel = a->host_vel; }
 		int r = b200sph_forces_euler(ctx, &f, &eu, &nb);
 		ctx->zc_host_pos = ctx->zc_host_vel = NULL;

@@ -1,4 +1,4 @@
-// pair_physics.cuh — per-pair WCSPH physics shared by the two forces kernels (gather and staged).
+// pair_physics.cuh — per-pair WCSPH physics of the forces kernel.
 // Behavioural specification: GPUSPH src/cuda/forces_kernel.def (lines cited inline), sph_core.cu, phys_core.cu,
 // visc_kernel.cu, visc_avg.cu.
 #pragma once
@@ -81,21 +81,6 @@ __device__ __forceinline__ uint ld_neib(const ushort *p)
 #endif
 	return v;
 }
-// B200_GATHER_EVICT_LAST: neighbour records (pos / vel) are the data with reuse: keep them in L1 preferentially
-#ifndef B200_GATHER_EVICT_LAST
-#define B200_GATHER_EVICT_LAST 0
-#endif
-__device__ __forceinline__ float4 ld_gather(const float4 *p)
-{
-#if B200_GATHER_EVICT_LAST
-	float4 v;
-	asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-	return v;
-#else
-	return __ldg(p);
-#endif
-}
-
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -103,6 +88,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 // reference does (P() and soundSpeed() with __powf = ex2(y*lg2(x)), phys_core.cu:99-136; precalc_pressure
 // forces_kernel.def:419-429) but sharing the logarithm between the two powers. Trading ~12 ALU/MUFU instructions
 // for one scattered 128-bit gather is a win because the pair kernel is L1-wavefront bound, not issue bound.
+// e.w: the fluid number (as int bits) from the DevParams overload, the raw pressure from the EosConsts (single-fluid) one
 struct EosConsts { float gamma, sspow, b, ss, rho0; };      // of fluid 0, kept in registers by the single-fluid kernels
 __device__ __forceinline__ float4 eos_from_density(const EosConsts &E, const float rho_tilde)
 {
@@ -114,7 +100,7 @@ __device__ __forceinline__ float4 eos_from_density(const EosConsts &E, const flo
 	e.x = E.b * (pw - 1.0f) * rcp_approx(rho * rho);
 	e.y = E.ss * ex2_approx(E.sspow * lg);
 	e.z = rho;
-	e.w = __int_as_float(0);
+	e.w = E.b * (pw - 1.0f);        // single fluid: the raw pressure P() rides in the slot the fluid number takes otherwise
 	return e;
 }
 __device__ __forceinline__ float4 eos_from_density(const DevParams &P, const float rho_tilde, const int f)
@@ -130,6 +116,7 @@ __device__ __forceinline__ float4 eos_from_density(const DevParams &P, const flo
 struct Central {
 	float4 pos, vel;
 	float rho, p_precalc, sspeed;
+	float press;      // raw pressure P(rho~), Molteni-Colagrossi switch only
 	int fnum;
 	bool momentum;    // accumulate the momentum equation (false for DYN boundary particles without force feedback)
 	bool xsph;        // accumulate the XSPH mean velocity (fluid particle and ENABLE_XSPH; general variant only)
@@ -186,7 +173,9 @@ pair_interaction_x(const DevParams &P, const PairConsts &k, const Central &c, co
 			DrDt = fmaf(k.diff * mf, s, DrDt);
 		} else if (rhodiff == B200SPH_RHODIFF_COLAGROSSI) {         // :1916-1951
 			if (!MULTIFLUID || c.fnum == nfnum) {
-				const float Pi = c.p_precalc * (rho * rho), Pj = np_precalc * (nrho * nrho);
+				// P() of both particles as the reference compares them (:1925-1928), not rebuilt from P/rho^2: the test is
+				// a discontinuous switch, a borderline pair must fall on the reference's side
+				const float Pi = c.press, Pj = MULTIFLUID ? eos_pressure(P, nv.w, nfnum) : ne.w;
 				const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
 				if (!(fabsf(Pi - Pj) < fabsf(gdot * rho)))
 					DrDt -= k.diff * (MULTIFLUID ? P.sscoeff[c.fnum] : 1.0f) * (nrho * rcp_approx(rho) - 1.0f) * mf;
@@ -300,8 +289,9 @@ struct BodyOut {
 	int eul_step;
 	float eul_dt;                          // dt of the sub-step unless eul_state is given
 	const StepState *eul_state;            // device-resident dt record
-	const float4 *eul_old_pos, *eul_old_vel;
+	const float4 *eul_old_pos, *eul_old_vel;   // NULL: state n is the state the pair loop reads (predictor)
 	float4 *eul_new_pos, *eul_new_vel;
+	PosVel *eul_new_packed;                // the same state as neighbour records for the next force evaluation (NULL: none)
 	const BodyData *eul_bodies;            // rigid motion of moving bodies (NULL: none)
 #if B200_HOST_ZEROCOPY
 	float4 *eul_host_pos, *eul_host_vel;   // mapped pinned HOST mirrors of eul_new_* (NULL: none), see forces.cu

@@ -196,11 +196,15 @@ class ForcesEngine:
 
     def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, fromParticle: int,
                   toParticle: int, cflOffset: int = 0, compute_object_forces: bool = False,
-                  step: int = 0, dt: float = 0.0, dt_from_device: bool = False, euler=None) -> int:
+                  step: int = 0, dt: float = 0.0, dt_from_device: bool = False, euler=None, packed=None,
+                  new_packed=None) -> int:
         """step / dt = the command's integrator step and dt (src/GPUWorker.cc:1931-1932), read by BREZZI diffusion only;
         dt_from_device: take dt from the context's device-resident record instead.
         euler = (old: BufferList, new: BufferList, step, dt | None): also integrate the same particles
-        (AbstractIntegrationEngine::basicstep) right behind their forces; dt None = from the device record."""
+        (AbstractIntegrationEngine::basicstep) right behind their forces; dt None = from the device record.
+        packed / new_packed (torch uint8 tensors of 32 bytes per particle, or None): the neighbour records of the state
+        in bufread the caller vouches for / the records of the integrated state (b200sph_forces_args.packed,
+        b200sph_fused_euler_args.new_packed)."""
         nblocks = C.c_uint32()
         a = capi.ForcesArgs()
         a.pos, a.vel, a.info = bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO)
@@ -211,6 +215,7 @@ class ForcesEngine:
         a.xsph = bufwrite.ptr(BUFFER_XSPH, False)
         a.num_particles, a.from_particle, a.to_particle, a.cfl_offset = numParticles, fromParticle, toParticle, cflOffset
         a.dt, a.step, a.dt_from_device = dt, step, 1 if dt_from_device else 0
+        a.packed = packed.data_ptr() if packed is not None else 0
         if euler is None:
             capi.check(self.lib.b200sph_forces_ex(self.ctx.handle, C.byref(a), C.byref(nblocks)))
         else:
@@ -220,8 +225,14 @@ class ForcesEngine:
             e.old_pos, e.old_vel = old.ptr(BUFFER_POS), old.ptr(BUFFER_VEL)
             e.new_pos, e.new_vel = new.ptr(BUFFER_POS), new.ptr(BUFFER_VEL)
             e.step, e.dt, e.dt_from_device = estep, (0.0 if edt is None else edt), (1 if edt is None else 0)
+            e.new_packed = new_packed.data_ptr() if new_packed is not None else 0
             capi.check(self.lib.b200sph_forces_euler(self.ctx.handle, C.byref(a), C.byref(e), C.byref(nblocks)))
         return nblocks.value
+
+    def pack_state(self, bufread: BufferList, packed: torch.Tensor, fromParticle: int, toParticle: int) -> None:
+        """Interleave POS / VEL of [from, to) into the pair kernel's 32-byte neighbour records (b200sph_pack_state)."""
+        capi.check(self.lib.b200sph_pack_state(self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL),
+                                               packed.data_ptr(), fromParticle, toParticle))
 
     # ---- moving / force-feedback bodies (src/engine_forces.h:62-74) ----
     @staticmethod
@@ -306,7 +317,11 @@ class IntegrationEngine:
 
     # ---- moving bodies (src/engine_integration.h:54-68) ----
     def setrbcg(self, cgGridPos, cgPos, numbodies: int) -> None:
-        ForcesEngine.setrbcg(self, cgGridPos, cgPos, numbodies)
+        """The integration engine's OWN copy of the centres of gravity (the reference keeps two, see include/b200sph.h)."""
+        import numpy as np
+        g = np.ascontiguousarray(np.asarray(cgGridPos, dtype=np.int32).reshape(numbodies, 3))
+        c, cp = ForcesEngine._farr(cgPos, numbodies, 3)
+        capi.check(self.lib.b200sph_set_rbcg_euler(self.ctx.handle, g.ctypes.data_as(C.POINTER(C.c_int)), cp, numbodies))
 
     def _setf(self, fn, a, numbodies, k):
         arr, ptr = ForcesEngine._farr(a, numbodies, k)

@@ -112,11 +112,17 @@ public:
 		p.gravity[0] = pp->gravity.x; p.gravity[1] = pp->gravity.y; p.gravity[2] = pp->gravity.z;
 		p.artvisccoeff = pp->artvisccoeff;
 		p.epsartvisc = pp->epsartvisc;
-		p.max_sound_speed_cfl = max_ss * 1.1f;                    // src/GPUWorker.cc:3010-3011
+		// `m_max_sound_speed *= 1.1` (float *= double literal, src/GPUWorker.cc:3010-3011): one rounding, in double.
+		// Only the device-resident dt path reads these two; the reference-style dtreduce() forwards the caller's values.
+		p.max_sound_speed_cfl = (float)((double)max_ss * 1.1);
 		p.max_kinvisc = sp->rheologytype == INVISCID ? 0.0f : max_kin;
+		if (sp->viscmodel == MONAGHAN) p.max_kinvisc *= pp->monaghan_visc_coeff;        // src/GPUWorker.cc:2011-2023
+		else if (sp->viscmodel == ESPANOL_REVENGA) p.max_kinvisc *= 5;
 		p.dtadapt = (sp->simflags & ENABLE_DTADAPT) ? 1 : 0;
-		// ENABLE_DTADAPT, ENABLE_XSPH, ENABLE_PLANES, ENABLE_DEM have the reference's bit values (src/simflags.h:71-86)
-		p.simflags = (uint32_t)(sp->simflags & (ENABLE_DTADAPT | ENABLE_XSPH | ENABLE_PLANES | ENABLE_DEM));
+		// the WHOLE flag word (same bit values, src/simflags.h:62-160): b200sph_validate refuses what is not implemented
+		static_assert(ENABLE_MULTIFLUID == B200SPH_ENABLE_MULTIFLUID && ENABLE_REPACKING == B200SPH_ENABLE_REPACKING &&
+			ENABLE_MOVING_BODIES == B200SPH_ENABLE_MOVING_BODIES, "simflags bit values changed");
+		p.simflags = (uint32_t)sp->simflags;
 		p.epsxsph = pp->epsxsph;
 		p.monaghan_visc_coeff = pp->monaghan_visc_coeff;
 		for (uint32_t f = 0; f < p.num_fluids; ++f) p.visc2coeff[f] = pp->visc2coeff[f];
@@ -317,10 +323,12 @@ public:
 	uint getFmaxElements(const uint n) override { return b200sph_fmax_elements(n); }
 	uint getFmaxTempElements(const uint n) override { return b200sph_fmax_temp_elements(n); }
 
-	float dtreduce(float, float, float, float, BufferList const& bufread, BufferList& bufwrite, uint numBlocks, uint) override
+	float dtreduce(float slength, float dtadaptfactor, float sspeed_cfl, float max_kinematic, BufferList const& bufread,
+		BufferList& bufwrite, uint numBlocks, uint) override
 	{
 		float dt = FLT_MAX;
-		check(b200sph_dtreduce(m_c->get(), bufread.getData<BUFFER_CFL>(), bufwrite.getData<BUFFER_CFL_TEMP>(), numBlocks, &dt));
+		check(b200sph_dtreduce_ex(m_c->get(), bufread.getData<BUFFER_CFL>(), bufwrite.getData<BUFFER_CFL_TEMP>(), numBlocks,
+			slength, dtadaptfactor, sspeed_cfl, max_kinematic, &dt));
 		return dt;
 	}
 };
@@ -340,8 +348,9 @@ public:
 	void getconstants(PhysParams *pp) override { if (m_ref) m_ref->getconstants(pp); }
 
 	// moving bodies (src/cuda/euler.cu:76-95)
+	// the integration engine's OWN copy of the centres of gravity (cg(n) for the whole step, src/cuda/euler_kernel.def:488)
 	void setrbcg(const int3* g, const float3* c, int n) override
-	{ if (m_ref) m_ref->setrbcg(g, c, n); check(b200sph_set_rbcg(m_c->get(), (const int*)g, (const float*)c, n)); }
+	{ if (m_ref) m_ref->setrbcg(g, c, n); check(b200sph_set_rbcg_euler(m_c->get(), (const int*)g, (const float*)c, n)); }
 	void setrbtrans(const float3* t, int n) override
 	{ if (m_ref) m_ref->setrbtrans(t, n); check(b200sph_set_rbtrans(m_c->get(), (const float*)t, n)); }
 	void setrbsteprot(const float* r, int n) override

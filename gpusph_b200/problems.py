@@ -114,9 +114,18 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
         p.is_const_visc = 0                                     # IS_SINGLEFLUID is false (visc_spec.h:262)
     p.artvisccoeff = artvisccoeff
     p.epsartvisc = np.float32(0.01 * float(slength) * float(slength))   # ProblemCore.cc:160-161
-    p.max_sound_speed_cfl = np.float32(np.float32(c0) * 1.1)     # GPUWorker.cc:3010-3011
-    p.max_kinvisc = kinvisc if rheology != capi.RHEOLOGY_INVISCID else 0.0
+    # float *= double literal: the product is evaluated in double and rounded once (GPUWorker.cc:3010-3011)
+    p.max_sound_speed_cfl = np.float32(float(np.float32(c0)) * 1.1)
+    # max kinematic viscosity for the viscous dt limit, scaled like GPUWorker::dt_reduce does (GPUWorker.cc:2011-2023)
+    visc_for_dt = np.float32(kinvisc)
+    if viscmodel == capi.VISCMODEL_MONAGHAN:
+        visc_for_dt = np.float32(visc_for_dt * np.float32(10.0))
+    elif viscmodel == capi.VISCMODEL_ESPANOL_REVENGA:
+        visc_for_dt = np.float32(visc_for_dt * np.float32(5.0))
+    p.max_kinvisc = visc_for_dt if rheology != capi.RHEOLOGY_INVISCID else 0.0
     p.dtadapt = 1 if simflags & capi.ENABLE_DTADAPT else 0
+    if fluids:
+        simflags |= capi.ENABLE_MULTIFLUID                      # required with more than one fluid (ProblemCore.cc:108-112)
     p.simflags = simflags
     p.epsxsph = epsxsph                                         # physparams.h:409
     p.monaghan_visc_coeff = 10.0                                # 2(d+2), physparams.h:396

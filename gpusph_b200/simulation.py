@@ -67,6 +67,11 @@ class Worker:
         self.hash = torch.zeros(A, dtype=torch.int32, device=dev)            # uint32 bits
         self.partindex = torch.zeros(A, dtype=torch.int32, device=dev)
         self.forces_buf = f4()
+        # neighbour records of the pair kernel (32 B per particle: pos and vel interleaved, one 256-bit gather each): [0]
+        # mirrors state n, [1] the predicted state n*. Handed from launch to launch by the fused integration epilogue;
+        # re-made by a streaming pre-pass whenever something else touched the state (state_modified()).
+        self.packed = [torch.empty(A * 32, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._packed_valid = False
         ncells = self.params.num_cells
         self.cellstart = torch.empty(ncells, dtype=torch.int32, device=dev)
         self.cellend = torch.empty(ncells, dtype=torch.int32, device=dev)
@@ -110,6 +115,11 @@ class Worker:
         self.last_neibs_info = None
         self.total_interactions = 0       # sum over steps of list entries x 2 force evaluations
         self.launches = 0                 # hand-written kernels launched (CUB's sort passes not counted)
+
+    def state_modified(self) -> None:
+        """Tell the worker that POS / VEL of the current state were written behind its back (direct tensor writes): the
+        pair kernel's neighbour records are re-made before the next force evaluation."""
+        self._packed_valid = False
 
     def _sync_time(self) -> None:
         if self._stale:
@@ -162,6 +172,7 @@ class Worker:
     def build_neibs(self, _fenced: bool = False) -> None:
         if not _fenced:
             self.host_fence()
+        self._packed_valid = False
         n = self.numParticles
         cur, oth = self.cur, 1 - self.cur
         s = self.state(cur)
@@ -194,6 +205,7 @@ class Worker:
         VEL of step n, writes the filtered VEL into the scratch state, and the two VEL buffers are swapped."""
         if self.iterations == 0:
             return
+        self._packed_valid = False
         cur, oth = self.cur, 1 - self.cur
         for eng, freq in self.filters:
             if self.iterations % freq:
@@ -207,6 +219,7 @@ class Worker:
     def postprocess(self) -> None:
         """TESTPOINTS post-processing before a write (src/GPUWorker.cc:2545-2580): in place on the current state."""
         s = self.state(self.cur)
+        self._packed_valid = False
         self.postproc.process(s, s, self.numParticles, self.particleRangeEnd)
         self.launches += 1
 
@@ -235,16 +248,21 @@ class Worker:
         cur, oth = self.cur, 1 - self.cur
         rd, wr = self.state(cur), self.state(oth)
         if self.device_dt:
+            fused = self.fused and n == end
+            if fused and not self._packed_valid:
+                self.forces.pack_state(rd, self.packed[0], 0, n)
+                self.launches += 1
             if self.graphs:
                 self._step_graph(cur, n, end)
             else:
                 self._enqueue_step(rd, wr, n, end)
-            fused = self.fused and n == end
+            self._packed_valid = fused        # the corrector's epilogue left the records of state n+1 in packed[0]
             self.launches += (2 * 2 if fused else 2 * 3) + 1
             self._stale = True
             if fused:
                 oth = cur                 # state n+1 is in the buffers state n was in
         else:
+            self._packed_valid = False
             dt = self._dt
             # predictor: forces(n) -> euler step 1 with dt/2 writes n*
             dt1 = self._forces(cur, 1, dt / 2)
@@ -275,8 +293,11 @@ class Worker:
             if self.xsph is not None:
                 self.xsph.zero_()
             if fused:
+                # gathers from the records of the state being evaluated; the epilogue writes the records of the state
+                # it integrates: n* (predictor) into packed[1], n+1 (corrector) back into packed[0]
                 nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True,
-                                                euler=(rd, wr if which == 1 else rd, which, None))
+                                                euler=(rd, wr if which == 1 else rd, which, None),
+                                                packed=self.packed[which - 1], new_packed=self.packed[2 - which])
                 self.forces.dtreduce_async(st, nblocks, which)
             else:
                 nblocks = self.forces.basicstep(st, st, n, 0, end, 0, step=which, dt_from_device=True)
@@ -392,6 +413,7 @@ class Worker:
         a.resident = 1 if rebuild else 0
         capi.check(lib.b200sph_step_host(ctx.handle, C.byref(a)))
         self._host_pending = True
+        self._packed_valid = False
         self.launches += 2 * len(stripes) * 2 + 4
         self._stale = True
         self.iterations += 1              # state n+1 is in the SAME buffers: self.cur does not flip

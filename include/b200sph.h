@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200SPH_ABI_VERSION 2
+#define B200SPH_ABI_VERSION 3
 
 /* error codes */
 #define B200SPH_OK        0
@@ -67,12 +67,24 @@ enum { B200SPH_COMPVISC_KINEMATIC = 0, B200SPH_COMPVISC_DYNAMIC = 1 };
 enum { B200SPH_VISCMODEL_MORRIS = 0, B200SPH_VISCMODEL_MONAGHAN = 1, B200SPH_VISCMODEL_ESPANOL_REVENGA = 2 };
 enum { B200SPH_AVG_ARITHMETIC = 0, B200SPH_AVG_HARMONIC = 1, B200SPH_AVG_GEOMETRIC = 2 };
 
-/* simulation flags honoured by these engines; numeric values are the reference's (src/simflags.h:71-83) so that
- * SimParams::simflags can be passed through (other bits are ignored or rejected by b200sph_validate) */
-#define B200SPH_ENABLE_DTADAPT 1u
-#define B200SPH_ENABLE_XSPH    2u
-#define B200SPH_ENABLE_PLANES  4u
-#define B200SPH_ENABLE_DEM     8u
+/* simulation flags; numeric values are the reference's (src/simflags.h:62-160) so that the WHOLE of SimParams::simflags
+ * is passed through. b200sph_validate refuses (B200SPH_EUNSUP) every bit outside B200SPH_SUPPORTED_SIMFLAGS: nothing is
+ * silently ignored. ENABLE_REPACKING only makes the reference's `--repack` run mode available (src/main.cc:357); that
+ * run mode itself is refused by the adapter (RunMode REPACK), the flag has no effect on a simulation. */
+#define B200SPH_ENABLE_DTADAPT          (1u << 0)
+#define B200SPH_ENABLE_XSPH             (1u << 1)
+#define B200SPH_ENABLE_PLANES           (1u << 2)
+#define B200SPH_ENABLE_DEM              (1u << 3)
+#define B200SPH_ENABLE_MOVING_BODIES    (1u << 4)
+#define B200SPH_ENABLE_INLET_OUTLET     (1u << 5)
+#define B200SPH_ENABLE_WATER_DEPTH      (1u << 6)
+#define B200SPH_ENABLE_DENSITY_SUM      (1u << 7)
+#define B200SPH_ENABLE_GAMMA_QUADRATURE (1u << 8)
+#define B200SPH_ENABLE_REPACKING        (1u << 9)
+#define B200SPH_ENABLE_INTERNAL_ENERGY  (1u << 10)
+#define B200SPH_ENABLE_MULTIFLUID       (1u << 11)
+#define B200SPH_SUPPORTED_SIMFLAGS (B200SPH_ENABLE_DTADAPT | B200SPH_ENABLE_XSPH | B200SPH_ENABLE_PLANES | \
+	B200SPH_ENABLE_MOVING_BODIES | B200SPH_ENABLE_REPACKING | B200SPH_ENABLE_MULTIFLUID)
 
 #define B200SPH_MAX_FLUIDS 4
 #define B200SPH_MAX_PLANES 8   /* src/particledefine.h:325 */
@@ -130,7 +142,7 @@ typedef struct b200sph_params {
 	float    max_kinvisc;          /* max kinematic viscosity (0 if inviscid) */
 	uint32_t dtadapt;              /* ENABLE_DTADAPT */
 	/* ---- ABI version 2 ---- */
-	uint32_t simflags;             /* SimParams::simflags; B200SPH_ENABLE_XSPH and B200SPH_ENABLE_PLANES are honoured */
+	uint32_t simflags;             /* the whole of SimParams::simflags (see B200SPH_SUPPORTED_SIMFLAGS) */
 	float    epsxsph;              /* PhysParams::epsxsph (src/cuda/euler.cu:56) */
 	float    monaghan_visc_coeff;  /* PhysParams::monaghan_visc_coeff = 2(d+2) (src/cuda/forces.cu:334) */
 	float    visc2coeff[B200SPH_MAX_FLUIDS]; /* bulk viscosity, ESPANOL_REVENGA only (src/cuda/forces.cu:328) */
@@ -249,9 +261,14 @@ int b200sph_forces(b200sph_ctx *ctx, const void *pos, const void *vel, const voi
 int b200sph_eos_probe(b200sph_ctx *ctx, const void *vel, const void *info, void *out, uint32_t num_particles);
 
 /* AbstractForcesEngine::dtreduce (src/engine_forces.h:163; src/cuda/forces.cu:557-607).
- * Synchronises the stream and returns dt on the host, like the reference. */
+ * Synchronises the stream and returns dt on the host, like the reference. b200sph_dtreduce uses the values given at
+ * context creation; b200sph_dtreduce_ex takes the four arguments the reference passes on every call (GPUWorker updates
+ * max_kinematic at run time, src/GPUWorker.cc:2642; sspeed_cfl is the product 1.1 * max c0 evaluated in double and
+ * rounded once, src/GPUWorker.cc:3011). */
 int b200sph_dtreduce(b200sph_ctx *ctx, const float *cfl, float *temp_cfl,
 	uint32_t num_blocks, float *dt_out);
+int b200sph_dtreduce_ex(b200sph_ctx *ctx, const float *cfl, float *temp_cfl, uint32_t num_blocks,
+	float slength, float dtadaptfactor, float sspeed_cfl, float max_kinematic, float *dt_out);
 
 /* The two halves of dtreduce for callers that combine CFL maxima across devices ON the device (multi-GPU: one
  * NCCL all-reduce(MAX) on `max_out` instead of a host loop over per-device dt, src/GPUSPH.cc:650-657):
@@ -266,7 +283,13 @@ int b200sph_dt_from_cfl(const b200sph_ctx *ctx, float max_cfl, float *dt_out);
  * (src/engine_integration.h:54-68; src/cuda/euler.cu:76-95). Host arrays, at most B200SPH_MAX_BODIES bodies.
  * cg_grid_pos: int[3*n] cell of each centre of gravity, cg_pos: float[3*n] in-cell coordinate. */
 #define B200SPH_MAX_BODIES 16
+/* The centres of gravity are kept TWICE, like the reference's two __constant__ copies (src/cuda/forces_kernel.cu:81-83,
+ * src/cuda/euler_kernel.cu:45-50): b200sph_set_rbcg is AbstractForcesEngine::setrbcg (torque arm in finalize),
+ * b200sph_set_rbcg_euler is AbstractIntegrationEngine::setrbcg (centre of the rigid motion). The reference's integrator
+ * moves the forces copy to cg(n+1) in the middle of a step while the integration keeps cg(n)
+ * (src/integrators/PredictorCorrectorIntegrator.cc:332,556-587). */
 int b200sph_set_rbcg(b200sph_ctx *ctx, const int *cg_grid_pos, const float *cg_pos, int numbodies);
+int b200sph_set_rbcg_euler(b200sph_ctx *ctx, const int *cg_grid_pos, const float *cg_pos, int numbodies);
 int b200sph_set_rbstart(b200sph_ctx *ctx, const int *rbfirstindex, int numbodies);
 int b200sph_set_rbtrans(b200sph_ctx *ctx, const float *trans, int numbodies);
 int b200sph_set_rbsteprot(b200sph_ctx *ctx, const float *rot /* 9 per body */, int numbodies);
@@ -304,6 +327,12 @@ typedef struct b200sph_forces_args {
 	float dt;
 	int step;
 	int dt_from_device;
+	/* ABI 3. The pair kernel gathers each neighbour as one 32-byte record {pos.xyz, mass, vel.xyz, rho~} (one 256-bit
+	 * load). packed == NULL (reference-style calls): the library interleaves pos / vel of [0, num_particles) into its
+	 * own scratch in a streaming pre-pass before the launch. packed != NULL: device buffer of 32 bytes x num_particles,
+	 * 32-byte aligned, that the CALLER vouches holds exactly the state in pos / vel (written by b200sph_pack_state or
+	 * by b200sph_forces_euler's new_packed); the pre-pass is skipped. */
+	const void *packed;
 } b200sph_forces_args;
 int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks);
 
@@ -313,16 +342,25 @@ int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_
  * With the default pair kernel the integration runs in the kernel's epilogue while the particle's forces are still in
  * registers; results are bitwise those of the two separate calls (same update code). old_* = state n (may be the
  * buffers args->pos / args->vel: predictor), new_* receives the integrated state and may alias old_* (in place) but
- * must not alias args->pos / args->vel, which other particles still gather from. forces is written as usual. */
+ * must not alias args->pos / args->vel (nor args->packed), which other particles still gather from - unless the caller
+ * provides args->packed, in which case the gathers read the records and pos / vel may be integrated in place.
+ * forces is written as usual. */
 typedef struct b200sph_fused_euler_args {
 	const void *old_pos, *old_vel;
 	void *new_pos, *new_vel;
 	float dt;                 /* dt of the sub-step (dt/2 for step 1), unless dt_from_device */
 	int step;                 /* 1 predictor, 2 corrector */
 	int dt_from_device;       /* dt from the device-resident record (dt/2 for step 1) */
+	void *new_packed;         /* ABI 3, may be NULL: also receives the integrated state as 32-byte neighbour records
+	                             (see b200sph_forces_args.packed) for [from_particle, to_particle) */
 } b200sph_fused_euler_args;
 int b200sph_forces_euler(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *euler,
 	uint32_t *num_cfl_blocks);
+
+/* Interleave pos / vel of [from_particle, to_particle) into the 32-byte neighbour records of
+ * b200sph_forces_args.packed (no reference counterpart; streaming, 64 bytes per particle). */
+int b200sph_pack_state(b200sph_ctx *ctx, const void *pos, const void *vel, void *packed,
+	uint32_t from_particle, uint32_t to_particle);
 
 /* AbstractForcesEngine::reduceRbForces (src/engine_forces.h:68-74; src/cuda/forces.cu:967-1003): in-place segmented
  * inclusive scan of rb_forces / rb_torques keyed by rb_keys, then the last element of each body's segment

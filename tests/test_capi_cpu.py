@@ -63,6 +63,25 @@ def test_validate_accepts_supported_and_rejects_unsupported():
         with pytest.raises(capi.B200Unsupported):
             capi.check(lib.b200sph_validate(C.byref(p)))
         assert b"unsupported" in lib.b200sph_last_error()
+    # the WHOLE of SimParams::simflags reaches the library: every flag outside the allow-list is refused by name,
+    # none is silently dropped (the reference would run the energy equation, open boundaries, ... for these)
+    for flag, name in [(capi.ENABLE_INTERNAL_ENERGY, b"ENABLE_INTERNAL_ENERGY"), (capi.ENABLE_INLET_OUTLET, b"ENABLE_INLET_OUTLET"),
+                       (capi.ENABLE_WATER_DEPTH, b"ENABLE_WATER_DEPTH"), (capi.ENABLE_DENSITY_SUM, b"ENABLE_DENSITY_SUM"),
+                       (capi.ENABLE_GAMMA_QUADRATURE, b"ENABLE_GAMMA_QUADRATURE"), (1 << 12, b"unknown")]:
+        p = params.copy()
+        p.simflags = capi.ENABLE_DTADAPT | flag
+        assert lib.b200sph_validate(C.byref(p)) == capi.E_UNSUP, name
+        assert name in lib.b200sph_last_error()
+    # DamBreak3D's own flag word: DTADAPT | REPACKING (src/problems/DamBreak3D.cu:53-57), with a body: MOVING_BODIES
+    for ok in (capi.ENABLE_DTADAPT | capi.ENABLE_REPACKING, capi.ENABLE_DTADAPT | capi.ENABLE_REPACKING | capi.ENABLE_MOVING_BODIES):
+        p = params.copy()
+        p.simflags = ok
+        assert lib.b200sph_validate(C.byref(p)) == 0
+    p = params.copy()
+    p.num_fluids = 2                    # more than one fluid needs ENABLE_MULTIFLUID (src/ProblemCore.cc:108-112)
+    assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL
+    p.simflags |= capi.ENABLE_MULTIFLUID
+    assert lib.b200sph_validate(C.byref(p)) == 0
     # everything reachable from the CLI options of DamBreak3D / Poiseuille is accepted
     for field, ok in [("densitydiffusiontype", capi.RHODIFF_BREZZI), ("simflags", capi.ENABLE_DTADAPT | capi.ENABLE_XSPH),
                       ("simflags", capi.ENABLE_DTADAPT | capi.ENABLE_PLANES)]:

@@ -1,32 +1,30 @@
 #!/usr/bin/env bash
-# Drop-in demonstration: link the REFERENCE's host code (GPUSPH orchestrator, integrator, GPUWorker, problem API,
-# writers) and its stock framework (visc / BC engines, other post-processing) with OUR engines: neibs, forces, integration,
-# the SHEPARD / MLS filters and the TESTPOINTS post-process
-# (gpusph_b200/host/b200_engines.h -> libb200sph.so). The only reference-side change is the 3-line patch of
-# GPUWorker's constructor shown in INTEGRATION.md; the problem file (DamBreak3D.cu) is compiled unchanged.
-# Needs the scratch tree and objects produced by oracle/build_ref.sh. Output: build/dropin/<Problem>_b200
-# (git-ignored, travels to the GPU box).
+# Drop-in build: the REFERENCE's unmodified host code (GPUSPH orchestrator, integrator, GPUWorker, problem API, writers)
+# and its unmodified problem files, with OUR framework seam: gpusph_b200/host/cudasimframework.cu is found before
+# src/cuda/cudasimframework.cu on the include path, so `#include "cudasimframework.cu"` in the problem file
+# (src/problems/DamBreak3D.cu:35, src/problems/Poiseuille.inc:50) yields the B200 engines (-> libb200sph.so).
+# No reference file is edited and none of the reference's CUDA engines is compiled or linked.
+# Needs the host objects produced by oracle/build_ref.sh (the texture shim that script applies only touches src/cuda
+# files, which this build does not use). Output: build/dropin/<Problem>_b200 (git-ignored, travels to the GPU box).
+#
+# Usage: tools/build_dropin.sh [Problem ...]      (default: DamBreak3D Poiseuille)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 WORK="${TMPDIR:-/tmp}/gpusph_b200_refbuild"
-P="${1:-DamBreak3D}"
-[ -d "$WORK/build" ] || "$HERE/oracle/build_ref.sh" "$P"
-OUT="$HERE/build/dropin"; mkdir -p "$OUT"
+PROBLEMS=("$@"); [ ${#PROBLEMS[@]} -eq 0 ] && PROBLEMS=(DamBreak3D Poiseuille)
+[ -f "$WORK/build/GPUWorker.o" ] || "$HERE/oracle/build_ref.sh" DamBreak3D
+OUT="$HERE/build/dropin"; mkdir -p "$OUT" "$WORK/build_b200"
 cd "$WORK"
-cp src/GPUWorker.cc src/GPUWorker_b200.cc
-# --- the maintainer's patch ---
-sed -i 's|^using namespace std;|#include "b200_engines.h"\nstatic std::shared_ptr<b200::Contexts> b200_contexts() { static std::shared_ptr<b200::Contexts> c = std::make_shared<b200::Contexts>(); return c; }\nusing namespace std;|' src/GPUWorker_b200.cc
-sed -i 's|neibsEngine(gdata->simframework->getNeibsEngine()),|neibsEngine(new b200::NeibsEngine(b200_contexts(), gdata->simframework->getNeibsEngine())),|' src/GPUWorker_b200.cc
-sed -i 's|forcesEngine(gdata->simframework->getForcesEngine()),|forcesEngine(new b200::ForcesEngine(b200_contexts(), gdata->simframework->getForcesEngine())),|' src/GPUWorker_b200.cc
-sed -i 's|integrationEngine(gdata->simframework->getIntegrationEngine()),|integrationEngine(new b200::IntegrationEngine(b200_contexts(), gdata->simframework->getIntegrationEngine())),|' src/GPUWorker_b200.cc
-sed -i 's|filterEngines(gdata->simframework->getFilterEngines()),|filterEngines(b200::filters(b200_contexts(), gdata->simframework->getFilterEngines())),|' src/GPUWorker_b200.cc
-sed -i 's|postProcEngines(gdata->simframework->getPostProcEngines()),|postProcEngines(b200::postprocess(b200_contexts(), gdata->simframework->getPostProcEngines())),|' src/GPUWorker_b200.cc
-grep -c "b200::" src/GPUWorker_b200.cc
-INC="-Isrc -Isrc/adaptors -Isrc/cuda -Isrc/geometries -Isrc/integrators -Isrc/problem_api -Isrc/problems -Isrc/writers -Isrc/problems/user -Ioptions"
-g++ -include cstdint -include climits -include cstring $INC -I/usr/local/cuda/include -I"$HERE/include" -I"$HERE/gpusph_b200/host" \
-    -D__STDC_CONSTANT_MACROS -D__STDC_LIMIT_MACROS -D_GLIBCXX_USE_C99_MATH -DUSE_HDF5=0 -D__COMPUTE__=100 \
-    -m64 -std=c++11 -O3 -w -c -o build/GPUWorker_b200.o src/GPUWorker_b200.cc
-OBJS=$(find build -name '*.o' ! -name 'GPUWorker.o' ! -name 'GPUWorker_b200.o' ! -name '*.gen.o' ! -path 'build/problems/*' ! -name 'DamBreak3D.o' ! -name 'Poiseuille.o' | tr '\n' ' ')
-/usr/local/cuda/bin/nvcc -arch=sm_100 -o "$OUT/${P}_b200" $OBJS build/GPUWorker_b200.o build/$P.gen.o build/$P.o \
-    -L"$HERE/gpusph_b200" -lb200sph -Xlinker -rpath -Xlinker '$ORIGIN/../../gpusph_b200' -lpthread -lrt
-echo "-> $OUT/${P}_b200"
+# our host directory first: that is the whole integration
+INC="-I$HERE/gpusph_b200/host -I$HERE/include -Isrc -Isrc/adaptors -Isrc/cuda -Isrc/geometries -Isrc/integrators -Isrc/problem_api -Isrc/problems -Isrc/writers -Isrc/problems/user -Ioptions"
+CPPFLAGS="-include cstdint -include climits -include cstring $INC -D__STDC_CONSTANT_MACROS -D__STDC_LIMIT_MACROS -D_GLIBCXX_USE_C99_MATH -DUSE_HDF5=0 -D__COMPUTE__=100"
+HOSTOBJS=$(find build -name '*.o' ! -name '*.gen.o' ! -path 'build/problems/*' $(for p in build/*.gen.o; do b=$(basename "$p" .gen.o); echo "! -name $b.o"; done) | tr '\n' ' ')
+for P in "${PROBLEMS[@]}"; do
+  echo "== drop-in build of $P"
+  [ -f "build/$P.gen.o" ] || { sed -e "s/PROBLEM/$P/g" src/problem_gen.tpl > "options/$P.gen.cc"; \
+    g++ $CPPFLAGS -I/usr/local/cuda/include -m64 -std=c++11 -O3 -w -c -o "build/$P.gen.o" "options/$P.gen.cc"; }
+  /usr/local/cuda/bin/nvcc $CPPFLAGS -arch=sm_100 -std=c++11 --compiler-options -m64,-O3,-w -w -c -o "build_b200/$P.o" "src/problems/$P.cu"
+  /usr/local/cuda/bin/nvcc -arch=sm_100 -o "$OUT/${P}_b200" $HOSTOBJS "build/$P.gen.o" "build_b200/$P.o" \
+      -L"$HERE/gpusph_b200" -lb200sph -Xlinker -rpath -Xlinker '$ORIGIN/../../gpusph_b200' -lpthread -lrt
+  echo "-> $OUT/${P}_b200"
+done

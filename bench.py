@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (kind, args) — BASELINE.json configs; see SURVEY.md section 6.2 for what they resolve to
     "dambreak2m": ("dambreak", dict(dp=0.0043)),     # configs[1]: DamBreak3D ~2M particles, Ferrari
-    "dambreak8m": ("dambreak", dict(dp=0.0026)),     # headline target size
+    "dambreak8m": ("dambreak", dict(dp=0.0026)),     # headline target size (north star): the N = 1 default
+    "dambreak16m": ("dambreak", dict(dp=0.002)),     # configs[3]: fixed 16 M problem split over 2 / 4 / 8 GPUs: the N > 1 default
     "dambreak84k": ("dambreak", dict(dp=0.015)),     # configs[0]: the reference's default
     "lattice8m": ("lattice", dict(n=200)),           # configs[2]
     "lattice2m": ("lattice", dict(n=126)),
@@ -38,26 +39,39 @@ WORKLOADS = {
 }
 FORCES_BYTES_PER_PARTICLE = 60      # R pos16+vel16+info8+hash4, W forces16
 L2_BYTES = 126 * 1024 * 1024
+# FP32 operations the pair kernel executes per list entry, counted in the SASS of its inner loop (Ferrari + artificial
+# viscosity variant, the bench default): 12 FFMA (2 flop each) + 45 FADD/FMUL + 6 MUFU + 1 FMNMX + 4 FSETP = 80
+# (DESIGN.md section 4 has the listing). The lattice / Poiseuille variants execute fewer; the same constant is used for all.
+FLOP_PER_PAIR = 80
+# Neighbour-list entries per particle of each workload as OUR neighbour engine counts them on the first build (printed
+# as config.neibs_per_particle by every run of this file; the list is bit-identical to the reference's, see
+# tests/test_golden.py, and the reference does not print its own numInteractions counter). The reference arm multiplies
+# its particle-updates/s by this constant so that it does not have to load anything of ours.
+NEIBS_PER_PARTICLE = {"dambreak84k": 36.45, "dambreak2m": 49.46, "dambreak8m": 52.30, "dambreak16m": 53.20}
 
 
-def make_problem(name, world=1):
-    """N = 1: the named configuration with the reference's default cell linearisation (yzx).
-    N > 1 (weak scaling): the same tank widened N times along y, cells linearised xzy so that the slowest hash digit —
-    the slab axis — is y (the reference's DamBreak3D also prefers the Y split, src/problems/DamBreak3D.cu:217-220):
-    every GPU owns one tank-width of the problem plus one halo cell layer per side."""
+def make_problem(name, world=1, scaling="strong"):
+    """N = 1: the named configuration with the reference's default cell linearisation (yzx): the particle set is the
+    reference's own (`DamBreak3D --deltap dp --density-diffusion 1 --num_obstacles 0`, 12 test points included; checked
+    against the reference's initial states in tests/test_golden.py).
+    N > 1: cells linearised xzy so that the slowest hash digit - the slab axis - is y (the reference's DamBreak3D also
+    prefers the Y split, src/problems/DamBreak3D.cu:217-220). scaling = "strong": the SAME problem split over N slabs
+    (BASELINE configs[3]); "weak": the tank widened N times along y, one tank width per GPU."""
     from gpusph_b200 import capi
     from gpusph_b200.problems import dambreak_problem, lattice_problem
     kind, kw = WORKLOADS[name]
     if kind == "dambreak":
-        extra = dict(width_scale=world, coord=(0, 2, 1)) if world > 1 else {}
-        return dambreak_problem(kw["dp"], densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1, **extra)
+        extra = dict(coord=(0, 2, 1)) if world > 1 else {}
+        if world > 1 and scaling == "weak":
+            extra["width_scale"] = world
+        return dambreak_problem(kw["dp"], densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1, testpoints=3, **extra)
     if kind == "poiseuille":
         if world > 1:
             raise SystemExit("poiseuille1m is a single-GPU workload (periodic along every slab axis)")
         from gpusph_b200.problems import poiseuille_problem
         return poiseuille_problem(kw["ppH"], ncell=kw["ncell"])
     if world > 1:
-        return lattice_problem(kw["n"], ny=kw["n"] * world, coord=(0, 2, 1), densitydiffusion=capi.RHODIFF_NONE)
+        return lattice_problem(kw["n"], ny=kw["n"] * (world if scaling == "weak" else 1), coord=(0, 2, 1), densitydiffusion=capi.RHODIFF_NONE)
     return lattice_problem(kw["n"], densitydiffusion=capi.RHODIFF_NONE)
 
 
@@ -119,22 +133,29 @@ def cpu_baseline_port(seconds=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the UNMODIFIED GPUSPH reference (shim-built binary oracle/_ref/DamBreak3D, its own
-    CUDA engines — the reference has no CPU compute path) on the same box."""
+    """--impl reference: the UNMODIFIED GPUSPH reference (shim-built binary oracle/_ref/DamBreak3D, its own CUDA
+    engines - the reference has no CPU compute path) on the same box, same problem, same
+    command-line options as our arm's workload. Nothing of this repository's product is imported or loaded here: the
+    process only spawns the reference binary and parses what it prints.
+    N > 1: the same fixed-size problem (strong scaling, like our arm's default) on N devices with the reference's own
+    slab decomposition and --striping (edge stripe, halo exchange overlapped with the inner stripe,
+    src/GPUWorker.cc:2086-2160). DamBreak3D always splits along Y (src/problems/DamBreak3D.cu:217-220); the binary used
+    at N > 1 is the same unmodified source built with the xzy cell linearisation (oracle/_ref/DamBreak3D_xzy, the
+    reference's own `linearization=` build option), which makes Y the slowest hash digit so that each halo is one
+    contiguous burst - with the default yzx order the reference's UPDATE_EXTERNAL degenerates into thousands of
+    per-cell-column copies (44 ms per call measured in round 1)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    binp = os.environ.get("B200SPH_REF_BIN") or os.path.join(ROOT, "oracle", "_ref", "DamBreak3D")
+    default_bin = os.path.join(ROOT, "oracle", "_ref", "DamBreak3D")
+    if args.gpus > 1 and os.path.exists(default_bin + "_xzy"):
+        default_bin += "_xzy"
+    binp = os.environ.get("B200SPH_REF_BIN") or default_bin
     kind, kw = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "particle_interactions_per_second", "unit": "M interactions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload}}
-    if args.gpus > 1:
-        # the reference's DamBreak3D has no option to widen the tank: its multi-GPU run splits the N = 1 problem
-        line["scaling"] = "strong"
-        line["config"]["note"] = ("reference at N > 1: the same (N = 1) DamBreak3D split over N devices by its own slab decomposition - "
-                                  "its problem file cannot widen the tank like our weak-scaling arm does")
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "binary": os.path.relpath(binp, ROOT)}}
     if kind != "dambreak" or not os.path.exists(binp):
         cb = cpu_baseline_port(20.0)
         line.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
@@ -150,10 +171,12 @@ def run_reference(args):
         cmd = [binp, "--deltap", str(kw["dp"]), "--maxiter", str(maxiter), "--nosave", "--dir", d,
                "--device", dev, "--density-diffusion", "1", "--num_obstacles", "0",
                "--debug", "benchmark_command_runtimes"]
+        if args.gpus > 1:
+            cmd.append("--striping")
         t0 = time.perf_counter()
         p = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
         el = time.perf_counter() - t0
-        return el, p.stdout + p.stderr, p.returncode
+        return el, p.stdout + p.stderr, p.returncode, " ".join(cmd[:1] + cmd[1:])
 
     def cycle_seconds(text):
         # the reference prints the wall time of its main loop itself (src/GPUSPH.cc runSimulation epilogue)
@@ -162,11 +185,11 @@ def run_reference(args):
 
     # ONE run of warm-up + timed iterations. The reference's per-command timers give (calls, max, total) per command; a
     # command's typical call = (total - max) / (calls - 1): the slowest call of every command (first-launch module
-    # loading, and the erratic thrust::sort_by_key of this build — measured anywhere between 1.6 and 700 ms per call on
-    # the same input) is dropped, the rest averaged. (Differences between two separate runs — what this arm used
-    # before — went negative whenever the shorter run happened to hit the slow sort.)
+    # loading, and the erratic thrust::sort_by_key of this build - measured anywhere between 1.6 and 700 ms per call on
+    # the same input) is dropped, the rest averaged. This is FAVOURABLE to the reference: its own wall clock per
+    # iteration (also reported, reference_wall_ms_per_step) is several times larger.
     iters = max(args.warmup, 1) + args.steps
-    t_k, out_k, rc_k = run(iters)
+    t_k, out_k, rc_k, cmdline = run(iters)
     m = re.findall(r"iteration=[\d,]+, dt=[0-9.eE+-]+s, ([\d,]+) parts", out_k)
     nparts = int(m[-1].replace(",", "")) if m else None
     c_k = cycle_seconds(out_k)
@@ -199,29 +222,18 @@ def run_reference(args):
     line["reference_phase_ms_per_step"] = {k: v for k, v in sorted(phases.items(), key=lambda kv: -kv[1])[:8]}
     line["reference_raw_cmdtimes_calls_max_total_ms"] = {k: ct_k[k] for k in line["reference_phase_ms_per_step"]}
     line["reference_cycle_seconds_2digits"] = c_k
+    line["reference_wall_ms_per_step"] = (c_k / iters * 1e3) if c_k else None
+    line["reference_command"] = cmdline
     ups = nparts * args.steps / sec
-    # interactions per particle: measured by our neighbour engine on the same geometry/dp (the reference
-    # does not print its numInteractions counter); see DESIGN.md "Measurement"
-    npp = float(os.environ.get("B200SPH_NEIBS_PER_PARTICLE", "0")) or None
-    if npp is None:
-        try:
-            import torch
-            from gpusph_b200.simulation import Worker
-            params, parts = make_problem(args.workload)
-            w = Worker(params, parts, 0)
-            w.build_neibs()
-            npp = w.last_neibs_info.num_interactions / parts.n
-            del w
-            torch.cuda.empty_cache()
-        except Exception:
-            npp = 0.0
+    npp = float(os.environ.get("B200SPH_NEIBS_PER_PARTICLE", "0")) or NEIBS_PER_PARTICLE.get(args.workload, 50.0)
     val = ups * npp * 2 / 1e6
     line.update({"value": val, "ms_per_step": sec / args.steps * 1e3, "particle_updates_per_s": ups,
                  "particles": nparts, "neibs_per_particle": npp,
+                 "neibs_per_particle_source": "committed constant (bench.py NEIBS_PER_PARTICLE): list entries per particle of this workload as counted by the neighbour engine of this repository, whose list is bit-identical to the reference's; the reference does not print its counter. The ratio of the two arms' values equals the ratio of their particle-updates/s times (our measured entries per particle / this constant).",
                  "cpu_baseline": {"value": val, "unit": "M interactions/s", "cores": 1 + args.gpus, "kind": "reference",
-                                  "sample": f"oracle/_ref/DamBreak3D --deltap {kw['dp']} --density-diffusion 1 --num_obstacles 0: "
+                                  "sample": f"{os.path.relpath(binp, ROOT)} --deltap {kw['dp']} --density-diffusion 1 --num_obstacles 0{' --striping' if args.gpus > 1 else ''}: "
                                             f"one run of {iters} iterations; per command (its own timers, --debug benchmark_command_runtimes) the slowest call is dropped and the others averaged; the reference's own CUDA engines "
-                                            "on the same GPU (it has no CPU compute path), 1 orchestrator + 1 worker host thread per GPU"},
+                                            "on the same GPU(s) (it has no CPU compute path), 1 orchestrator + 1 worker host thread per GPU"},
                  "e2e": {"value": val, "unit": "M interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
     return 0
@@ -237,11 +249,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", action="store_true", help="replay the time step as a CUDA graph between neighbour rebuilds")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: plain upload / step / download instead of Worker.step_host")
+    ap.add_argument("--quick", action="store_true", help="kernel tuning sweeps: skip the e2e leg and the CPU baseline")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: split the same problem over N slabs (default, BASELINE configs[3]) or widen the tank N times")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.workload is None:
-        args.workload = "dambreak2m"
+        # N = 1: the north-star size (DamBreak3D at 8 M particles); N > 1: the fixed 16 M problem of BASELINE configs[3]
+        args.workload = "dambreak8m" if args.gpus <= 1 else "dambreak16m"
     if args.impl == "reference":
         return run_reference(args)
 
@@ -264,7 +280,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gpusph_b200.simulation import Worker
 
-    params, parts = make_problem(args.workload, world)
+    params, parts = make_problem(args.workload, world, args.scaling)
     if world > 1:
         from gpusph_b200.multigpu import SlabWorker
         w = SlabWorker(params, parts, local, rank=rank, world=world)
@@ -309,7 +325,7 @@ def main():
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
-    if True:
+    if not args.quick:
         n = w.numParticles
         A = w.pos[0].shape[0]
         hp = [torch.empty((A, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -401,6 +417,7 @@ def main():
             return tot / reps
         # one force evaluation = the fused pair kernel (forces_gather_kernel: fluid<-fluid, fluid<-boundary,
         # boundary<-fluid, finalize and CFL in one launch)
+        w.forces_once()                         # untimed: makes the neighbour records of the current state if needed
         t_kernel = timed(w.forces_once)
         # a streaming kernel for comparison: euler reads pos, vel, forces, info (56 B) and writes pos, vel (32 B)
         t_euler = timed(w.euler_once)
@@ -413,18 +430,27 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = FORCES_BYTES_PER_PARTICLE * n / (t_kernel / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "forces_gather_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
-                    "algorithmic_bytes_per_particle": FORCES_BYTES_PER_PARTICLE, "kernel_ms": t_kernel,
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_achieved = FORCES_BYTES_PER_PARTICLE * n / (t_kernel / 1e3) / 1e9
+        # The pair kernel is bound by FP32 instruction issue and the L1 gather path, not by HBM (ncu: DRAM < 10 % of peak):
+        # its roofline is the non-tensor FP32 pipe, 148 SMs x 128 lanes x 2 flop (FMA) x the SM clock seen under load.
+        pairs = float(w.last_neibs_info.num_interactions)
+        sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        fp32_achieved = pairs * FLOP_PER_PAIR / (t_kernel / 1e3) / 1e12
+        roofline = {"bound": "fp32", "kernel": "forces_gather_kernel", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": fp32_achieved / fp32_peak, "traffic": None,
+                    "peak_source": f"non-tensor FP32: 148 SM x 128 lanes x 2 flop x {sm_mhz:.0f} MHz (SM clock sampled under load by this run)",
+                    "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": t_kernel,
                     "timed": "one forces_gather_kernel launch (= one force evaluation), CUDA events, L2 flushed between launches",
+                    "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                            "algorithmic_bytes_per_particle": FORCES_BYTES_PER_PARTICLE,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+                            "note": "reported because the contract asks for it; an efficient pair kernel sits at 5-15 % of the HBM roof (SURVEY.md 8d)"},
                     "streaming_reference": {"kernel": "euler_kernel", "algorithmic_bytes_per_particle": 88, "kernel_ms": t_euler,
-                                            "achieved": 88 * n / (t_euler / 1e3) / 1e9, "frac": 88 * n / (t_euler / 1e3) / 1e9 / peak},
+                                            "achieved": 88 * n / (t_euler / 1e3) / 1e9, "frac": 88 * n / (t_euler / 1e3) / 1e9 / hbm_peak},
                     "neighbour_rebuild_ms": t_rebuild,
-                    "pair_rate_G_per_s": w.last_neibs_info.num_interactions / (t_kernel / 1e3) / 1e9,
-                    "note": "the pair kernel is L1-gather / instruction-issue bound (ncu: L1TEX 81 %, issue 67 %, DRAM 8 %; profiles/r01_forces_gather_final_ncu.txt), not HBM bound (SURVEY.md 8d); the HBM fraction is reported because the contract asks for it"}
+                    "pair_rate_G_per_s": pairs / (t_kernel / 1e3) / 1e9}
         tr = os.path.join(ROOT, "profiles", "forces_traffic.json")
         if os.path.exists(tr):
             try:
@@ -434,12 +460,12 @@ def main():
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             cpu = cpu_baseline_port()
         line = {
             "metric": "particle_interactions_per_second", "value": value, "unit": "M interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if world == 1 else args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "particles": n_global,
                        "neibs_per_particle": w.last_neibs_info.num_interactions / max(w.numOwn if world > 1 else w.numParticles, 1),
@@ -447,7 +473,8 @@ def main():
                        "viscosity": "laminar (Morris)" if "poiseuille" in args.workload else "artificial",
                        "l2": f"inputs larger than L2 (working set {working_set / 1e6:.0f} MB vs 126 MB)" if working_set > L2_BYTES
                              else "working set fits L2 (small reference config)",
-                       "parallelism": f"slab{world} (1-D slabs along y, tank widened x{world}, NCCL halo exchange)" if world > 1 else "single"},
+                       "parallelism": (f"slab{world} (1-D slabs along y, NCCL halo exchange; " +
+                                       ("the same problem split over the ranks)" if args.scaling == "strong" else f"tank widened x{world})")) if world > 1 else "single"},
             "particle_updates_per_s": updates,
             "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -50,7 +50,7 @@ int main(int argc, char **argv)
 	p.sscoeff[0] = (float)c0; p.sspowercoeff[0] = (float)((gamma - 1.0) / 2.0);
 	p.gravity[2] = -9.81f;
 	p.artvisccoeff = 0.3f; p.epsartvisc = (float)(0.01 * (double)slength * (double)slength);
-	p.max_sound_speed_cfl = (float)c0 * 1.1f; p.dtadapt = 1; p.simflags = B200SPH_ENABLE_DTADAPT;
+	p.max_sound_speed_cfl = (float)((double)(float)c0 * 1.1); p.dtadapt = 1;       // float *= 1.1 (double), GPUWorker.cc:3011 p.simflags = B200SPH_ENABLE_DTADAPT;
 	p.epsxsph = 0.5f; p.monaghan_visc_coeff = 10.0f;
 	p.r0 = (float)dp; p.dcoeff = (float)(5.0 * 9.81); p.p1coeff = 12.0f; p.p2coeff = 6.0f;
 	CK(b200sph_validate(&p));
@@ -65,9 +65,11 @@ int main(int argc, char **argv)
 		const double g[3] = { (ix + 0.5) * dp, (iy + 0.5) * dp, (iz + 0.5) * dp };
 		uint32_t c[3];
 		for (int a = 0; a < 3; ++a) {
-			long q = (long)floor((g[a] + pad) / (double)p.cell_size[a]);
+			// relative to the FLOAT world origin the engines were given (ProblemCore.cc:1554-1583)
+			const double rel = g[a] - (double)p.world_origin[a];
+			long q = (long)floor(rel / (double)p.cell_size[a]);
 			c[a] = (uint32_t)(q < 0 ? 0 : (q >= (long)G[a] ? G[a] - 1 : q));
-			pos[4 * (size_t)i + a] = (float)(g[a] + pad - (c[a] + 0.5) * (double)p.cell_size[a]);
+			pos[4 * (size_t)i + a] = (float)(rel - (c[a] + 0.5) * (double)p.cell_size[a]);
 			vel[4 * (size_t)i + a] = (float)(0.1 * c0 * (a == 1 ? cos(2 * M_PI * g[a] / L) : sin(2 * M_PI * g[a] / L)));
 		}
 		pos[4 * (size_t)i + 3] = (float)(rho0 * dp * dp * dp);
@@ -130,6 +132,7 @@ int main(int argc, char **argv)
 			f.info = d_info; f.hash = d_hash; f.cell_start = d_cs; f.neibs_list = d_nl; f.forces = d_forces; f.cfl = d_cfl;
 			f.num_particles = np; f.from_particle = 0; f.to_particle = np; f.cfl_offset = 0; f.step = step; f.dt_from_device = 1;
 			b200sph_fused_euler_args e;
+			memset(&e, 0, sizeof(e));
 			e.old_pos = d_pos[cur]; e.old_vel = d_vel[cur];
 			e.new_pos = d_pos[step == 1 ? 1 - cur : cur]; e.new_vel = d_vel[step == 1 ? 1 - cur : cur];
 			e.dt = 0.0f; e.step = step; e.dt_from_device = 1;

@@ -32,6 +32,10 @@ static std::mutex g_kernel_cache_lock;
 #ifndef GATHER_PF
 #define GATHER_PF 2
 #endif
+// B200_GATHER_AHEAD=1: the neighbour record of the next list entry is requested before the current one is evaluated
+#ifndef B200_GATHER_AHEAD
+#define B200_GATHER_AHEAD 0
+#endif
 
 // ---------------------------------------------------------------------------
 // per-particle pre-passes
@@ -119,19 +123,19 @@ __device__ __forceinline__ float4 cell_offset(const DevParams &P, const int c)
 		(float)(c / 9 - 1) * P.cellSize[2], 0.f);
 }
 
-// Walk one section of a particle's neighbour-list column. fetch(slot, np, nv, ne) loads the neighbour record
-// `slot` = base-of-its-cell + offset-in-cell (global particle index); lut(cell, base, ox, oy, oz) returns the first slot of neighbour cell `cell` and its offset times
-// the cell size. PF list rows are read ahead of use; the read-ahead offset is clamped to the list.
+// Walk one section of a particle's neighbour-list column. fetch(j, np, nv) loads the record of neighbour j =
+// base-of-its-cell + offset-in-cell; eos(j, nv) gives its {P/rho^2, sound speed, density, fluid# | pressure};
+// lut(cell, base, ox, oy, oz) returns the first particle of neighbour cell `cell` and its offset times the cell size. PF list rows are read ahead of use; the read-ahead offset is clamped to the list.
 // WIDE: 64-bit list offsets (lists of 2^31 entries or more), else 32-bit (one VIADDMNMX per row).
 // Accumulation order = list order, as in the reference (neibs_iteration.cuh:56-200).
 struct ListGeom { const ushort *list; uint stride, rows, boundpos; };      // neighbour list + its shape (DevParams copies)
 template<bool WIDE> struct ListOff { typedef uint type; typedef int stype; };
 template<> struct ListOff<true> { typedef unsigned long long type; typedef long long stype; };
 
-template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch>
+template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch, typename Eos>
 __device__ __forceinline__ void
 walk_section(const DevParams &P, const PairConsts &k, const Central &c, const uint index, Lut lut,
-	const ListGeom &L, Fetch fetch, float4 &acc, float3 &xs)
+	const ListGeom &L, Fetch fetch, Eos eos, float4 &acc, float3 &xs)
 {
 	typedef typename ListOff<WIDE>::type off_t;
 	typedef typename ListOff<WIDE>::stype soff_t;
@@ -150,35 +154,69 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 	uint q[PF];
 #pragma unroll
 	for (int i = 0; i < PF; ++i) { q[i] = ld_neib(neibsList + off); off = advance(off); }
-	while (q[0] != NEIBS_END) {
-		uint nd = q[0];
+	auto next_entry = [&]() -> uint {              // pops the oldest row in flight, reads one more
+		const uint nd = q[0];
 #pragma unroll
 		for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
 		q[PF - 1] = ld_neib(neibsList + off);        // rows past the end marker are never used
 		off = advance(off);
-		if (nd >= CELLNUM_ENCODED) {                                    // getNeibIndex, cellgrid.cuh:198-226
+		return nd;
+	};
+	auto decode = [&](uint nd) -> uint {           // list entry -> neighbour index (getNeibIndex, cellgrid.cuh:198-226)
+		if (nd >= CELLNUM_ENCODED) {
 			const uint cell = (nd >> CELLNUM_SHIFT) - 1;
 			nd &= NEIBINDEX_MASK;
 			float ox, oy, oz;
 			lut(cell, base, ox, oy, oz);
 			pcx = c.pos.x - ox; pcy = c.pos.y - oy; pcz = c.pos.z - oz;
 		}
-		float4 np, nv, ne;
-		fetch(base + nd, np, nv, ne);
+		return base + nd;
+	};
+#if B200_GATHER_AHEAD
+	// software pipeline: the record of entry i+1 is requested before entry i is evaluated, so that a warp has one
+	// gather in flight while it computes (the kernel is latency-bound on exactly that load)
+	uint nd = next_entry();
+	if (nd == NEIBS_END) return;
+	uint j = decode(nd);
+	float4 np, nv;
+	fetch(j, np, nv);
+	float rx = pcx - np.x, ry = pcy - np.y, rz = pcz - np.z;
+	while (true) {
+		const uint nd2 = next_entry();
+		const bool more = nd2 != NEIBS_END;
+		float4 np2 = np, nv2 = nv;
+		uint j2 = j;
+		if (more) { j2 = decode(nd2); fetch(j2, np2, nv2); }
+		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
+		if ((r2 < k.R2) && (fabsf(np.w) < __int_as_float(0x7f800000)))
+			pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, eos(j, nv), NFLUID, acc, xs);
+		if (!more) break;
+		np = np2; nv = nv2; j = j2;
+		rx = pcx - np.x; ry = pcy - np.y; rz = pcz - np.z;
+	}
+#else
+	while (true) {
+		const uint nd = next_entry();
+		if (nd == NEIBS_END) break;
+		const uint j = decode(nd);
+		float4 np, nv;
+		fetch(j, np, nv);
 		const float rx = pcx - np.x, ry = pcy - np.y, rz = pcz - np.z;
 		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
 		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
-		pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, ne, NFLUID, acc, xs);
+		pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, eos(j, nv), NFLUID, acc, xs);
 	}
+#endif
 }
 
 // all sections of one particle (forces.cu:759,782,792 in the reference) + finalize; returns the CFL term
-template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch>
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch, typename Eos>
 __device__ __forceinline__ float
 particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
 	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo, Lut lut,
-	const ListGeom &L, Fetch fetch, float4 *__restrict__ forces, float4 *__restrict__ xsph = NULL, float4 *acc_out = NULL)
+	const ListGeom &L, Fetch fetch, Eos eos, float4 *__restrict__ forces, float4 *__restrict__ xsph = NULL, float4 *acc_out = NULL)
 {
 	Central c;
 	c.pos = pos; c.vel = vel;
@@ -193,14 +231,14 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 		// fluid<-fluid then fluid<-boundary; DYN boundary neighbours interact like fluid ones (forces_kernel.def:3717-3726)
 		c.momentum = true;
 		c.xsph = RHODIFF == RHODIFF_RUNTIME && xsph != NULL;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc, xs);
-		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc, xs);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, eos, acc, xs);
+		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, eos, acc, xs);
 		// write_xsph :3366-3368
 		if (c.xsph) xsph[index] = make_float4(2.0f * xs.x, 2.0f * xs.y, 2.0f * xs.z, 0.0f);
 	} else {
 		// boundary<-fluid: density always, momentum only with force feedback (forces_kernel.def:3634-3667)
 		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, acc, xs);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, eos, acc, xs);
 	}
 	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
 	forces[index] = acc;
@@ -295,12 +333,12 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 				ox = o.x; oy = o.y; oz = o.z;
 			};
 			// one 256-bit gather per neighbour: its {pos, mass, vel, rho~} record; EOS terms from rho~ on the fly
-			auto fetch = [&](const uint j, float4 &np, float4 &nv, float4 &ne) {
-				ld_posvel(pv + j, np, nv);
-				ne = MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
+			auto fetch = [&](const uint j, float4 &np, float4 &nv) { ld_posvel(pv + j, np, nv); };
+			auto eos = [&](const uint j, const float4 nv) {
+				return MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
 			};
 			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE>(P, k, index, info, type, pos,
-				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, forces,
+				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, eos, forces,
 				GEN ? bo.xsph : NULL, &acc);
 		}
 		// fused integration epilogue: exactly the stand-alone euler kernel's update of this particle (euler_update.cuh),

@@ -121,9 +121,13 @@ class CudaBackend:
         self.fw.neibsEngine.buildNeibsList(b, b, n, range_end)
         return self.fw.neibsEngine.getinfo()
 
-    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to, cfl_offset=0):
+    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to, cfl_offset=0, packed=None):
         b = self._b(pos=pos, vel=vel, info=info, hash=hashv, cs=cs, nl=nl, forces=forces, cfl=cfl)
-        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, cfl_offset)
+        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, cfl_offset, packed=packed)
+
+    def pack_state(self, pos, vel, packed, frm, to):
+        """pos / vel of [frm, to) interleaved into the pair kernel's neighbour records (b200sph_pack_state)."""
+        self.fw.forcesEngine.pack_state(self._b(pos=pos, vel=vel), packed, frm, to)
 
     def dtreduce(self, cfl, nblocks):
         b = self._b(cfl=cfl)
@@ -197,6 +201,9 @@ class SlabWorker:
         self.hash = torch.zeros(A, dtype=torch.int32, device=dev)
         self.partindex = torch.zeros(A, dtype=torch.int32, device=dev)
         self.forces_buf = f4()
+        # neighbour records of the pair kernel (CUDA engines): made once per force evaluation for own + halo particles,
+        # then gathered by both stripes' launches
+        self.packed = torch.empty(A * 32, dtype=torch.uint8, device=dev) if hasattr(self.backend, "pack_state") else None
         nc = p.num_cells
         self.cellstart = torch.empty(nc, dtype=torch.int32, device=dev)
         self.cellend = torch.empty(nc, dtype=torch.int32, device=dev)
@@ -384,6 +391,11 @@ class SlabWorker:
         e0 = min(self.edge_start, n_own)
         args = (self.pos[which], self.vel[which], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
         f = self.forces_buf
+        kw = {}
+        if self.packed is not None:
+            be.pack_state(self.pos[which], self.vel[which], self.packed, 0, n)
+            kw["packed"] = self.packed
+            self.launches += 1
 
         def exchange():
             # UPDATE_EXTERNAL(FORCES): owner's inner-edge forces -> neighbour's halo range
@@ -404,20 +416,20 @@ class SlabWorker:
             es.wait_stream(main)
             try:
                 ctx.use_stream(es)
-                nb_edge = be.forces(*args, e0, n_own, 0)
+                nb_edge = be.forces(*args, e0, n_own, 0, **kw)
             finally:
                 ctx.use_stream(main)
             with torch.cuda.stream(es):
                 works = exchange()
-            nb_inner = be.forces(*args, 0, e0, nb_edge)
+            nb_inner = be.forces(*args, 0, e0, nb_edge, **kw)
             with torch.cuda.stream(es):
                 for w_ in works:
                     w_.wait()
             main.wait_stream(es)
         else:
-            nb_edge = be.forces(*args, e0, n_own, 0) if n_own > e0 else 0
+            nb_edge = be.forces(*args, e0, n_own, 0, **kw) if n_own > e0 else 0
             works = exchange()
-            nb_inner = be.forces(*args, 0, e0, nb_edge) if e0 > 0 else 0
+            nb_inner = be.forces(*args, 0, e0, nb_edge, **kw) if e0 > 0 else 0
             for w_ in works:
                 w_.wait()
         nblocks = nb_edge + nb_inner

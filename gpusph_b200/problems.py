@@ -151,11 +151,14 @@ def initial_dt(p: capi.Params) -> float:
     return float(f32(dt))
 
 
-def localpos_and_hash(p: capi.Params, gpos: np.ndarray, mass: np.ndarray):
-    """Global double positions -> (cell-local float4 + mass, cell hash); ProblemCore.cc:1554-1583."""
-    origin = np.array([p.world_origin[a] for a in range(3)], dtype=np.float64)
-    cs = np.array([p.cell_size[a] for a in range(3)], dtype=np.float64)
+def localpos_and_hash(p: capi.Params, gpos: np.ndarray, mass: np.ndarray, origin=None, size=None):
+    """Global double positions -> (cell-local float4 + mass, cell hash); ProblemCore.cc:1554-1583. The reference does
+    this in double with its double world origin and cell size (m_origin, m_cellsize = m_size / gridsize): pass
+    origin / size to reproduce its choice of cell for particles lying on a cell face; without them the float copies
+    the engines hold are used."""
     G = np.array([p.grid_size[a] for a in range(3)], dtype=np.int64)
+    origin = np.array([p.world_origin[a] for a in range(3)], dtype=np.float64) if origin is None else np.asarray(origin, dtype=np.float64)
+    cs = np.array([p.cell_size[a] for a in range(3)], dtype=np.float64) if size is None else np.asarray(size, dtype=np.float64) / G
     g = np.floor((gpos - origin) / cs).astype(np.int64)
     g = np.minimum(np.maximum(g, 0), G - 1)
     c = [p.coord[a] for a in range(3)]
@@ -216,8 +219,10 @@ def lattice_problem(n: int, *, dp: float = 0.01, jitter: float = 0.05, seed: int
 
 
 def _box_shell(lo, hi, dp, layers):
-    """Points of `layers` layers of spacing dp lining the inside of the box [lo,hi] (all six faces)."""
-    n = np.maximum(np.round((np.asarray(hi) - np.asarray(lo)) / dp).astype(int), 1)
+    """Points of `layers` layers lining the inside of the box [lo,hi] (all six faces), laid out like the reference's
+    Cube::FillIn (src/geometries/Cube.cc:564-640): n = (int)(length / dp) intervals per side (TRUNCATED, so the actual
+    spacing is length / n >= dp), points at i / n of the side, i = 0..n."""
+    n = np.maximum(np.floor((np.asarray(hi, dtype=np.float64) - np.asarray(lo, dtype=np.float64)) / dp).astype(int), 1)
     xs = [np.asarray(lo)[a] + (np.arange(n[a] + 1)) * ((np.asarray(hi)[a] - np.asarray(lo)[a]) / n[a]) for a in range(3)]
     I, J, K = np.meshgrid(np.arange(n[0] + 1), np.arange(n[1] + 1), np.arange(n[2] + 1), indexing="ij")
     shell = (I < layers) | (I > n[0] - layers) | (J < layers) | (J > n[1] - layers) | (K < layers) | (K > n[2] - layers)
@@ -228,17 +233,24 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
                      alloc_extra: float = 0.0, width_scale: int = 1, obstacle: bool = False, testpoints: int = 0, **kw):
     """DamBreak3D-like setup (src/problems/DamBreak3D.cu:36-205 with --num_obstacles 0): a 1.6 x 0.67 x 0.6 m
     tank lined with `layers` layers of DYN boundary particles, a 0.4 m long, 0.4 m high water column,
-    Wendland kernel, artificial viscosity, c0 = 20, gamma = 7. Fill order/ids are ours, not the reference's
-    (bit-level parity with the reference is tested from the reference's own initial state instead).
+    Wendland kernel, artificial viscosity, c0 = 20, gamma = 7. The particle SET is the reference's (same counts and
+    positions as its Cube::FillIn / Cube::Fill, checked against the reference's own initial states in
+    tests/test_golden.py); fill order/ids are ours (bit-level parity with the reference is tested from the
+    reference's own initial state instead). Masses are the reference's too: volume-with-margin x density / particle
+    count per geometry (Object::SetPartMass, src/geometries/Object.cc:45-52; Cube::Volume, Cube.cc:216-224), and every
+    particle starts with the hydrostatic density of its depth below the water level (ProblemAPI_1.cc:1770-1810).
     width_scale = N widens the tank (and the water column) N times along y: the weak-scaling variant used by
     bench.py on N GPUs (same physics per unit width, N times the particles)."""
     dim = np.array([1.6, 0.67 * width_scale, 0.6])
     H = 0.4
     bd = dp * layers
-    wall = _box_shell(np.zeros(3), dim, dp, layers)
+    # non-fluid geometries are filled with r0 = the FLOAT copy of deltap (ProblemAPI<1>::preferredDeltaP,
+    # src/problem_api/ProblemAPI_1.cc:109-118; PhysParams::r0 is a float), fluid ones with the double deltap
+    dpb = float(np.float32(dp))
+    wall = _box_shell(np.zeros(3), dim, dpb, layers)
     lo = np.array([bd, bd, bd])
     ext = np.array([0.4 - bd, dim[1] - 2 * bd, H - bd])
-    nf = np.maximum(np.floor(ext / dp + 1e-9).astype(int), 1)
+    nf = np.maximum(np.floor(ext / dp).astype(int), 1)             # Cube::Fill: (int)(l / dx), src/geometries/Cube.cc:405-440
     I, J, K = np.meshgrid(np.arange(nf[0] + 1), np.arange(nf[1] + 1), np.arange(nf[2] + 1), indexing="ij")
     fluid = lo + np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1) * (ext / nf)
     nfl, nb = fluid.shape[0], wall.shape[0]
@@ -249,7 +261,7 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
         # (axis-aligned here; the reference rotates it by 45 degrees)
         side = 0.12
         blo = np.array([0.9 - side / 2, dim[1] / 2 - side / 2, bd])
-        body = _box_shell(blo, blo + np.array([side, side, dim[2] - 2 * bd]), dp, min(layers, 2))
+        body = _box_shell(blo, blo + np.array([side, side, dim[2] - 2 * bd]), dpb, min(layers, 2))
     nob = body.shape[0]
     # test points (src/problems/DamBreak3D.cu:201-213): `testpoints` per probe column at 0.25, 0.4, 0.75, 0.9 of the length
     tp = np.zeros((0, 3))
@@ -263,16 +275,25 @@ def dambreak_problem(dp: float = 0.015, *, densitydiffusion: int = capi.RHODIFF_
     params = make_params(origin=np.zeros(3), size=dim, deltap=dp, allocated_particles=int(N * (1 + alloc_extra)),
                          rho0=rho0, c0=c0, densitydiffusion=densitydiffusion, **kw)
     gpos = np.concatenate([fluid, wall, body, tp], axis=0)
-    mass = np.full(N, rho0 * dp ** 3, dtype=np.float32)
-    pos, hashv = localpos_and_hash(params, gpos, mass)
+
+    def part_mass(length, dx):
+        # Object::SetPartMass(dx, rho): Volume(dx) * rho / (particles of a full Fill), Cube::Volume = prod(l + dx)
+        length = np.asarray(length, dtype=np.float64)
+        cnt = np.prod(np.maximum(np.floor(length / dx).astype(int), 1) + 1)
+        return np.prod(length + dx) * rho0 / cnt
+    mass = np.concatenate([np.full(nfl, part_mass(ext, dp)), np.full(nb, part_mass(dim, dpb)),
+                           np.full(nob, part_mass([0.12, 0.12, dim[2]], dpb)), np.zeros(ntp)]).astype(np.float32)
+    pos, hashv = localpos_and_hash(params, gpos, mass, origin=np.zeros(3), size=dim)
     vel = np.zeros((N, 4), dtype=np.float32)
-    # hydrostatic initial density for the fluid column (ProblemAPI_1.cc hydrostatic filling):
-    # rho = rho0 (1 + g (H - z)/B)^(1/gamma), stored as rho/rho0 - 1
-    gam = 7.0
-    B = rho0 * c0 * c0 / gam
-    depth = np.clip(H - gpos[:, 2], 0, None)
-    in_column = gpos[:, 0] <= 0.4 + bd
-    dens = np.where(in_column, np.power(1.0 + rho0 * 9.81 * depth / B, 1.0 / gam) - 1.0, 0.0)
+    # hydrostatic initial density of EVERY particle below the water level (fluid, DYN boundary and test points alike,
+    # ProblemAPI_1.cc:1770-1810; ProblemCore::hydrostatic_density, ProblemCore.cc:890-902, float arithmetic):
+    # rho~ = (g rho0 h / B + 1)^(1/gamma) - 1
+    f32 = np.float32
+    gam = f32(7.0)
+    B = f32(rho0 * c0 * c0 / 7.0)
+    depth = (H - gpos[:, 2]).astype(np.float32)
+    g_abs = f32(abs(kw.get("gravity", (0.0, 0.0, -9.81))[2]))
+    dens = np.where(depth > 0, np.power((g_abs * f32(rho0) * depth / B + f32(1.0)).astype(np.float64), 1.0 / float(gam)) - 1.0, 0.0)
     vel[:, 3] = dens.astype(np.float32)
     info = np.concatenate([make_info(capi.PT_FLUID, ids=np.arange(nfl)),
                            make_info(capi.PT_BOUNDARY, ids=np.arange(nfl, nfl + nb)),

@@ -430,9 +430,13 @@ class Worker:
         capi.check(self.framework.ctx.lib.b200sph_host_sync(self.framework.ctx.handle))
 
     def forces_once(self) -> None:
-        """One force evaluation on the current state (bench.py roofline timing)."""
+        """One force evaluation on the current state (bench.py roofline timing): the pair kernel alone, gathering from
+        the neighbour records of the current state (made first if something invalidated them)."""
         s = self.state(self.cur)
-        self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0)
+        if not self._packed_valid:
+            self.forces.pack_state(s, self.packed[0], 0, self.numParticles)
+            self._packed_valid = True
+        self.forces.basicstep(s, s, self.numParticles, 0, self.particleRangeEnd, 0, packed=self.packed[0])
 
     def euler_once(self) -> None:
         """One predictor sub-step into the scratch state (bench.py: streaming-kernel reference point)."""

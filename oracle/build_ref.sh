@@ -27,11 +27,16 @@
 # same one-line contents / the reference's own awk scripts.
 #
 # Usage: oracle/build_ref.sh [Problem ...]     (default: DamBreak3D)
+#        LINEARIZATION=xzy REF_SUFFIX=_xzy oracle/build_ref.sh DamBreak3D
+#            the same unmodified sources with another cell linearisation (the reference's own `linearization=` build
+#            option, Makefile + src/linearization.h) -> oracle/_ref/DamBreak3D_xzy: used by bench.py's reference arm on
+#            N > 1 GPUs, where DamBreak3D's Y split needs Y to be the slowest hash digit for contiguous halo bursts
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${REF:-/root/reference}"
 OUT="$HERE/_ref"
-WORK="${TMPDIR:-/tmp}/gpusph_b200_refbuild"
+REF_SUFFIX="${REF_SUFFIX:-}"
+WORK="${TMPDIR:-/tmp}/gpusph_b200_refbuild${REF_SUFFIX}"
 PROBLEMS=("$@"); [ ${#PROBLEMS[@]} -eq 0 ] && PROBLEMS=(DamBreak3D)
 JOBS="${JOBS:-$(nproc)}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
@@ -118,6 +123,6 @@ for P in "${PROBLEMS[@]}"; do
   $CXX $CPPFLAGS $CUDA_INC $CXXFLAGS -c -o build/$P.gen.o options/$P.gen.cc &
   $NVCC $CPPFLAGS $CUFLAGS -c -o build/$P.o src/problems/$P.cu
   wait
-  $NVCC -arch=$ARCH -o "$OUT/$P" $HOSTOBJS build/$P.gen.o build/$P.o -lpthread -lrt
-  echo "   -> $OUT/$P"
+  $NVCC -arch=$ARCH -o "$OUT/$P$REF_SUFFIX" $HOSTOBJS build/$P.gen.o build/$P.o -lpthread -lrt
+  echo "   -> $OUT/$P$REF_SUFFIX"
 done

@@ -80,6 +80,35 @@ def test_fixture_matches_host_setup(path):
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_dambreak_problem_is_the_reference_particle_set(path):
+    """gpusph_b200.problems.dambreak_problem (what bench.py and the parity tests run) fills the tank exactly like the
+    reference's DamBreak3D (--num_obstacles 0): same particle count per type, same positions (to the last bit of the
+    cell-local floats), same cells, same masses, hydrostatic rho~ to float rounding. Ids / order are ours."""
+    from scipy.spatial import cKDTree
+    from gpusph_b200.problems import dambreak_problem
+    d = np.load(path)
+    if int(d["num_obstacles"]) if "num_obstacles" in d else 0:
+        pytest.skip("fixture with the obstacle")
+    if int(d["use_planes"]) if "use_planes" in d else 0:
+        pytest.skip("fixture with planes instead of the boundary box")
+    params, states = load(path)
+    ref = states[0][0]
+    mp, mine = dambreak_problem(float(d["deltap"]), densitydiffusion=int(d["rhodiff"]), testpoints=3)
+    assert mine.n == ref.n
+    tr, tm = ref.info[:, 0] & 7, mine.info[:, 0] & 7
+    gr, gm = global_positions(params, ref.pos, ref.hash), global_positions(mp, mine.pos, mine.hash)
+    for k in (capi.PT_FLUID, capi.PT_BOUNDARY, capi.PT_TESTPOINT):
+        assert (tr == k).sum() == (tm == k).sum()
+        dist, idx = cKDTree(gm[tm == k]).query(gr[tr == k])
+        assert dist.max() < 1e-7 and len(np.unique(idx)) == idx.size
+        a, b = ref.pos[tr == k], mine.pos[tm == k][idx]
+        assert np.abs(a[:, :3] - b[:, :3]).max() < 1e-8
+        assert np.array_equal(a[:, 3], b[:, 3]), "masses differ"
+        assert np.array_equal(ref.hash[tr == k], mine.hash[tm == k][idx]), "cells differ"
+        assert np.abs(ref.vel[tr == k][:, 3] - mine.vel[tm == k][idx][:, 3]).max() < 2e-7
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_oracle_reproduces_reference_single_step(path):
     params, states = load(path)
     s20, _, dt20 = states[20]

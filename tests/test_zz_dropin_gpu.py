@@ -1,0 +1,127 @@
+"""Regression in the reference's own style (scripts/check-problem.sh:44-55: run the problem, compare what it wrote):
+the SAME command line is run on the stock reference binary (oracle/_ref/<Problem>, built unmodified by
+oracle/build_ref.sh) and on the drop-in binary (build/dropin/<Problem>_b200: the reference's unmodified host code and
+problem file compiled against gpusph_b200/host/cudasimframework.cu, i.e. our engines behind the reference's
+GPUWorker through the C++ adapter and the C ABI; tools/build_dropin.sh), and the HotFile checkpoints both wrote at
+the last iteration are compared particle by particle.
+
+Cases: BASELINE configs[0] (default DamBreak3D, 84 k particles WITH its force-feedback obstacle, 100 iterations),
+configs[1] (--deltap 0.0043, Ferrari, 2 M particles, 21 iterations), the option set of SURVEY.md section 8 rows f2/f3
+(MLS filter, Brezzi diffusion, Lennard-Jones planes) and Poiseuille (configs[4]: periodic XY, laminar Morris viscosity).
+
+Bar: the neighbour-dependent integer results — the cell of every particle and its slot in the sorted order — are
+identical for (almost) every particle: a particle whose float position differs in the last bits can cross a cell face
+one step earlier or later, so the assertion is on the fraction (>= 99.9 % same cell) and positions are compared in
+the cell-local coordinates of the particles whose cell agrees. Positions within 1e-3 dp, velocities within 1e-3 of the velocity scale, rho~ within 1e-4
+(test_golden.py's ten-step tolerances scaled to 21-100 steps of a chaotic free-surface flow).
+"""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gpusph_b200 import capi
+from gpusph_b200.hotfile import particle_arrays, read_hotfile
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def binaries(problem):
+    ref = os.path.join(ROOT, "oracle", "_ref", problem)
+    ours = os.path.join(ROOT, "build", "dropin", problem + "_b200")
+    if not (os.path.exists(ref) and os.path.exists(ours)):
+        pytest.skip(f"{problem}: reference / drop-in binary not built (oracle/build_ref.sh, tools/build_dropin.sh)")
+    return ref, ours
+
+
+def run(binp, d, maxiter, args, timeout=900):
+    os.makedirs(d, exist_ok=True)
+    cmd = [binp, "--maxiter", str(maxiter), "--dir", d, "--checkpoint-every", "1000", "--checkpoints", "0", *args]
+    p = subprocess.run(cmd, capture_output=True, text=True, cwd=d, timeout=timeout)
+    log = p.stdout + p.stderr
+    assert p.returncode == 0, f"{' '.join(cmd)} failed (rc {p.returncode}):\n{log[-2500:]}"
+    files = sorted(glob.glob(os.path.join(d, "data", "hot_*.bin")))
+    assert files, f"no checkpoint written:\n{log[-1500:]}"
+    hf = read_hotfile(files[-1])
+    assert hf["iterations"] == maxiter, (hf["iterations"], maxiter)
+    return hf, log
+
+
+def ids_of(info):
+    return (info[:, 3].astype(np.int64) << 16) | info[:, 2]
+
+
+def compare(ref_hf, our_hf, dp, *, pos_tol_dp=1e-3, vel_tol=1e-3, rho_tol=1e-4, same_cell_min=0.999):
+    assert our_hf["particle_count"] == ref_hf["particle_count"]
+    assert our_hf["t"] == pytest.approx(ref_hf["t"], rel=2e-5), "simulated time differs (dt history)"
+    pr, vr, ir, hr = particle_arrays(ref_hf)
+    po, vo, io, ho = particle_arrays(our_hf)
+    a, b = np.argsort(ids_of(ir), kind="stable"), np.argsort(ids_of(io), kind="stable")
+    assert np.array_equal(ids_of(ir)[a], ids_of(io)[b]), "particle ids differ"
+    assert np.array_equal(ir[a], io[b]), "particle info differs"
+    same_cell = hr[a] == ho[b]
+    same_slot = float((ids_of(ir) == ids_of(io)).mean())
+    frac = float(same_cell.mean())
+    assert frac >= same_cell_min, f"only {frac:.5f} of the particles are in the reference's cell"
+    live = (ir[a, 0] & 7) != capi.PT_TESTPOINT
+    vs = max(float(np.abs(vr[:, :3]).max()), 1e-3)
+    verr = float(np.abs(vr[a][live, :3] - vo[b][live, :3]).max() / vs)
+    rerr = float(np.abs(vr[a][live, 3] - vo[b][live, 3]).max())
+    # positions: cell-local coordinates of the particles whose cell agrees (the others are the cell-face crossers)
+    perr = float(np.abs(pr[a][same_cell, :3] - po[b][same_cell, :3]).max() / dp)
+    assert np.array_equal(pr[a][:, 3], po[b][:, 3]), "masses differ"
+    assert perr < pos_tol_dp, f"position error {perr:.2e} dp"
+    assert verr < vel_tol, f"velocity error {verr:.2e} of the velocity scale {vs:.3g}"
+    assert rerr < rho_tol, f"relative density error {rerr:.2e}"
+    # test points carry the interpolated velocity / pressure the TESTPOINTS post-process wrote at the checkpoint
+    tp = ~live
+    if tp.any():
+        tv = np.abs(vr[a][tp] - vo[b][tp])
+        scale = np.maximum(np.abs(vr[a][tp]).max(axis=0), [vs, vs, vs, 1.0])
+        assert float((tv / scale).max()) < 5e-3, f"test point values differ: {vr[a][tp]} vs {vo[b][tp]}"
+    return {"same_cell": frac, "same_slot": same_slot, "pos_dp": perr, "vel": verr, "rho": rerr}
+
+
+DAMBREAK_CASES = {
+    # BASELINE configs[0]: the default problem, obstacle (force-feedback body) included
+    "default_84k_obstacle": (0.015, 100, []),
+    # BASELINE configs[1]: 2 M particles, Ferrari
+    "2m_ferrari": (0.0043, 21, ["--deltap", "0.0043", "--density-diffusion", "1", "--num_obstacles", "0"]),
+    # SURVEY section 8 f2 / f3 options, small
+    "mls10_no_diffusion": (0.03, 41, ["--deltap", "0.03", "--density-diffusion", "0", "--mls", "10", "--num_obstacles", "0"]),
+    "brezzi": (0.03, 41, ["--deltap", "0.03", "--density-diffusion", "3", "--num_obstacles", "0"]),
+    "planes": (0.03, 41, ["--deltap", "0.03", "--use_planes", "1", "--num_obstacles", "0"]),
+    "obstacle_ferrari_dp02": (0.02, 100, ["--deltap", "0.02", "--density-diffusion", "1"]),
+}
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("case", sorted(DAMBREAK_CASES))
+def test_dambreak3d_dropin_matches_stock_reference(case, tmp_path):
+    ref, ours = binaries("DamBreak3D")
+    dp, iters, args = DAMBREAK_CASES[case]
+    r, rlog = run(ref, str(tmp_path / "ref"), iters, args)
+    o, olog = run(ours, str(tmp_path / "ours"), iters, args)
+    res = compare(r, o, dp)
+    print(case, r["particle_count"], "particles", res)
+
+
+POISEUILLE_CASES = {
+    "ppH16": (1.0 / 16, 100, ["--ppH", "16"]),
+    "ppH32_monaghan_dyn": (1.0 / 32, 41, ["--ppH", "32", "--viscmodel", "1", "--compvisc", "1"]),
+    "ppH16_colagrossi_geometric": (1.0 / 16, 41, ["--ppH", "16", "--density-diffusion", "2", "--viscavg", "2"]),
+}
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("case", sorted(POISEUILLE_CASES))
+def test_poiseuille_dropin_matches_stock_reference(case, tmp_path):
+    ref, ours = binaries("Poiseuille")
+    dp, iters, args = POISEUILLE_CASES[case]
+    r, _ = run(ref, str(tmp_path / "ref"), iters, args)
+    o, _ = run(ours, str(tmp_path / "ours"), iters, args)
+    res = compare(r, o, dp)
+    print(case, r["particle_count"], "particles", res)

@@ -22,6 +22,8 @@
 #include <stdlib.h>
 #include <mutex>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 // the per-kernel caches below are process-wide and the engines are shared by one host thread per device
 // (SURVEY.md section 8b "Threading")
@@ -34,7 +36,7 @@ static std::mutex g_kernel_cache_lock;
 #endif
 // B200_GATHER_AHEAD=1: the neighbour record of the next list entry is requested before the current one is evaluated
 #ifndef B200_GATHER_AHEAD
-#define B200_GATHER_AHEAD 0
+#define B200_GATHER_AHEAD 1
 #endif
 
 // ---------------------------------------------------------------------------
@@ -132,7 +134,7 @@ struct ListGeom { const ushort *list; uint stride, rows, boundpos; };      // ne
 template<bool WIDE> struct ListOff { typedef uint type; typedef int stype; };
 template<> struct ListOff<true> { typedef unsigned long long type; typedef long long stype; };
 
-template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch, typename Eos>
+template<bool NFLUID, int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, bool AHEAD, typename Lut, typename Fetch, typename Eos>
 __device__ __forceinline__ void
 walk_section(const DevParams &P, const PairConsts &k, const Central &c, const uint index, Lut lut,
 	const ListGeom &L, Fetch fetch, Eos eos, float4 &acc, float3 &xs)
@@ -172,9 +174,9 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		}
 		return base + nd;
 	};
-#if B200_GATHER_AHEAD
+	if (AHEAD) {
 	// software pipeline: the record of entry i+1 is requested before entry i is evaluated, so that a warp has one
-	// gather in flight while it computes (the kernel is latency-bound on exactly that load)
+	// gather in flight while it computes (the gather kernel is latency-bound on exactly that load)
 	uint nd = next_entry();
 	if (nd == NEIBS_END) return;
 	uint j = decode(nd);
@@ -195,7 +197,7 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		np = np2; nv = nv2; j = j2;
 		rx = pcx - np.x; ry = pcy - np.y; rz = pcz - np.z;
 	}
-#else
+	} else {
 	while (true) {
 		const uint nd = next_entry();
 		if (nd == NEIBS_END) break;
@@ -208,11 +210,11 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
 		pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, eos(j, nv), NFLUID, acc, xs);
 	}
-#endif
+	}
 }
 
 // all sections of one particle (forces.cu:759,782,792 in the reference) + finalize; returns the CFL term
-template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, typename Lut, typename Fetch, typename Eos>
+template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, int PF, bool WIDE, bool AHEAD, typename Lut, typename Fetch, typename Eos>
 __device__ __forceinline__ float
 particle_forces(const DevParams &P, const PairConsts &k, const uint index, const ushort4 info, const int type,
 	const float4 pos, const float4 vel, const float4 e, const uint cellHash, const BodyOut &bo, Lut lut,
@@ -231,19 +233,49 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 		// fluid<-fluid then fluid<-boundary; DYN boundary neighbours interact like fluid ones (forces_kernel.def:3717-3726)
 		c.momentum = true;
 		c.xsph = RHODIFF == RHODIFF_RUNTIME && xsph != NULL;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, eos, acc, xs);
-		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, eos, acc, xs);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE, AHEAD>(P, k, c, index, lut, L, fetch, eos, acc, xs);
+		walk_section<false, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE, AHEAD>(P, k, c, index, lut, L, fetch, eos, acc, xs);
 		// write_xsph :3366-3368
 		if (c.xsph) xsph[index] = make_float4(2.0f * xs.x, 2.0f * xs.y, 2.0f * xs.z, 0.0f);
 	} else {
 		// boundary<-fluid: density always, momentum only with force feedback (forces_kernel.def:3634-3667)
 		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
-		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE>(P, k, c, index, lut, L, fetch, eos, acc, xs);
+		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE, AHEAD>(P, k, c, index, lut, L, fetch, eos, acc, xs);
 	}
 	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
 	forces[index] = acc;
 	if (acc_out) *acc_out = acc;
 	return cfl_term;
+}
+
+// Fused integration epilogue: exactly the stand-alone euler kernel's update of this particle (euler_update.cuh), with
+// the forces still in registers. A particle the pair loop skips integrates with its FORCES entry as is.
+__device__ __forceinline__ void
+integrate_epilogue(const DevParams &P, const BodyOut &bo, const uint index, const ushort4 info, const float4 pos, const float4 vel,
+	float4 acc, const bool have_acc, const uint *__restrict__ particleHash, const float4 *__restrict__ forces)
+{
+	if (!bo.eul_step) return;
+	if (!have_acc) acc = forces[index];
+	float4 p = pos, v = vel;
+	if (bo.eul_old_pos) { p = bo.eul_old_pos[index]; v = bo.eul_old_vel[index]; }
+	const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (bo.eul_step == 1)
+		euler_update<1>(P, p, v, acc, info, particleHash, index, euler_dt<1>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
+	else
+		euler_update<2>(P, p, v, acc, info, particleHash, index, euler_dt<2>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
+	bo.eul_new_pos[index] = p;
+	bo.eul_new_vel[index] = v;
+	// the integrated state as the record the NEXT force evaluation gathers (no pack pre-pass between launches)
+	if (bo.eul_new_packed) st_posvel(bo.eul_new_packed + index, p, v);
+#if B200_HOST_ZEROCOPY
+	// B200_HOST_ZEROCOPY (experimental, off): the integrated state also goes straight to the caller's mapped host
+	// buffers - a warp writes 512 contiguous bytes per array over PCIe - so that b200sph_step_host needs no
+	// device-to-host copy (and no copy-engine hand-over) behind the corrector
+	if (bo.eul_host_pos) {
+		__stcs(bo.eul_host_pos + index, p);
+		__stcs(bo.eul_host_vel + index, v);
+	}
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -260,7 +292,7 @@ __device__ __forceinline__ float4 lds_f4(uint a)
 #define B200_HOIST 1
 #endif
 #ifndef B200_MIN_BLOCKS
-#define B200_MIN_BLOCKS 8
+#define B200_MIN_BLOCKS 7
 #endif
 // (the detour through shared memory is what stops ptxas from re-deriving the value from the constant bank)
 struct Pinned { float v[24]; };
@@ -337,35 +369,11 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 			auto eos = [&](const uint j, const float4 nv) {
 				return MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
 			};
-			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE>(P, k, index, info, type, pos,
+			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE, B200_GATHER_AHEAD != 0>(P, k, index, info, type, pos,
 				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, eos, forces,
 				GEN ? bo.xsph : NULL, &acc);
 		}
-		// fused integration epilogue: exactly the stand-alone euler kernel's update of this particle (euler_update.cuh),
-		// with the forces still in registers. A particle the pair loop skips integrates with its FORCES entry as is.
-		if (bo.eul_step) {
-			if (!have_acc) acc = forces[index];
-			float4 p = pos, v = vel;
-			if (bo.eul_old_pos) { p = bo.eul_old_pos[index]; v = bo.eul_old_vel[index]; }
-			const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (bo.eul_step == 1)
-				euler_update<1>(P, p, v, acc, info, particleHash, index, euler_dt<1>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
-			else
-				euler_update<2>(P, p, v, acc, info, particleHash, index, euler_dt<2>(bo.eul_state, bo.eul_dt), bo.eul_bodies, false, none);
-			bo.eul_new_pos[index] = p;
-			bo.eul_new_vel[index] = v;
-			// the integrated state as the record the NEXT force evaluation gathers (no pack pre-pass between launches)
-			if (bo.eul_new_packed) st_posvel(bo.eul_new_packed + index, p, v);
-#if B200_HOST_ZEROCOPY
-			// B200_HOST_ZEROCOPY (experimental, off): the integrated state also goes straight to the caller's mapped host
-			// buffers — a warp writes 512 contiguous bytes per array over PCIe — so that b200sph_step_host needs no
-			// device-to-host copy (and no copy-engine hand-over) behind the corrector
-			if (bo.eul_host_pos) {
-				__stcs(bo.eul_host_pos + index, p);
-				__stcs(bo.eul_host_vel + index, v);
-			}
-#endif
-		}
+		integrate_epilogue(P, bo, index, info, pos, vel, acc, have_acc, particleHash, forces);
 	}
 
 	// block max (maxBlockReduce, device_core.cu:40-59) with warp shuffles
@@ -384,11 +392,80 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 	}
 }
 
+#include "forces_brick.cuh"
+
 // ---------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------
 typedef void (*gather_kernel_t)(const DevParams, const PosVel *, const ushort4 *, const uint *,
 	const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
+typedef void (*brick_kernel_t)(const DevParams, const PosVel *, const ushort4 *, const uint *, const uint *, const uint *,
+	const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint, const uint *, const uint, uint *);
+
+void b200_invalidate_bricks(b200sph_ctx *ctx) { ctx->brick_state = 0; ctx->brick_cell_start = ctx->brick_cell_end = NULL; }
+
+// The list of non-empty bricks for the cell arrays of this neighbour-list build (grid order, so that consecutive bricks
+// share most of their neighbourhood in L2); its length comes back through pinned memory behind an event.
+int b200_build_bricks(b200sph_ctx *ctx, const uint32_t *cell_start, const uint32_t *cell_end)
+{
+	b200_invalidate_bricks(ctx);
+	if (!ctx->use_bricks) return B200SPH_OK;
+	const BrickGrid g = brick_grid(ctx->dp);
+	// a brick sticking out of a periodic COORD1 would need its row split once more: leave those grids to the gather kernel
+	if (g.per1 && g.G1 % BRK_B1 != 0) return B200SPH_OK;
+	const size_t nbricks = (size_t)g.nb1 * g.nb2 * g.nb3;
+	if (nbricks >= 0x7fffffffull) return B200SPH_OK;
+	if (ctx->brick_cap < nbricks) {
+		cudaFree(ctx->brick_list); cudaFree(ctx->brick_flags); ctx->brick_list = NULL; ctx->brick_flags = NULL; ctx->brick_cap = 0;
+		CUDA_TRY(cudaMalloc(&ctx->brick_list, nbricks * sizeof(uint)));
+		CUDA_TRY(cudaMalloc(&ctx->brick_flags, nbricks));
+		ctx->brick_cap = nbricks;
+	}
+	brick_flags_kernel<<<div_up((uint)nbricks, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, cell_start, ctx->brick_flags, (uint)nbricks);
+	KERNEL_TRY();
+	cub::CountingInputIterator<uint> ids(0u);
+	size_t tmp = 0;
+	CUDA_TRY(cub::DeviceSelect::Flagged(NULL, tmp, ids, ctx->brick_flags, ctx->brick_list, ctx->d_brick_count, (int)nbricks, ctx->stream));
+	if (ctx->sort_tmp_bytes < tmp) {
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->sort_tmp); ctx->sort_tmp = NULL; ctx->sort_tmp_bytes = 0;
+		CUDA_TRY(cudaMalloc(&ctx->sort_tmp, tmp));
+		ctx->sort_tmp_bytes = tmp;
+	}
+	tmp = ctx->sort_tmp_bytes;
+	CUDA_TRY(cub::DeviceSelect::Flagged(ctx->sort_tmp, tmp, ids, ctx->brick_flags, ctx->brick_list, ctx->d_brick_count, (int)nbricks, ctx->stream));
+	CUDA_TRY(cudaMemcpyAsync(ctx->h_brick_count, ctx->d_brick_count, sizeof(uint), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaEventRecord(ctx->brick_event, ctx->stream));
+	ctx->brick_state = 1;
+	ctx->brick_cell_start = cell_start; ctx->brick_cell_end = cell_end;
+	return B200SPH_OK;
+}
+
+template<int RHODIFF>
+static brick_kernel_t pick_brick_kernel(bool artvisc, bool laminar, bool multi)
+{
+#define PICKB(A, L, M) return forces_brick_kernel<RHODIFF, A, L, M, false>
+	if (multi) {
+		if (artvisc) { if (laminar) PICKB(true, true, true); else PICKB(true, false, true); }
+		else { if (laminar) PICKB(false, true, true); else PICKB(false, false, true); }
+	} else {
+		if (artvisc) { if (laminar) PICKB(true, true, false); else PICKB(true, false, false); }
+		else { if (laminar) PICKB(false, true, false); else PICKB(false, false, false); }
+	}
+#undef PICKB
+}
+
+// dynamic shared memory opt-in of a brick kernel: once per (kernel, device)
+static int set_brick_smem(const b200sph_ctx *ctx, const void *kernel)
+{
+	static const void *known[128]; static int dev[128]; static int nknown = 0;
+	std::lock_guard<std::mutex> guard(g_kernel_cache_lock);
+	for (int i = 0; i < nknown; ++i) if (known[i] == kernel && dev[i] == ctx->device) return B200SPH_OK;
+	CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
+	CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	if (nknown < 128) { known[nknown] = kernel; dev[nknown] = ctx->device; ++nknown; }
+	return B200SPH_OK;
+}
 
 template<int RHODIFF>
 static void pick_kernels(bool artvisc, bool laminar, bool multi, gather_kernel_t *g /* [wide] */)
@@ -574,6 +651,41 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 	ctx->zc_host_pos = ctx->zc_host_vel = NULL;      // one launch only
 	// 32-bit list offsets unless the list has 2^31 entries or more
 	const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
+	// staged (brick) kernel: when the brick list of the last neighbour-list build describes these cell arrays and the
+	// range is most of the particles (small stripes - multi-GPU edge layers, host-step stripes - stay on the gather kernel)
+	if (ctx->brick_state == 1) {
+		CUDA_TRY(cudaEventSynchronize(ctx->brick_event));
+		ctx->num_bricks = *ctx->h_brick_count;
+		ctx->brick_state = 2;
+	}
+	if (ctx->use_bricks && ctx->brick_state == 2 && ctx->num_bricks > 0 && ctx->brick_cell_start == cell_start && !wide &&
+		(unsigned long long)(to - from) * 2 >= num_particles) {
+		brick_kernel_t bk;
+		if (general) bk = forces_brick_kernel<RHODIFF_RUNTIME, true, true, true, false>;
+		else switch (d.densitydiffusiontype) {
+		case B200SPH_RHODIFF_FERRARI: bk = pick_brick_kernel<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi); break;
+		case B200SPH_RHODIFF_COLAGROSSI: bk = pick_brick_kernel<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi); break;
+		default: bk = pick_brick_kernel<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi); break;
+		}
+		{ const int rc = set_brick_smem(ctx, (const void *)bk); if (rc) return rc; }
+		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
+		CUDA_TRY(cudaMemsetAsync(ctx->d_brick_count + 1, 0, sizeof(uint), ctx->stream));
+		const uint grid = ctx->num_bricks < (uint)ctx->sm_count ? ctx->num_bricks : (uint)ctx->sm_count;
+		bk<<<grid, BRK_THREADS, sizeof(BrickSmem), ctx->stream>>>(general ? dp_launch : ctx->dp, pv, (const ushort4 *)info, hash, cell_start,
+			ctx->brick_cell_end, neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset, ctx->brick_list, ctx->num_bricks,
+			ctx->d_brick_count + 1);
+		KERNEL_TRY();
+		if (num_cfl_blocks) *num_cfl_blocks = nblocks;
+		if (eul && !fuse) {
+			const size_t o = (size_t)from * 16;
+			const int rc = b200sph_euler_ex(ctx, (const char *)eul->old_pos + o, (const char *)eul->old_vel + o, (const char *)info + (size_t)from * 8,
+				hash + from, (const char *)forces + o, args->xsph ? (const char *)args->xsph + o : NULL, (char *)eul->new_pos + o,
+				(char *)eul->new_vel + o, to - from, to - from, eul->dt, eul->step, eul->dt_from_device);
+			if (rc) return rc;
+			if (eul->new_packed) return b200sph_pack_state(ctx, eul->new_pos, eul->new_vel, eul->new_packed, from, to);
+		}
+		return B200SPH_OK;
+	}
 	gather_kernel_t gks[2];
 	if (general) {
 		gks[0] = forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, false>;

@@ -19,8 +19,8 @@ import tempfile
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from hotfile import particle_arrays, read_hotfile  # noqa: E402
+sys.path.insert(0, ROOT)
+from gpusph_b200.hotfile import particle_arrays, read_hotfile  # noqa: E402  (file-format reader only: no engine is loaded)
 
 CONFIGS = {
     # name: (deltap, density-diffusion enum: 0 none, 1 Ferrari, 2 Colagrossi, 3 Brezzi, extra DamBreak3D options

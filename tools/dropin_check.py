@@ -13,9 +13,8 @@ import tempfile
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
-from hotfile import particle_arrays, read_hotfile  # noqa: E402
+from gpusph_b200.hotfile import particle_arrays, read_hotfile  # noqa: E402
 
 
 def run(binp, dp, maxiter, rhodiff, save, obstacles=0):

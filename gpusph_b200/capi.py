@@ -180,6 +180,8 @@ PROTOTYPES = {
     "b200sph_set_rblinearvel": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200sph_set_rbangularvel": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200sph_forces_bodies": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, C.POINTER(_U)]),
+    "b200sph_euler_packed": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, C.c_float, C.c_int, C.c_int]),
+    "b200sph_unpack_state": (C.c_int, [_P, _P, _P, _P, _U, _U]),
     "b200sph_pack_state": (C.c_int, [_P, _P, _P, _P, _U, _U]),
     "b200sph_reduce_rb_forces": (C.c_int, [_P, _P, _P, _P, C.POINTER(_U), C.POINTER(C.c_float), C.POINTER(C.c_float), _U, _U]),
     "b200sph_eos_probe": (C.c_int, [_P, _P, _P, _P, _U]),

@@ -64,7 +64,7 @@ extern "C" int b200sph_calc_hash(b200sph_ctx *ctx, void *pos, uint32_t *hash, ui
 	const void *info, const uint32_t *cdm, uint32_t n)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_bricks(ctx);
+	b200_invalidate_sweep(ctx);
 	if (n == 0) return B200SPH_OK;
 	if (!pos || !hash || !part_index || !info) { b200_set_error("calcHash: null buffer"); return B200SPH_EINVAL; }
 	calc_hash_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (float4 *)pos, hash, part_index,
@@ -91,7 +91,7 @@ extern "C" int b200sph_fix_hash(b200sph_ctx *ctx, uint32_t *hash, uint32_t *part
 	const void *info, const uint32_t *cdm, uint32_t n)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_bricks(ctx);
+	b200_invalidate_sweep(ctx);
 	(void)info;
 	if (n == 0) return B200SPH_OK;
 	if (!part_index) { b200_set_error("fixHash: null buffer"); return B200SPH_EINVAL; }
@@ -180,7 +180,7 @@ static int ensure_sort_scratch(b200sph_ctx *ctx, uint n)
 extern "C" int b200sph_sort(b200sph_ctx *ctx, uint32_t *hash, void *info, uint32_t *part_index, uint32_t n)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_bricks(ctx);
+	b200_invalidate_sweep(ctx);
 	if (n == 0) return B200SPH_OK;
 	if (!hash || !info || !part_index) { b200_set_error("sort: null buffer"); return B200SPH_EINVAL; }
 	int rc = ensure_sort_scratch(ctx, n);
@@ -279,7 +279,7 @@ extern "C" int b200sph_reorder(b200sph_ctx *ctx, uint32_t *cell_start, uint32_t 
 	uint32_t n, uint32_t *new_num_particles)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_bricks(ctx);
+	b200_invalidate_sweep(ctx);
 	(void)sorted_info;
 	if (!cell_start || !cell_end || !sorted_pos || !sorted_vel || !unsorted_pos || !unsorted_vel ||
 		!sorted_hash || !part_index || !new_num_particles) {
@@ -619,6 +619,6 @@ extern "C" int b200sph_build_neibs(b200sph_ctx *ctx, const void *pos, const void
 	build_neibs_kernel<<<div_up(particle_range_end, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp,
 		(const float4 *)pos, sx, sy, sz, (const ushort4 *)info, hash, cell_start, cell_end, neibs_list, particle_range_end, ctx->d_counters);
 	KERNEL_TRY();
-	// work decomposition of the staged pair kernel for these cell ranges (forces_brick.cuh)
-	return b200_build_bricks(ctx, cell_start, cell_end);
+	// work decomposition of the locality-scheduled pair kernel for these cell ranges (forces_sweep.cuh)
+	return b200_build_sweep(ctx, cell_start, cell_end, ncand);
 }

@@ -308,11 +308,19 @@ class IntegrationEngine:
         self.lib = ctx.lib
 
     def basicstep(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
-                  dt: float, step: int) -> None:
-        capi.check(self.lib.b200sph_euler_ex(
+                  dt: float, step: int, new_packed=None) -> None:
+        """new_packed (torch uint8 tensor, 32 bytes per particle) also receives the integrated particles as the pair
+        kernel's neighbour records (b200sph_euler_packed)."""
+        capi.check(self.lib.b200sph_euler_packed(
             self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
             bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES), bufread.ptr(BUFFER_XSPH, False),
-            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, dt, step, 0))
+            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), new_packed.data_ptr() if new_packed is not None else 0,
+            numParticles, particleRangeEnd, dt, step, 0))
+
+    def unpack_state(self, packed: torch.Tensor, bufwrite: BufferList, fromParticle: int, toParticle: int) -> None:
+        """Neighbour records of [from, to) back into POS / VEL (b200sph_unpack_state)."""
+        capi.check(self.lib.b200sph_unpack_state(self.ctx.handle, packed.data_ptr(), bufwrite.ptr(BUFFER_POS),
+                                                 bufwrite.ptr(BUFFER_VEL), fromParticle, toParticle))
 
 
     # ---- moving bodies (src/engine_integration.h:54-68) ----
@@ -340,12 +348,13 @@ class IntegrationEngine:
         self._setf(self.lib.b200sph_set_rbangularvel, v, numbodies, 3)
 
     def basicstep_async(self, bufread: BufferList, bufwrite: BufferList, numParticles: int, particleRangeEnd: int,
-                        step: int) -> None:
+                        step: int, new_packed=None) -> None:
         """basicstep with dt taken from the context's device-resident record (no host round trip)."""
-        capi.check(self.lib.b200sph_euler_ex(
+        capi.check(self.lib.b200sph_euler_packed(
             self.ctx.handle, bufread.ptr(BUFFER_POS), bufread.ptr(BUFFER_VEL), bufread.ptr(BUFFER_INFO),
             bufread.ptr(BUFFER_HASH, False), bufread.ptr(BUFFER_FORCES), bufread.ptr(BUFFER_XSPH, False),
-            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), numParticles, particleRangeEnd, 0.0, step, 1))
+            bufwrite.ptr(BUFFER_POS), bufwrite.ptr(BUFFER_VEL), new_packed.data_ptr() if new_packed is not None else 0,
+            numParticles, particleRangeEnd, 0.0, step, 1))
 
 
 class FilterEngine:

@@ -121,9 +121,19 @@ class CudaBackend:
         self.fw.neibsEngine.buildNeibsList(b, b, n, range_end)
         return self.fw.neibsEngine.getinfo()
 
-    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to, cfl_offset=0, packed=None):
+    def forces(self, pos, vel, info, hashv, cs, nl, forces, cfl, n, frm, to, cfl_offset=0, packed=None, fused=None):
+        """fused = (old_pos, old_vel, new_pos, new_vel, step, new_packed): integrate [frm, to) in the kernel's epilogue with
+        the device-resident dt (b200sph_forces_euler)."""
         b = self._b(pos=pos, vel=vel, info=info, hash=hashv, cs=cs, nl=nl, forces=forces, cfl=cfl)
-        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, cfl_offset, packed=packed)
+        if fused is None:
+            return self.fw.forcesEngine.basicstep(b, b, n, frm, to, cfl_offset, packed=packed)
+        opos, ovel, npos, nvel, step, new_packed = fused
+        return self.fw.forcesEngine.basicstep(b, b, n, frm, to, cfl_offset, step=step, dt_from_device=True, packed=packed,
+                                              euler=(self._b(pos=opos, vel=ovel), self._b(pos=npos, vel=nvel), step, None),
+                                              new_packed=new_packed)
+
+    def unpack_state(self, packed, pos, vel, frm, to):
+        self.fw.integrationEngine.unpack_state(packed, self._b(pos=pos, vel=vel), frm, to)
 
     def pack_state(self, pos, vel, packed, frm, to):
         """pos / vel of [frm, to) interleaved into the pair kernel's neighbour records (b200sph_pack_state)."""
@@ -143,10 +153,10 @@ class CudaBackend:
     def dtreduce_async(self, cfl, nblocks, which):
         self.fw.forcesEngine.dtreduce_async(self._b(cfl=cfl), nblocks, which)
 
-    def euler_async(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, step):
+    def euler_async(self, opos, ovel, info, hashv, forces, npos, nvel, n, range_end, step, new_packed=None):
         rd = self._b(pos=opos, vel=ovel, info=info, hash=hashv, forces=forces)
         wr = self._b(pos=npos, vel=nvel)
-        self.fw.integrationEngine.basicstep_async(rd, wr, n, range_end, step)
+        self.fw.integrationEngine.basicstep_async(rd, wr, n, range_end, step, new_packed=new_packed)
 
     def step_set_dt(self, dt):
         self.fw.forcesEngine.step_set_dt(dt)
@@ -203,7 +213,10 @@ class SlabWorker:
         self.forces_buf = f4()
         # neighbour records of the pair kernel (CUDA engines): made once per force evaluation for own + halo particles,
         # then gathered by both stripes' launches
-        self.packed = torch.empty(A * 32, dtype=torch.uint8, device=dev) if hasattr(self.backend, "pack_state") else None
+        # one per state buffer: packed[i] mirrors (pos[i], vel[i]) of own + halo particles
+        self.packed = [torch.empty(A * 32, dtype=torch.uint8, device=dev) for _ in range(2)] if hasattr(self.backend, "pack_state") else None
+        self._pending_x = [[], []]        # halo updates in flight, per state buffer
+        self._xops = {}                   # cached P2P op lists, per state buffer (rebuilt with the neighbour list)
         nc = p.num_cells
         self.cellstart = torch.empty(nc, dtype=torch.int32, device=dev)
         self.cellend = torch.empty(nc, dtype=torch.int32, device=dev)
@@ -316,6 +329,15 @@ class SlabWorker:
         be = self.backend
         n = self.numParticles
         cur, oth = self.cur, 1 - self.cur
+        # halo updates still in flight land first; with neighbour records the halo particles only live as records
+        # between rebuilds: bring them back into pos / vel, where the hash update below looks for particles that
+        # crossed the slab face (that is how ownership changes, src/Integrator.cc:216-221)
+        self._wait_halo(0)
+        self._wait_halo(1)
+        self._xops = {}
+        records = self.packed is not None and self.device_dt
+        if records and self.iterations > 0 and n > self.numOwn:
+            be.unpack_state(self.packed[cur], self.pos[cur], self.vel[cur], self.numOwn, n)
         # CALCHASH (with the compact device map) + SORT + REORDER  (src/Integrator.cc:93-160)
         be.hash_update(self.iterations == 0, self.pos[cur], self.hash, self.partindex, self.info, self.cdm, n)
         be.sort(self.hash, self.info, self.partindex, n)
@@ -380,60 +402,50 @@ class SlabWorker:
         # BUILDNEIBS for the particles this rank owns (their neighbours include the halo)
         self.last_neibs_info = be.build_neibs(self.pos[self.cur], self.info, self.hash, self.cellstart, self.cellend,
                                               self.neibslist, n, n_own)
-        self.launches += 8
+        if records:
+            be.pack_state(self.pos[self.cur], self.vel[self.cur], self.packed[self.cur], 0, n)
+        self.launches += 9
 
     # ------------------------------------------------------------------ time stepping
-    def _forces(self, which: int, cand: int = 0) -> float:
-        be = self.backend
-        n, n_own = self.numParticles, self.numOwn
-        # striping (reference: --striping, src/GPUWorker.cc:2086-2160): forces of the EDGE stripe first, then its
-        # exchange is enqueued and overlaps with the forces kernel of the INNER stripe
-        e0 = min(self.edge_start, n_own)
-        args = (self.pos[which], self.vel[which], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
-        f = self.forces_buf
-        kw = {}
+    # What crosses the slab faces is the STATE, not the forces. The reference sends the owner's FORCES of the edge layer
+    # to the neighbour, which then integrates its halo copies itself (UPDATE_EXTERNAL, src/GPUWorker.cc:2086-2160);
+    # SURVEY.md section 8e names the alternative used here: the owner integrates its particles - in the epilogue of the
+    # pair kernel - and sends the integrated edge layer (one 32-byte {pos, vel} record per particle instead of a
+    # 16-byte force) into the neighbour's halo range. Halo copies are never integrated locally, so there is no
+    # integration launch over them and no forces exchange sitting between the two stripes of a force evaluation; the
+    # values a rank sees for its halo are the owner's bits, so the run stays bitwise the single-GPU run.
+    def _halo_tensors(self, which: int):
+        """The arrays a halo update of state buffer `which` carries (row = one particle)."""
         if self.packed is not None:
-            be.pack_state(self.pos[which], self.vel[which], self.packed, 0, n)
-            kw["packed"] = self.packed
-            self.launches += 1
+            return [self.packed[which].view(-1, 32)]
+        return [self.pos[which], self.vel[which]]
 
-        def exchange():
-            # UPDATE_EXTERNAL(FORCES): owner's inner-edge forces -> neighbour's halo range
+    def _start_halo_update(self, which: int):
+        """Owner's edge layers -> neighbours' halo ranges for state buffer `which`: one batched NCCL group, enqueued
+        behind the work already on the current stream. The op list is cached until the next rebuild."""
+        ops = self._xops.get(which)
+        if ops is None:
             sends, recvs = [], []
-            if self._left() is not None:
-                sends.append((f[self.edge_left[0]:self.edge_left[0] + self.edge_left[1]], self._left()))
-                recvs.append((f[self.halo_left[0]:self.halo_left[0] + self.halo_left[1]], self._left()))
-            if self._right() is not None:
-                sends.append((f[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
-                recvs.append((f[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
-            return self._exchange_start(sends, recvs)
+            for t in self._halo_tensors(which):
+                if self._left() is not None:
+                    sends.append((t[self.edge_left[0]:self.edge_left[0] + self.edge_left[1]], self._left()))
+                    recvs.append((t[self.halo_left[0]:self.halo_left[0] + self.halo_left[1]], self._left()))
+                if self._right() is not None:
+                    sends.append((t[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
+                    recvs.append((t[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
+            ops = [dist.P2POp(dist.isend, t.view(torch.uint8), peer, self.group) for t, peer in sends if t.numel()]
+            ops += [dist.P2POp(dist.irecv, t.view(torch.uint8), peer, self.group) for t, peer in recvs if t.numel()]
+            self._xops[which] = ops
+        return dist.batch_isend_irecv(ops) if ops else []
 
-        if self._edge_stream is not None and n_own > e0 > 0:
-            # the edge stripe is one cell layer: a quarter of a wave of CTAs. On its own high-priority stream it runs NEXT
-            # TO the inner stripe's grid instead of in front of it; its exchange follows it on that stream
-            main, es = torch.cuda.current_stream(self.device), self._edge_stream
-            ctx = be.fw.ctx
-            es.wait_stream(main)
-            try:
-                ctx.use_stream(es)
-                nb_edge = be.forces(*args, e0, n_own, 0, **kw)
-            finally:
-                ctx.use_stream(main)
-            with torch.cuda.stream(es):
-                works = exchange()
-            nb_inner = be.forces(*args, 0, e0, nb_edge, **kw)
-            with torch.cuda.stream(es):
-                for w_ in works:
-                    w_.wait()
-            main.wait_stream(es)
-        else:
-            nb_edge = be.forces(*args, e0, n_own, 0, **kw) if n_own > e0 else 0
-            works = exchange()
-            nb_inner = be.forces(*args, 0, e0, nb_edge, **kw) if e0 > 0 else 0
-            for w_ in works:
-                w_.wait()
-        nblocks = nb_edge + nb_inner
-        self.launches += 2
+    def _wait_halo(self, which: int):
+        for w_ in self._pending_x[which]:
+            w_.wait()
+        self._pending_x[which] = []
+
+    def _cfl_candidate(self, nblocks: int, cand: int) -> float:
+        """dt candidate of one force evaluation (local CFL maximum; combined over ranks by the caller's scheme)."""
+        be, n_own = self.backend, self.numOwn
         if self.fixed_dt is not None:
             return self.fixed_dt
         if self.device_dt:
@@ -460,37 +472,128 @@ class SlabWorker:
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         return float(t.item())
 
+    def _forces(self, which: int, cand: int = 0, fused=None) -> float:
+        """One force evaluation of the particles this rank owns, on state buffer `which`.
+        fused = (old, step): integrate them in the kernel's epilogue (device dt) from state buffer `old`, in place, the
+        integrated edge layer leaving for the neighbours as soon as the edge stripe's launch is done."""
+        be = self.backend
+        n, n_own = self.numParticles, self.numOwn
+        e0 = min(self.edge_start, n_own)
+        args = (self.pos[which], self.vel[which], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
+        kw = {}
+        if self.packed is not None:
+            kw["packed"] = self.packed[which]
+        kwf = dict(kw)
+        if fused is not None:
+            old, step = fused
+            kwf["fused"] = (self.pos[old], self.vel[old], self.pos[old], self.vel[old], step, self.packed[old])
+        if self._edge_stream is not None and n_own > e0 > 0:
+            # striping (reference: --striping): the EDGE stripe (one cell layer, a quarter of a wave of CTAs) runs on its own
+            # high-priority stream next to the INNER stripe's grid; it is the only one that reads the halo, so it alone
+            # waits for the halo update still in flight for this state buffer
+            main, es = torch.cuda.current_stream(self.device), self._edge_stream
+            ctx = be.fw.ctx
+            es.wait_stream(main)
+            with torch.cuda.stream(es):
+                self._wait_halo(which)
+            try:
+                ctx.use_stream(es)
+                nb_edge = be.forces(*args, e0, n_own, 0, **kwf)
+            finally:
+                ctx.use_stream(main)
+            if fused is not None:
+                with torch.cuda.stream(es):
+                    self._pending_x[fused[0]] = self._start_halo_update(fused[0])
+            nb_inner = be.forces(*args, 0, e0, nb_edge, **kwf)
+            main.wait_stream(es)          # the edge stripe's kernel (the transfer runs on the communicator's stream)
+            self.launches += 2
+        else:
+            self._wait_halo(which)
+            if fused is not None and n_own > e0:
+                nb_edge = be.forces(*args, e0, n_own, 0, **kwf)
+                self._pending_x[fused[0]] = self._start_halo_update(fused[0])
+                nb_inner = be.forces(*args, 0, e0, nb_edge, **kwf) if e0 > 0 else 0
+                nblocks_ = nb_edge + nb_inner
+                self.launches += 2
+                return self._finish_forces(nblocks_, cand)
+            nb_edge, nb_inner = (be.forces(*args, 0, n_own, 0, **kwf) if n_own > 0 else 0), 0
+            if fused is not None:
+                self._pending_x[fused[0]] = self._start_halo_update(fused[0])
+            self.launches += 1
+        return self._finish_forces(nb_edge + nb_inner, cand)
+
+    def _finish_forces(self, nblocks: int, cand: int) -> float:
+        return self._cfl_candidate(nblocks, cand)
+
     def step(self) -> None:
         if self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None:
             self.build_neibs()
         be = self.backend
-        n = self.numParticles
+        n, n_own = self.numParticles, self.numOwn
         cur, oth = self.cur, 1 - self.cur
-        eargs = (self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n)
-        if self.device_dt:
-            # dt of a step only depends on the CFL maxima of the PREVIOUS step (src/GPUSPH.cc:636-699), and nothing before
-            # the first euler needs it: the all-reduce (one per step, both maxima) overlaps with the forces kernel
+        # integration of the particles this rank OWNS (numParticles = n, range end = n_own)
+        eargs = (self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth], n, n_own)
+        if self.device_dt and self.packed is not None:
+            # production path (CUDA engines): neighbour records for both states, corrector fused, nothing read back.
+            # dt of a step only depends on the CFL maxima of the PREVIOUS step (src/GPUSPH.cc:636-699) and nothing before
+            # the first integration needs it: the all-reduce (one per step, both maxima) overlaps with the predictor's
+            # pair kernels, which is why the predictor integrates in a separate (streaming) launch and the corrector,
+            # whose dt is known by then, in the pair kernel's epilogue.
             self._forces(cur, 1)
             self._finish_dt()
-            be.euler_async(*eargs, 1)
-            self._forces(oth, 2)
-            be.euler_async(*eargs, 2)
+            be.euler_async(*eargs, 1, new_packed=self.packed[oth])
+            self._pending_x[oth] = self._start_halo_update(oth)
+            self._forces(oth, 2, fused=(cur, 2))         # state n+1 lands IN PLACE in the buffers of state n
             self.cfl_global.copy_(self.cfl_local)
             self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True
             self._stale = True
+            self.launches += 1
+            oth = cur
+        elif self.device_dt:
+            self._forces(cur, 1)
+            self._finish_dt()
+            be.euler_async(*eargs, 1)
+            self._pending_x[oth] = self._start_halo_update(oth)
+            self._forces(oth, 2)
+            be.euler_async(*eargs, 2)
+            self._pending_x[oth] = self._start_halo_update(oth)
+            self.cfl_global.copy_(self.cfl_local)
+            self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True
+            self._stale = True
+            self.launches += 2
         else:
             dt = self._dt
+            if self.packed is not None:
+                be.pack_state(self.pos[cur], self.vel[cur], self.packed[cur], 0, n)
             dt1 = self._forces(cur)
             be.euler(*eargs, dt / 2, 1)
+            self._pending_x[oth] = self._start_halo_update_arrays(oth)
+            self._wait_halo(oth)
+            if self.packed is not None:
+                be.pack_state(self.pos[oth], self.vel[oth], self.packed[oth], 0, n)
             dt2 = self._forces(oth)
             be.euler(*eargs, dt, 2)
+            self._pending_x[oth] = self._start_halo_update_arrays(oth)
+            self._wait_halo(oth)
             self._t += dt
             if self.fixed_dt is None:
                 self._dt = min(dt1, dt2)
-        self.launches += 3
+            self.launches += 2
         self.cur = oth
         self.iterations += 1
         self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
+
+    def _start_halo_update_arrays(self, which: int):
+        """Host-dt path with the CUDA engines: the halo update carries the pos / vel arrays themselves."""
+        sends, recvs = [], []
+        for t in (self.pos[which], self.vel[which]):
+            if self._left() is not None:
+                sends.append((t[self.edge_left[0]:self.edge_left[0] + self.edge_left[1]], self._left()))
+                recvs.append((t[self.halo_left[0]:self.halo_left[0] + self.halo_left[1]], self._left()))
+            if self._right() is not None:
+                sends.append((t[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
+                recvs.append((t[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
+        return self._exchange_start(sends, recvs)
 
     def download_own(self) -> ParticleArrays:
         n = self.numOwn
@@ -504,5 +607,7 @@ class SlabWorker:
 
     def forces_once(self) -> None:
         """One force evaluation on the current state without exchange (bench.py roofline timing)."""
+        kw = {"packed": self.packed[self.cur]} if (self.packed is not None and self.device_dt) else {}
+        self._wait_halo(self.cur)
         self.backend.forces(self.pos[self.cur], self.vel[self.cur], self.info, self.hash, self.cellstart, self.neibslist,
-                            self.forces_buf, self.cfl, self.numParticles, 0, self.numOwn)
+                            self.forces_buf, self.cfl, self.numParticles, 0, self.numOwn, **kw)

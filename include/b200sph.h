@@ -386,6 +386,18 @@ int b200sph_euler_ex(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
 	void *new_pos, void *new_vel,
 	uint32_t num_particles, uint32_t particle_range_end, float dt, int step, int dt_from_device);
 
+/* b200sph_euler_ex that ALSO writes the integrated particles as the pair kernel's 32-byte neighbour records
+ * (b200sph_forces_args.packed) into new_packed[0 .. particle_range_end) (no reference counterpart; saves the
+ * b200sph_pack_state pass before the next force evaluation). new_packed == NULL: exactly b200sph_euler_ex. */
+int b200sph_euler_packed(b200sph_ctx *ctx, const void *old_pos, const void *old_vel,
+	const void *info, const uint32_t *hash, const void *forces, const void *xsph,
+	void *new_pos, void *new_vel, void *new_packed,
+	uint32_t num_particles, uint32_t particle_range_end, float dt, int step, int dt_from_device);
+/* the inverse of b200sph_pack_state: records of [from_particle, to_particle) back into pos / vel (multi-GPU: the halo
+ * particles only live as records between neighbour rebuilds, gpusph_b200/multigpu.py) */
+int b200sph_unpack_state(b200sph_ctx *ctx, const void *packed, void *pos, void *vel,
+	uint32_t from_particle, uint32_t to_particle);
+
 /* ---- filter engines and post-processing ---------
  * AbstractFilterEngine::process for SHEPARD_FILTER and MLS_FILTER (src/engine_filter.h:75-82;
  * src/cuda/forces.cu:1026-1122; kernels src/cuda/forces_kernel.cu:418-507, 509-721): density of every fluid

@@ -51,7 +51,7 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
                 kinvisc: float = 0.0, viscavgop: int = capi.AVG_ARITHMETIC,
                 artvisccoeff: float = 0.3, dtadaptfactor: float = 0.3, fluids=None,
                 viscmodel: int = capi.VISCMODEL_MORRIS, compvisc: int = capi.COMPVISC_KINEMATIC, bulkvisc: float = 0.0,
-                simflags: int = capi.ENABLE_DTADAPT, epsxsph: float = 0.5) -> capi.Params:
+                simflags: int = capi.ENABLE_DTADAPT, epsxsph: float = 0.5, maxfall: float = 1.0) -> capi.Params:
     """Build b200sph_params the way ProblemCore + the engines' setconstants derive them."""
     p = capi.Params()
     p.abi_version = capi.ABI_VERSION
@@ -133,10 +133,34 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
         p.visc2coeff[f] = (fluids[f - 1].get("bulkvisc", bulkvisc) if f else bulkvisc)
     # Lennard-Jones defaults of ProblemCore::initialize (src/ProblemCore.cc:121-140, physparams.h:398-403)
     p.r0 = np.float32(deltap)
-    p.dcoeff = np.float32(5.0 * math.sqrt(sum(float(g) ** 2 for g in gravity)))
+    # dcoeff = 5 g H: H = 1 in ProblemCore, the problem's maximum fall height with the problem API (DamBreak3D: setMaxFall(0.4);
+    # src/problem_api/ProblemAPI_1.cc:322-326)
+    p.dcoeff = np.float32(np.float32(5.0) * np.float32(math.sqrt(sum(float(g) ** 2 for g in gravity))) * np.float32(maxfall))
     p.p1coeff, p.p2coeff = 12.0, 6.0
     p.partsurf = 0.0
     return p
+
+
+def universe_box_planes(p: capi.Params, origin, size):
+    """The six planes of ProblemAPI<1>::makeUniverseBox (src/problem_api/ProblemAPI_1.cc:1329-1365) as plane_t triples
+    (unit normal, cell, in-cell position) the way ProblemCore::implicit_plane builds them (src/ProblemCore.cc:945-963): the
+    reference point of a plane a x + b y + c z + d = 0 is the point of the plane closest to the centre of the domain."""
+    origin = np.asarray(origin, dtype=np.float64)
+    size = np.asarray(size, dtype=np.float64)
+    lo, hi = origin, origin + size
+    mid = origin + size / 2
+    G = np.array([p.grid_size[a] for a in range(3)], dtype=np.int64)
+    cs = size / G
+    out = []
+    for a in range(3):
+        for sign, d in ((1.0, -lo[a]), (-1.0, hi[a])):
+            n = np.zeros(3)
+            n[a] = sign
+            point = mid - (np.dot(mid, n) + d) * n
+            g = np.minimum(np.maximum(np.floor((point - origin) / cs).astype(np.int64), 0), G - 1)
+            local = (point - origin - (g + 0.5) * cs).astype(np.float32)
+            out.append((tuple(n.astype(np.float32)), tuple(int(x) for x in g), tuple(float(x) for x in local)))
+    return out
 
 
 def initial_dt(p: capi.Params) -> float:

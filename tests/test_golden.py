@@ -20,7 +20,7 @@ import pytest
 
 import oracle_binding as ob
 from gpusph_b200 import capi
-from gpusph_b200.problems import ParticleArrays, global_positions, initial_dt, make_params
+from gpusph_b200.problems import ParticleArrays, global_positions, initial_dt, make_params, universe_box_planes
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
 
@@ -35,10 +35,39 @@ def load(path):
                       float(d[f"t_{it}"]), float(d[f"dt_{it}"]))
     n = states[0][0].n
     # DamBreak3D: origin 0, size 1.6 x 0.67 x 0.6 (src/problems/DamBreak3D.cu:107-122), neiblist 128,
-    # artificial viscosity, c0 = 20, gamma = 7, Colagrossi xi = 0.1 / Ferrari coefficient 0.1 (:46,:95)
+    # artificial viscosity, c0 = 20, gamma = 7, diffusion coefficient 0.1 whatever the model (:46,:95), H = 0.4 (:82)
+    flags = capi.ENABLE_DTADAPT | capi.ENABLE_REPACKING | (capi.ENABLE_PLANES if _opt(d, "use_planes") else 0)
     params = make_params(origin=(0, 0, 0), size=(1.6, 0.67, 0.6), deltap=dp, allocated_particles=n,
-                         densitydiffusion=int(d["rhodiff"]), density_diff_coeff=0.1 if int(d["rhodiff"]) else None)
+                         densitydiffusion=int(d["rhodiff"]), density_diff_coeff=0.1 if int(d["rhodiff"]) else None,
+                         simflags=flags, maxfall=0.4)
     return params, states
+
+
+def _opt(d, key):
+    return int(d[key]) if key in d.files else 0
+
+
+def single_step_rho_tol(path):
+    """rho~ tolerance of the 20 -> 21 step. With --mls N iteration 20 applies the MLS filter first: a 4 x 4 moment matrix
+    inverted in float per particle (src/cuda/forces_kernel.cu:509-721), whose result moves by ~1e-6 with the order of
+    the float operations (FMA contraction of the GPU build vs the CPU oracle): 2e-6 there, 2e-7 otherwise."""
+    return 2e-6 if _opt(np.load(path), "mls") else None
+
+
+def options(path, params):
+    """Worker / OracleWorker keyword arguments of a fixture's DamBreak3D options: --mls N adds the MLS filter every N
+    iterations (src/problems/DamBreak3D.cu:63-71), --use_planes 1 replaces the boundary box by the six planes of the
+    universe box (:127-130). The obstacle of --num_obstacles 1 is a force-feedback body that never moves (no callback,
+    :169-180): its particles carry FG_MOVING_BOUNDARY | FG_COMPUTE_FORCE and are integrated like fixed DYN boundaries."""
+    d = np.load(path)
+    kw_gpu, kw_cpu = {}, {}
+    if _opt(d, "mls"):
+        from gpusph_b200.engines import MLS_FILTER
+        kw_gpu["filters"] = {MLS_FILTER: _opt(d, "mls")}
+        kw_cpu["filters"] = {"MLS_FILTER": _opt(d, "mls")}
+    if _opt(d, "use_planes"):
+        kw_gpu["planes"] = kw_cpu["planes"] = universe_box_planes(params, (0, 0, 0), (1.6, 0.67, 0.6))
+    return kw_gpu, kw_cpu
 
 
 def ids_of(info):
@@ -113,9 +142,9 @@ def test_oracle_reproduces_reference_single_step(path):
     params, states = load(path)
     s20, _, dt20 = states[20]
     s21, _, dt21 = states[21]
-    w = ob.OracleWorker(params, s20, start_iteration=20, dt=dt20)
+    w = ob.OracleWorker(params, s20, start_iteration=20, dt=dt20, **options(path, params)[1])
     w.step()
-    compare(params, w.download(), s21, pos_tol_dp=2e-6, vel_tol=2e-5, exact_order=True)
+    compare(params, w.download(), s21, pos_tol_dp=2e-6, vel_tol=2e-5, exact_order=True, rho_tol=single_step_rho_tol(path))
     assert w.dt == pytest.approx(dt21, rel=1e-5)
     assert w.neibs_info.has_too_many_neibs == -1
 
@@ -126,7 +155,7 @@ def test_oracle_reproduces_reference_ten_steps(path, start):
     params, states = load(path)
     s0, t0, dt0 = states[start]
     s1, t1, dt1 = states[start + 10]
-    w = ob.OracleWorker(params, s0, start_iteration=start, dt=dt0)
+    w = ob.OracleWorker(params, s0, start_iteration=start, dt=dt0, **options(path, params)[1])
     for _ in range(10):
         w.step()
     assert w.t == pytest.approx(t1 - t0, rel=1e-5)
@@ -141,9 +170,9 @@ def test_gpu_reproduces_reference_single_step(path):
     params, states = load(path)
     s20, _, dt20 = states[20]
     s21, _, dt21 = states[21]
-    w = Worker(params, s20, 0, start_iteration=20, dt=dt20, clobber=True)
+    w = Worker(params, s20, 0, start_iteration=20, dt=dt20, clobber=True, **options(path, params)[0])
     w.step()
-    compare(params, w.download(), s21, pos_tol_dp=2e-6, vel_tol=2e-5, exact_order=True)
+    compare(params, w.download(), s21, pos_tol_dp=2e-6, vel_tol=2e-5, exact_order=True, rho_tol=single_step_rho_tol(path))
     assert w.dt == pytest.approx(dt21, rel=1e-5)
     assert w.last_neibs_info.has_too_many_neibs == -1
 
@@ -156,7 +185,7 @@ def test_gpu_reproduces_reference_ten_steps(path, start):
     params, states = load(path)
     s0, t0, dt0 = states[start]
     s1, t1, dt1 = states[start + 10]
-    w = Worker(params, s0, 0, start_iteration=start, dt=dt0, clobber=True)
+    w = Worker(params, s0, 0, start_iteration=start, dt=dt0, clobber=True, **options(path, params)[0])
     for _ in range(10):
         w.step()
     assert w.t == pytest.approx(t1 - t0, rel=1e-5)

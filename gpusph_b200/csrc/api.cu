@@ -124,11 +124,6 @@ extern "C" int b200sph_create(const b200sph_params *p, b200sph_ctx **out)
 	fill_devparams(p, &ctx->dp);
 	CUDA_TRY(cudaGetDevice(&ctx->device));
 	ctx->stream = 0;
-	{ const char *e = getenv("B200SPH_FORCES_SWEEP"); ctx->use_sweep = e ? atoi(e) : 1; }
-	{ int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device)); ctx->sm_count = sms > 0 ? sms : 148; }
-	CUDA_TRY(cudaMalloc(&ctx->sweep_queues, 1024 * sizeof(uint)));
-	CUDA_TRY(cudaMallocHost(&ctx->h_sweep_count, sizeof(uint)));
-	CUDA_TRY(cudaEventCreateWithFlags(&ctx->sweep_event, cudaEventDisableTiming));
 	CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(NeibsCounters)));
 	CUDA_TRY(cudaMalloc(&ctx->d_scalar, 4 * sizeof(float)));
 	CUDA_TRY(cudaMalloc(&ctx->d_flag, sizeof(int)));
@@ -152,9 +147,8 @@ extern "C" int b200sph_destroy(b200sph_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	b200_hoststep_destroy(ctx);
 	cudaFree(ctx->sort_tmp); cudaFree(ctx->keys_in); cudaFree(ctx->keys_out); cudaFree(ctx->vals_out);
-	cudaFree(ctx->info_tmp); cudaFree(ctx->pv[0]); cudaFree(ctx->pv[1]); cudaFree(ctx->soa);
-	cudaFree(ctx->sweep_chunks); cudaFree(ctx->sweep_counts); cudaFree(ctx->sweep_queues); cudaFreeHost(ctx->h_sweep_count);
-	if (ctx->sweep_event) cudaEventDestroy(ctx->sweep_event);
+	cudaFree(ctx->info_tmp); cudaFree(ctx->pv[0]); cudaFree(ctx->pv[1]);
+
 	cudaFree(ctx->d_step); cudaFreeHost(ctx->h_step); cudaFree(ctx->d_bodies); cudaFreeHost(ctx->h_bodies);
 	cudaFree(ctx->d_counters); cudaFree(ctx->d_scalar); cudaFree(ctx->d_flag);
 	cudaFreeHost(ctx->h_scalar); cudaFreeHost(ctx->h_flag);

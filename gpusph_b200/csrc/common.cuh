@@ -126,15 +126,6 @@ struct b200sph_ctx {
 	// scratch (grown on demand)
 	void *sort_tmp; size_t sort_tmp_bytes;
 	uint64_t *keys_in, *keys_out; uint32_t *vals_out; void *info_tmp; size_t sort_cap;
-	// chunk table of the locality-scheduled pair kernel (forces_sweep.cuh), rebuilt with the neighbour list
-	void *sweep_chunks; size_t sweep_chunk_cap;         // SweepChunk[]
-	uint *sweep_counts; size_t sweep_rw_cap;            // per row-window: chunk counts, then (scan) offsets; [nrw] = total
-	uint *sweep_queues;                                 // one claim counter per SM
-	uint *h_sweep_count; cudaEvent_t sweep_event;
-	int sweep_state;                                    // 0 none, 1 count copy in flight, 2 valid
-	uint num_chunks; const uint32_t *sweep_cell_start;
-	int use_sweep, sm_count;                            // env B200SPH_FORCES_SWEEP (default 1)
-	float *soa; size_t soa_cap;             // candidate coordinates as three arrays (neibs.cu split_pos_kernel)
 	PosVel *pv[2]; size_t pv_cap[2];        // context-owned neighbour records (forces.cu b200_packed_scratch)
 	NeibsCounters *d_counters;
 	float *d_scalar;                        // device scalar for reductions
@@ -213,8 +204,6 @@ __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
 
 // ---- internal launchers implemented in the .cu files ----
 int b200_packed_scratch(b200sph_ctx *ctx, int which, uint32_t n, PosVel **out);   // forces.cu
-int b200_build_sweep(b200sph_ctx *ctx, const uint32_t *cell_start, const uint32_t *cell_end, uint32_t num_particles);   // forces.cu
-void b200_invalidate_sweep(b200sph_ctx *ctx);
 void b200_hoststep_destroy(b200sph_ctx *ctx);
 int b200_euler_bodies(b200sph_ctx *ctx, const uint32_t *hash, const BodyData **out);   // api.cu
 int b200_zero_copy_supported(void);   // forces.cu: was the pair kernel compiled with the zero-copy epilogue?

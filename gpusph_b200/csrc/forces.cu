@@ -391,94 +391,12 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 	}
 }
 
-#include "forces_sweep.cuh"
 
 // ---------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------
 typedef void (*gather_kernel_t)(const DevParams, const PosVel *, const ushort4 *, const uint *,
 	const uint *, const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint);
-typedef void (*sweep_kernel_t)(const DevParams, const PosVel *, const ushort4 *, const uint *, const uint *,
-	const ushort *, float4 *, float *, const BodyOut, const uint, const uint, const uint, const SweepChunk *, const uint, uint *, const uint);
-
-void b200_invalidate_sweep(b200sph_ctx *ctx) { ctx->sweep_state = 0; ctx->sweep_cell_start = NULL; }
-
-// The chunk table for the cell arrays of this neighbour-list build: chunks per row-window, exclusive scan, fill; the
-// total comes back through pinned memory behind an event (nothing waits for it here).
-int b200_build_sweep(b200sph_ctx *ctx, const uint32_t *cell_start, const uint32_t *cell_end, uint32_t num_particles)
-{
-	b200_invalidate_sweep(ctx);
-	if (!ctx->use_sweep) return B200SPH_OK;
-	const SweepGrid g = sweep_grid(ctx->dp);
-	const size_t nrw = (size_t)g.nw * g.G2 * g.G3;
-	if (nrw >= 0x7fffffffull) return B200SPH_OK;
-	if (ctx->sweep_rw_cap < nrw + 1) {
-		cudaFree(ctx->sweep_counts); ctx->sweep_counts = NULL; ctx->sweep_rw_cap = 0;
-		CUDA_TRY(cudaMalloc(&ctx->sweep_counts, (nrw + 1) * sizeof(uint)));
-		ctx->sweep_rw_cap = nrw + 1;
-	}
-	const size_t max_chunks = (size_t)num_particles / 32 + nrw + 1;      // every row-window adds at most one partial chunk
-	if (ctx->sweep_chunk_cap < max_chunks) {
-		cudaFree(ctx->sweep_chunks); ctx->sweep_chunks = NULL; ctx->sweep_chunk_cap = 0;
-		const size_t cap = max_chunks + max_chunks / 8;
-		CUDA_TRY(cudaMalloc(&ctx->sweep_chunks, cap * sizeof(SweepChunk)));
-		ctx->sweep_chunk_cap = cap;
-	}
-	cudaStream_t s = ctx->stream;
-	CUDA_TRY(cudaMemsetAsync(ctx->sweep_counts + nrw, 0, sizeof(uint), s));
-	sweep_count_kernel<<<div_up((uint)nrw, BLOCK_STREAM), BLOCK_STREAM, 0, s>>>(ctx->dp, cell_start, cell_end, ctx->sweep_counts, (uint)nrw);
-	KERNEL_TRY();
-	size_t tmp = 0;
-	CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmp, ctx->sweep_counts, ctx->sweep_counts, (int)(nrw + 1), s));
-	if (ctx->sort_tmp_bytes < tmp) {
-		CUDA_TRY(cudaStreamSynchronize(s));
-		cudaFree(ctx->sort_tmp); ctx->sort_tmp = NULL; ctx->sort_tmp_bytes = 0;
-		CUDA_TRY(cudaMalloc(&ctx->sort_tmp, tmp));
-		ctx->sort_tmp_bytes = tmp;
-	}
-	tmp = ctx->sort_tmp_bytes;
-	CUDA_TRY(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp, tmp, ctx->sweep_counts, ctx->sweep_counts, (int)(nrw + 1), s));
-	sweep_fill_kernel<<<div_up((uint)nrw, BLOCK_STREAM), BLOCK_STREAM, 0, s>>>(ctx->dp, cell_start, cell_end, ctx->sweep_counts,
-		(SweepChunk *)ctx->sweep_chunks, (uint)nrw);
-	KERNEL_TRY();
-	CUDA_TRY(cudaMemcpyAsync(ctx->h_sweep_count, ctx->sweep_counts + nrw, sizeof(uint), cudaMemcpyDeviceToHost, s));
-	CUDA_TRY(cudaEventRecord(ctx->sweep_event, s));
-	ctx->sweep_state = 1;
-	ctx->sweep_cell_start = cell_start;
-	return B200SPH_OK;
-}
-
-template<int RHODIFF>
-static sweep_kernel_t pick_sweep_kernel(bool artvisc, bool laminar, bool multi)
-{
-#define PICKS(A, L, M) return forces_sweep_kernel<RHODIFF, A, L, M, false>
-	if (multi) {
-		if (artvisc) { if (laminar) PICKS(true, true, true); else PICKS(true, false, true); }
-		else { if (laminar) PICKS(false, true, true); else PICKS(false, false, true); }
-	} else {
-		if (artvisc) { if (laminar) PICKS(true, true, false); else PICKS(true, false, false); }
-		else { if (laminar) PICKS(false, true, false); else PICKS(false, false, false); }
-	}
-#undef PICKS
-}
-
-// persistent grid of a sweep kernel: resident CTAs per SM (occupancy query, once per kernel and device) x SMs
-static int sweep_ctas_per_sm(const b200sph_ctx *ctx, const void *kernel, int *out)
-{
-	static const void *known[128]; static int dev[128]; static int val[128]; static int nknown = 0;
-	std::lock_guard<std::mutex> guard(g_kernel_cache_lock);
-	for (int i = 0; i < nknown; ++i) if (known[i] == kernel && dev[i] == ctx->device) { *out = val[i]; return B200SPH_OK; }
-	// as much of the SM as possible stays L1: the kernel's static shared memory is a few KB per CTA
-	CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 16));
-	int n = 0;
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, BLOCK_FORCES, 0));
-	if (n < 1) n = 1;
-	if (n > SWEEP_CTAS_PER_SM) n = SWEEP_CTAS_PER_SM;
-	if (nknown < 128) { known[nknown] = kernel; dev[nknown] = ctx->device; val[nknown] = n; ++nknown; }
-	*out = n;
-	return B200SPH_OK;
-}
-
 template<int RHODIFF>
 static void pick_kernels(bool artvisc, bool laminar, bool multi, gather_kernel_t *g /* [wide] */)
 {
@@ -663,44 +581,6 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 	ctx->zc_host_pos = ctx->zc_host_vel = NULL;      // one launch only
 	// 32-bit list offsets unless the list has 2^31 entries or more
 	const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
-	// locality-scheduled kernel: when the chunk table of the last neighbour-list build describes these cell arrays and
-	// the range is most of the particles (small stripes - multi-GPU edge layers, host-step stripes - stay on the plain
-	// kernel, whose grid covers just the range)
-	if (ctx->sweep_state == 1) {
-		CUDA_TRY(cudaEventSynchronize(ctx->sweep_event));
-		ctx->num_chunks = *ctx->h_sweep_count;
-		ctx->sweep_state = 2;
-	}
-	if (ctx->use_sweep && ctx->sweep_state == 2 && ctx->num_chunks > 0 && ctx->sweep_cell_start == cell_start && !wide &&
-		(unsigned long long)(to - from) * 2 >= num_particles) {
-		sweep_kernel_t sk;
-		if (general) sk = forces_sweep_kernel<RHODIFF_RUNTIME, true, true, true, false>;
-		else switch (d.densitydiffusiontype) {
-		case B200SPH_RHODIFF_FERRARI: sk = pick_sweep_kernel<B200SPH_RHODIFF_FERRARI>(artvisc, laminar, multi); break;
-		case B200SPH_RHODIFF_COLAGROSSI: sk = pick_sweep_kernel<B200SPH_RHODIFF_COLAGROSSI>(artvisc, laminar, multi); break;
-		default: sk = pick_sweep_kernel<B200SPH_RHODIFF_NONE>(artvisc, laminar, multi); break;
-		}
-		int per_sm = 1;
-		{ const int rc = sweep_ctas_per_sm(ctx, (const void *)sk, &per_sm); if (rc) return rc; }
-		const uint nq = (uint)(ctx->sm_count < 1024 ? ctx->sm_count : 1024);
-		if (cfl) CUDA_TRY(cudaMemsetAsync(cfl + cfl_offset, 0, nblocks * sizeof(float), ctx->stream));
-		CUDA_TRY(cudaMemsetAsync(ctx->sweep_queues, 0, nq * sizeof(uint), ctx->stream));
-		const uint want = (ctx->num_chunks + SWEEP_WARPS - 1) / SWEEP_WARPS, full = (uint)(ctx->sm_count * per_sm);
-		sk<<<want < full ? want : full, BLOCK_FORCES, 0, ctx->stream>>>(general ? dp_launch : ctx->dp, pv, (const ushort4 *)info, hash, cell_start,
-			neibs_list, (float4 *)forces, cfl, bo, from, to, cfl_offset, (const SweepChunk *)ctx->sweep_chunks, ctx->num_chunks,
-			ctx->sweep_queues, nq);
-		KERNEL_TRY();
-		if (num_cfl_blocks) *num_cfl_blocks = nblocks;
-		if (eul && !fuse) {
-			const size_t o = (size_t)from * 16;
-			const int rc = b200sph_euler_ex(ctx, (const char *)eul->old_pos + o, (const char *)eul->old_vel + o, (const char *)info + (size_t)from * 8,
-				hash + from, (const char *)forces + o, args->xsph ? (const char *)args->xsph + o : NULL, (char *)eul->new_pos + o,
-				(char *)eul->new_vel + o, to - from, to - from, eul->dt, eul->step, eul->dt_from_device);
-			if (rc) return rc;
-			if (eul->new_packed) return b200sph_pack_state(ctx, eul->new_pos, eul->new_vel, eul->new_packed, from, to);
-		}
-		return B200SPH_OK;
-	}
 	gather_kernel_t gks[2];
 	if (general) {
 		gks[0] = forces_gather_kernel<RHODIFF_RUNTIME, true, true, true, false>;

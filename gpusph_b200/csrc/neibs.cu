@@ -64,7 +64,6 @@ extern "C" int b200sph_calc_hash(b200sph_ctx *ctx, void *pos, uint32_t *hash, ui
 	const void *info, const uint32_t *cdm, uint32_t n)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_sweep(ctx);
 	if (n == 0) return B200SPH_OK;
 	if (!pos || !hash || !part_index || !info) { b200_set_error("calcHash: null buffer"); return B200SPH_EINVAL; }
 	calc_hash_kernel<<<div_up(n, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp, (float4 *)pos, hash, part_index,
@@ -91,7 +90,6 @@ extern "C" int b200sph_fix_hash(b200sph_ctx *ctx, uint32_t *hash, uint32_t *part
 	const void *info, const uint32_t *cdm, uint32_t n)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_sweep(ctx);
 	(void)info;
 	if (n == 0) return B200SPH_OK;
 	if (!part_index) { b200_set_error("fixHash: null buffer"); return B200SPH_EINVAL; }
@@ -180,7 +178,6 @@ static int ensure_sort_scratch(b200sph_ctx *ctx, uint n)
 extern "C" int b200sph_sort(b200sph_ctx *ctx, uint32_t *hash, void *info, uint32_t *part_index, uint32_t n)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_sweep(ctx);
 	if (n == 0) return B200SPH_OK;
 	if (!hash || !info || !part_index) { b200_set_error("sort: null buffer"); return B200SPH_EINVAL; }
 	int rc = ensure_sort_scratch(ctx, n);
@@ -279,7 +276,6 @@ extern "C" int b200sph_reorder(b200sph_ctx *ctx, uint32_t *cell_start, uint32_t 
 	uint32_t n, uint32_t *new_num_particles)
 {
 	CHECK_CTX(ctx);
-	b200_invalidate_sweep(ctx);
 	(void)sorted_info;
 	if (!cell_start || !cell_end || !sorted_pos || !sorted_vel || !unsorted_pos || !unsorted_vel ||
 		!sorted_hash || !part_index || !new_num_particles) {
@@ -339,9 +335,10 @@ __device__ __forceinline__ bool too_many_neibs(const DevParams &P, uint nf, uint
 #ifndef B200_NL_LOAD_EL
 #define B200_NL_LOAD_EL 0
 #endif
-// B200_NL_PRUNE: skip neighbour cells that lie entirely beyond the search radius of the particle (see the kernel)
-#ifndef B200_NL_PRUNE
-#define B200_NL_PRUNE 1
+// B200_NL_GROUP4: distance tests four candidates at a time in the uniform-cell fast path (written at the end of round 1,
+// not yet measured on a GPU: off)
+#ifndef B200_NL_GROUP4
+#define B200_NL_GROUP4 0
 #endif
 __device__ __forceinline__ void st_list(ushort *p, const ushort v)
 {
@@ -364,33 +361,8 @@ __device__ __forceinline__ float4 ld_cand(const float4 *p)
 #endif
 }
 
-// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE-rounded operations per instruction) ----
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2_bcast(const float a) { f32x2 r; asm("mov.b64 %0, {%1,%1};" : "=l"(r) : "f"(a)); return r; }
-__device__ __forceinline__ void f2_unpack(const f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 f2_sub(const f32x2 a, const f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 f2_mul(const f32x2 a, const f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 f2_fma(const f32x2 a, const f32x2 b, const f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 ldg_f2(const float *p) { f32x2 v; asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
-
-// Candidate coordinates as three separate arrays (private scratch of the context, refreshed by every list build):
-// two CONSECUTIVE candidates of a cell are one aligned 64-bit load per coordinate, i.e. exactly the operand of the
-// packed instructions above. An inactive particle (non-finite mass, reference :612) gets x = NaN: its distance test
-// fails by itself, the list builder never looks at w.
-__global__ void __launch_bounds__(BLOCK_STREAM)
-split_pos_kernel(const float4 *__restrict__ pos, float *__restrict__ px, float *__restrict__ py, float *__restrict__ pz, const uint n)
-{
-	const uint i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const float4 p = pos[i];
-	px[i] = inactive_w(p.w) ? __int_as_float(0x7fc00000) : p.x;
-	py[i] = p.y;
-	pz[i] = p.z;
-}
-
 __global__ void __launch_bounds__(BLOCK_STREAM)
 build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict__ posArray,
-	const float *__restrict__ posX, const float *__restrict__ posY, const float *__restrict__ posZ,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const uint *__restrict__ cellEnd,
 	ushort *__restrict__ neibsList, const uint numParticles, NeibsCounters *__restrict__ counters)
@@ -433,22 +405,6 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 				const float px = __fmaf_rn(-(float)x, P.cellSize[0], pos.x);
 				const float py = __fmaf_rn(-(float)y, P.cellSize[1], pos.y);
 				const float pz = __fmaf_rn(-(float)z, P.cellSize[2], pos.z);
-#if B200_NL_PRUNE
-				// Cells whose box lies entirely beyond the search radius of THIS particle cannot contribute (8 corner and
-				// 12 edge cells of the 27: about half / a fifth of the visits). The box of the neighbour cell, in the
-				// coordinates px,py,pz are already in, is [-cs/2, cs/2]^3; calcHash keeps every particle inside its cell's
-				// box to within rounding EXCEPT in cells on a non-periodic domain face, where particles that left the
-				// domain are clamped (:257-262): those cells are never pruned. The comparison carries a 1e-4 relative
-				// margin, orders of magnitude above any rounding of the exact distance test it anticipates.
-				if (((x != 0) + (y != 0) + (z != 0)) >= 2) {
-					const bool onface = (!(P.periodic & 1) && (gx == 0 || gx == P.gridSize[0] - 1)) ||
-						(!(P.periodic & 2) && (gy == 0 || gy == P.gridSize[1] - 1)) ||
-						(!(P.periodic & 4) && (gz == 0 || gz == P.gridSize[2] - 1));
-					const float dx = fmaxf(fabsf(px) - 0.5f * P.cellSize[0], 0.0f), dy = fmaxf(fabsf(py) - 0.5f * P.cellSize[1], 0.0f),
-						dz = fmaxf(fabsf(pz) - 0.5f * P.cellSize[2], 0.0f);
-					if (!onface && dx * dx + dy * dy + dz * dz > R2 * 1.0001f) continue;
-				}
-#endif
 				bool encode_cell = true;
 				int neib_type = PT_FLUID;
 				// Particles of a cell are sorted by type (sort key: cell, type, id), so first == last type means the
@@ -472,48 +428,42 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					}
 				};
 				if (uniform) {
-					// one particle type in the whole cell (the common case): nothing but the distance test per candidate,
-					// two candidates per packed instruction (FADD2 / FMUL2 / FFMA2 round each half like the scalar
-					// instruction, so r2 is bit for bit the reference's x*x + y*y + z*z as nvcc contracts it).
+					// one particle type in the whole cell (the common case): nothing but the distance test per candidate.
+					// The empty asm keeps the cell's base pointer in registers (otherwise it is re-derived from the
+					// constant bank for every candidate).
+					const float4 *cand = posArray + bucketStart;
+					asm volatile("" : "+l"(cand));
 					const uint count = bucketEnd - bucketStart;
 					const uint self = index - bucketStart;                              // >= count when in another cell
-					// candidate k (0-based in the cell) passes: :553 not self (:612 inactive candidates carry NaN)
-					auto test1 = [&](const uint k) {
-						const float rx = __fsub_rn(px, __ldg(posX + bucketStart + k)), ry = __fsub_rn(py, __ldg(posY + bucketStart + k)),
-							rz = __fsub_rn(pz, __ldg(posZ + bucketStart + k));
-						const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
-						if (r2 < R2 && k != self) append(bucketStart + k, t_first);          // :386-392
-					};
 					uint k = 0;
-					if ((bucketStart & 1u) && count) { test1(0); k = 1; }                // 64-bit alignment of the pairs
-					const float *cx = posX + bucketStart, *cy = posY + bucketStart, *cz = posZ + bucketStart;
-					asm volatile("" : "+l"(cx), "+l"(cy), "+l"(cz));                     // keep the bases in registers
-					const f32x2 PX = f2_bcast(px), PY = f2_bcast(py), PZ = f2_bcast(pz);
-					auto sq2 = [&](const uint kk) {
-						const f32x2 rx = f2_sub(PX, ldg_f2(cx + kk)), ry = f2_sub(PY, ldg_f2(cy + kk)), rz = f2_sub(PZ, ldg_f2(cz + kk));
-						return f2_fma(rz, rz, f2_fma(ry, ry, f2_mul(rx, rx)));
+#if B200_NL_GROUP4
+					// four candidates per trip: four loads in flight, one branch for the (52 % likely) case that none of
+					// them is inside the search radius; accepted candidates are appended in index order like below
+					auto sq = [&](const float4 c) {
+						const float rx = __fsub_rn(px, c.x), ry = __fsub_rn(py, c.y), rz = __fsub_rn(pz, c.z);
+						return __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
 					};
-					// four candidates per trip: six loads in flight, one branch for the (about 50 % likely) case that none
-					// of them is inside the search radius; accepted candidates are appended in index order
 					for (; k + 4 <= count; k += 4) {
-						const f32x2 a = sq2(k), b = sq2(k + 2);
-						float r0, r1, r2, r3;
-						f2_unpack(a, r0, r1); f2_unpack(b, r2, r3);
-						const bool a0 = r0 < R2, a1 = r1 < R2, a2 = r2 < R2, a3 = r3 < R2;
+						const float4 c0 = ld_cand(cand + k), c1 = ld_cand(cand + k + 1), c2 = ld_cand(cand + k + 2), c3 = ld_cand(cand + k + 3);
+						const bool a0 = sq(c0) < R2, a1 = sq(c1) < R2, a2 = sq(c2) < R2, a3 = sq(c3) < R2;
 						if (!(a0 | a1 | a2 | a3)) continue;
-						if (a0 && k != self) append(bucketStart + k, t_first);
-						if (a1 && k + 1 != self) append(bucketStart + k + 1, t_first);
-						if (a2 && k + 2 != self) append(bucketStart + k + 2, t_first);
-						if (a3 && k + 3 != self) append(bucketStart + k + 3, t_first);
+						if (a0 && k != self && !inactive_w(c0.w)) append(bucketStart + k, t_first);
+						if (a1 && k + 1 != self && !inactive_w(c1.w)) append(bucketStart + k + 1, t_first);
+						if (a2 && k + 2 != self && !inactive_w(c2.w)) append(bucketStart + k + 2, t_first);
+						if (a3 && k + 3 != self && !inactive_w(c3.w)) append(bucketStart + k + 3, t_first);
 					}
-					if (k + 2 <= count) {
-						float r0, r1;
-						f2_unpack(sq2(k), r0, r1);
-						if (r0 < R2 && k != self) append(bucketStart + k, t_first);
-						if (r1 < R2 && k + 1 != self) append(bucketStart + k + 1, t_first);
-						k += 2;
+#endif
+#pragma unroll 2
+					for (; k < count; ++k) {
+						const float4 np = ld_cand(cand + k);
+						const float rx = __fsub_rn(px, np.x), ry = __fsub_rn(py, np.y), rz = __fsub_rn(pz, np.z);
+						// sqlength(relPos) = x*x + y*y + z*z as nvcc contracts it
+						const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx)));
+						if (r2 < R2) {                                                  // :386-392 (85 % of the candidates fail)
+							// :553 self, :612 an inactive candidate has a non-finite w
+							if (k != self && !inactive_w(np.w)) append(bucketStart + k, t_first);
+						}
 					}
-					if (k < count) test1(k);
 					continue;
 				}
 				for (uint j = bucketStart; j < bucketEnd; ++j) {
@@ -602,23 +552,12 @@ extern "C" int b200sph_build_neibs(b200sph_ctx *ctx, const void *pos, const void
 	uint32_t num_particles, uint32_t particle_range_end)
 {
 	CHECK_CTX(ctx);
+	(void)num_particles;
 	if (particle_range_end == 0) return B200SPH_OK;
 	if (!pos || !info || !hash || !cell_start || !cell_end || !neibs_list) { b200_set_error("buildNeibsList: null buffer"); return B200SPH_EINVAL; }
 	if (particle_range_end > ctx->dp.stride) { b200_set_error("buildNeibsList: range end %u exceeds neighbour list stride %u", particle_range_end, ctx->dp.stride); return B200SPH_EINVAL; }
-	// candidates can be any of the num_particles particles (own + halo), builders only [0, particle_range_end)
-	const uint32_t ncand = num_particles > particle_range_end ? num_particles : particle_range_end;
-	if (ctx->soa_cap < ncand) {
-		cudaFree(ctx->soa); ctx->soa = NULL; ctx->soa_cap = 0;
-		const size_t cap = ((size_t)ncand + (ncand >> 3) + 1024 + 1) & ~(size_t)1;      // even: every array stays 8-byte aligned
-		CUDA_TRY(cudaMalloc(&ctx->soa, 3 * cap * sizeof(float)));
-		ctx->soa_cap = cap;
-	}
-	float *sx = ctx->soa, *sy = sx + ctx->soa_cap, *sz = sy + ctx->soa_cap;
-	split_pos_kernel<<<div_up(ncand, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>((const float4 *)pos, sx, sy, sz, ncand);
-	KERNEL_TRY();
 	build_neibs_kernel<<<div_up(particle_range_end, BLOCK_STREAM), BLOCK_STREAM, 0, ctx->stream>>>(ctx->dp,
-		(const float4 *)pos, sx, sy, sz, (const ushort4 *)info, hash, cell_start, cell_end, neibs_list, particle_range_end, ctx->d_counters);
+		(const float4 *)pos, (const ushort4 *)info, hash, cell_start, cell_end, neibs_list, particle_range_end, ctx->d_counters);
 	KERNEL_TRY();
-	// work decomposition of the locality-scheduled pair kernel for these cell ranges (forces_sweep.cuh)
-	return b200_build_sweep(ctx, cell_start, cell_end, ncand);
+	return B200SPH_OK;
 }

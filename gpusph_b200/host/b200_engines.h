@@ -16,7 +16,8 @@
  * Engines are shared by all worker threads (one SimFramework per process, SURVEY.md section 8b "Threading"), so the
  * per-device context lives in a map keyed by the CUDA device of the calling thread.
  *
- * How a maintainer wires it in: INTEGRATION.md.
+ * How a maintainer wires it in: the framework seam gpusph_b200/host/cudasimframework.cu builds these engines when a
+ * problem file says SETUP_FRAMEWORK(...).
  */
 #ifndef B200_ENGINES_H
 #define B200_ENGINES_H
@@ -148,21 +149,16 @@ public:
 	}
 };
 
-// `ref` (optional) is the reference engine of the stock framework: its setconstants()/setgravity() are still
-// called so that the reference subsystems we do NOT replace (post-processing, filters, visc, BC engines — they read
-// the reference's __constant__ symbols) keep working next to ours. No compute call is ever forwarded to it.
 class NeibsEngine : public AbstractNeibsEngine
 {
 	std::shared_ptr<Contexts> m_c;
-	AbstractNeibsEngine *m_ref;
 public:
-	NeibsEngine(std::shared_ptr<Contexts> c, AbstractNeibsEngine *ref = NULL) : m_c(c), m_ref(ref) {}
+	explicit NeibsEngine(std::shared_ptr<Contexts> c) : m_c(c) {}
 
 	void setconstants(const SimParams *simparams, const PhysParams *physparams,
 		float3 const& worldOrigin, uint3 const& gridSize, float3 const& cellSize,
 		idx_t const& allocatedParticles) override
 	{
-		if (m_ref) m_ref->setconstants(simparams, physparams, worldOrigin, gridSize, cellSize, allocatedParticles);
 		m_c->configure(simparams, physparams, worldOrigin, gridSize, cellSize, allocatedParticles); m_c->get();
 	}
 
@@ -239,25 +235,22 @@ public:
 class ForcesEngine : public AbstractForcesEngine
 {
 	std::shared_ptr<Contexts> m_c;
-	AbstractForcesEngine *m_ref;
 	static void unsupported(const char *what)
 	{ throw std::runtime_error(std::string("B200 forces engine: ") + what + " is out of scope (SURVEY.md section 8)"); }
 public:
-	ForcesEngine(std::shared_ptr<Contexts> c, AbstractForcesEngine *ref = NULL) : m_c(c), m_ref(ref) {}
+	explicit ForcesEngine(std::shared_ptr<Contexts> c) : m_c(c) {}
 
 	void setconstants(const SimParams *simparams, const PhysParams *physparams,
 		float3 const& worldOrigin, uint3 const& gridSize, float3 const& cellSize,
 		idx_t const& allocatedParticles) override
 	{
-		if (m_ref) m_ref->setconstants(simparams, physparams, worldOrigin, gridSize, cellSize, allocatedParticles);
 		m_c->configure(simparams, physparams, worldOrigin, gridSize, cellSize, allocatedParticles); m_c->get();
 	}
 
-	void getconstants(PhysParams *pp) override { if (m_ref) m_ref->getconstants(pp); }
+	void getconstants(PhysParams *pp) override { }
 
 	void setplanes(PlaneList const& planes) override
 	{
-		if (m_ref) m_ref->setplanes(planes);
 		// plane_t = { float3 normal; int3 gridPos; float3 pos; } (src/planes.h:42-46)
 		std::vector<float> nrm, pos; std::vector<int> gp;
 		for (auto const& pl : planes) {
@@ -268,14 +261,12 @@ public:
 		check(b200sph_set_planes(m_c->get(), nrm.data(), gp.data(), pos.data(), (int)planes.size()));
 	}
 	void setgravity(float3 const& g) override
-	{ if (m_ref) m_ref->setgravity(g); const float v[3] = { g.x, g.y, g.z }; check(b200sph_set_gravity(m_c->get(), v)); }
+	{ const float v[3] = { g.x, g.y, g.z }; check(b200sph_set_gravity(m_c->get(), v)); }
 	// moving / force-feedback bodies (src/cuda/forces.cu:430-447, 967-1003)
 	void setrbcg(const int3* cgGridPos, const float3* cgPos, int numbodies) override
-	{ if (m_ref) m_ref->setrbcg(cgGridPos, cgPos, numbodies);
-	  check(b200sph_set_rbcg(m_c->get(), (const int*)cgGridPos, (const float*)cgPos, numbodies)); }
+	{ check(b200sph_set_rbcg(m_c->get(), (const int*)cgGridPos, (const float*)cgPos, numbodies)); }
 	void setrbstart(const int* rbfirstindex, int numbodies) override
-	{ if (m_ref) m_ref->setrbstart(rbfirstindex, numbodies);
-	  check(b200sph_set_rbstart(m_c->get(), rbfirstindex, numbodies)); }
+	{ check(b200sph_set_rbstart(m_c->get(), rbfirstindex, numbodies)); }
 	void reduceRbForces(BufferList& bufwrite, uint *lastindex, float3 *totalforce, float3 *totaltorque,
 		uint numforcesbodies, uint numForcesBodiesParticles) override
 	{
@@ -336,29 +327,28 @@ public:
 class IntegrationEngine : public AbstractIntegrationEngine
 {
 	std::shared_ptr<Contexts> m_c;
-	AbstractIntegrationEngine *m_ref;
 	static void unsupported(const char *what)
 	{ throw std::runtime_error(std::string("B200 integration engine: ") + what + " is out of scope (SURVEY.md section 8)"); }
 public:
-	IntegrationEngine(std::shared_ptr<Contexts> c, AbstractIntegrationEngine *ref = NULL) : m_c(c), m_ref(ref) {}
+	explicit IntegrationEngine(std::shared_ptr<Contexts> c) : m_c(c) {}
 
 	// everything this engine needs was already flattened by the neibs/forces setconstants
 	void setconstants(const PhysParams *pp, float3 const& o, uint3 const& g, float3 const& c, idx_t const& a, int const& n, float const& h) override
-	{ if (m_ref) m_ref->setconstants(pp, o, g, c, a, n, h); }
-	void getconstants(PhysParams *pp) override { if (m_ref) m_ref->getconstants(pp); }
+	{ }
+	void getconstants(PhysParams *pp) override { }
 
 	// moving bodies (src/cuda/euler.cu:76-95)
 	// the integration engine's OWN copy of the centres of gravity (cg(n) for the whole step, src/cuda/euler_kernel.def:488)
 	void setrbcg(const int3* g, const float3* c, int n) override
-	{ if (m_ref) m_ref->setrbcg(g, c, n); check(b200sph_set_rbcg_euler(m_c->get(), (const int*)g, (const float*)c, n)); }
+	{ check(b200sph_set_rbcg_euler(m_c->get(), (const int*)g, (const float*)c, n)); }
 	void setrbtrans(const float3* t, int n) override
-	{ if (m_ref) m_ref->setrbtrans(t, n); check(b200sph_set_rbtrans(m_c->get(), (const float*)t, n)); }
+	{ check(b200sph_set_rbtrans(m_c->get(), (const float*)t, n)); }
 	void setrbsteprot(const float* r, int n) override
-	{ if (m_ref) m_ref->setrbsteprot(r, n); check(b200sph_set_rbsteprot(m_c->get(), r, n)); }
+	{ check(b200sph_set_rbsteprot(m_c->get(), r, n)); }
 	void setrblinearvel(const float3* v, int n) override
-	{ if (m_ref) m_ref->setrblinearvel(v, n); check(b200sph_set_rblinearvel(m_c->get(), (const float*)v, n)); }
+	{ check(b200sph_set_rblinearvel(m_c->get(), (const float*)v, n)); }
 	void setrbangularvel(const float3* v, int n) override
-	{ if (m_ref) m_ref->setrbangularvel(v, n); check(b200sph_set_rbangularvel(m_c->get(), (const float*)v, n)); }
+	{ check(b200sph_set_rbangularvel(m_c->get(), (const float*)v, n)); }
 
 	void density_sum(const BufferList&, BufferList&, const uint, const uint, const float, const int, const float,
 		const float, const float, const float, const float) override { unsupported("density summation (SA)"); }
@@ -410,14 +400,12 @@ public:
 class TestpointsEngine : public AbstractPostProcessEngine
 {
 	std::shared_ptr<Contexts> m_c;
-	AbstractPostProcessEngine *m_ref;   // stock engine: only its setconstants is forwarded (GPUWorker uploads the
-	                                    // post-processing constants through the FIRST engine of the set, GPUWorker.cc:3000-3001)
 public:
-	TestpointsEngine(std::shared_ptr<Contexts> c, flag_t options = NO_FLAGS, AbstractPostProcessEngine *ref = NULL) :
-		AbstractPostProcessEngine(options), m_c(c), m_ref(ref) {}
+	explicit TestpointsEngine(std::shared_ptr<Contexts> c, flag_t options = NO_FLAGS) :
+		AbstractPostProcessEngine(options), m_c(c) {}
 
 	void setconstants(const SimParams *sp, const PhysParams *pp, idx_t const& n) const override
-	{ if (m_ref) m_ref->setconstants(sp, pp, n); }
+	{ }
 	void getconstants() override {}
 
 	void process(const BufferList& bufread, BufferList& bufwrite, uint numParticles, uint particleRangeEnd,
@@ -436,28 +424,6 @@ public:
 	void hostProcess(const GlobalData * const) override {}
 	void write(WriterMap, double) override {}
 };
-
-//! The framework's filter set with SHEPARD / MLS replaced by ours (same frequencies). GPUWorker keeps a reference to
-//! the set (src/GPUWorker.h:79), hence the static storage.
-inline FilterEngineSet const& filters(std::shared_ptr<Contexts> c, FilterEngineSet const& stock)
-{
-	static FilterEngineSet ours;
-	ours.clear();
-	for (auto const& kv : stock)
-		ours[kv.first] = (kv.first == SHEPARD_FILTER || kv.first == MLS_FILTER) ?
-			new FilterEngine(c, kv.first, kv.second->frequency()) : kv.second;
-	return ours;
-}
-
-//! The framework's post-processing set with TESTPOINTS replaced by ours
-inline PostProcessEngineSet const& postprocess(std::shared_ptr<Contexts> c, PostProcessEngineSet const& stock)
-{
-	static PostProcessEngineSet ours;
-	ours.clear();
-	for (auto const& kv : stock)
-		ours[kv.first] = kv.first == TESTPOINTS ? new TestpointsEngine(c, kv.second->get_options(), kv.second) : kv.second;
-	return ours;
-}
 
 } // namespace b200
 #endif

@@ -500,7 +500,8 @@ static void forces_pass(const b200sph_params *P, const oracle_forces_opts *opts,
 					DrDt += t; a_w += fabsf(t);
 				} else if (P->densitydiffusiontype == B200SPH_RHODIFF_COLAGROSSI) { /* :1916-1951 */
 					if (fnum == nfnum) {
-						const float Pi = p_precalc * (rho * rho), Pj = np_precalc * (nrho * nrho);
+						/* the switch compares the pressures P() themselves (:1925-1928), not P/rho^2 scaled back */
+						const float Pi = eos_P(P, v.w, fnum), Pj = eos_P(P, nrho_t, nfnum);
 						const float gdot = P->gravity[0] * rx + P->gravity[1] * ry + P->gravity[2] * rz;
 						if (!(fabsf(Pi - Pj) < fabsf(gdot * rho))) {
 							const float t = P->density_diff_coeff * P->sscoeff[fnum] * (nrho / rho - 1) * f * nmass;

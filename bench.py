@@ -344,7 +344,8 @@ def main():
             # constant between neighbour rebuilds and already resident (the reference uploads them once,
             # GPUWorker::uploadSubdomain). device -> host: the step's result (state n+1); after a rebuild also the
             # re-sorted info/hash.
-            n = w.numParticles
+            # slabs: the host owns the particles this rank OWNS; halo copies come from the neighbours over NVLink
+            n = w.numOwn if world > 1 else w.numParticles
             rebuilt = w.iterations % freq == 0
             traffic[0] += n * 32
             if pipelined:
@@ -354,8 +355,9 @@ def main():
             else:
                 w.pos[w.cur][:n].copy_(hp[0][:n], non_blocking=True)
                 w.vel[w.cur][:n].copy_(hp[1][:n], non_blocking=True)
+                w.state_modified()
                 w.step()
-                n = w.numParticles
+                n = w.numOwn if world > 1 else w.numParticles
                 hp[0][:n].copy_(w.pos[w.cur][:n], non_blocking=True)
                 hp[1][:n].copy_(w.vel[w.cur][:n], non_blocking=True)
             traffic[1] += n * 32

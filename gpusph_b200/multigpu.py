@@ -595,6 +595,13 @@ class SlabWorker:
                 recvs.append((t[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
         return self._exchange_start(sends, recvs)
 
+    def state_modified(self) -> None:
+        """POS / VEL of the particles this rank owns were written behind the worker's back (a host upload): refresh their
+        neighbour records. The halo records stay: they are the neighbours' current states, delivered by the exchange."""
+        if self.packed is not None and self.device_dt and self.numOwn > 0:
+            self.backend.pack_state(self.pos[self.cur], self.vel[self.cur], self.packed[self.cur], 0, self.numOwn)
+            self.launches += 1
+
     def download_own(self) -> ParticleArrays:
         n = self.numOwn
         return ParticleArrays(self.pos[self.cur][:n].cpu().numpy(), self.vel[self.cur][:n].cpu().numpy(),

@@ -335,7 +335,7 @@ def main():
         barrier()
         freq = w.buildneibsfreq
         esteps = max(freq, int(round(args.steps / 2 / freq)) * freq)      # whole rebuild periods: 1 rebuild step in `freq`
-        pipelined = world == 1 and not args.no_pipeline
+        pipelined = not args.no_pipeline
         traffic = [0, 0]
         side = torch.cuda.Stream()
 
@@ -349,9 +349,10 @@ def main():
             rebuilt = w.iterations % freq == 0
             traffic[0] += n * 32
             if pipelined:
-                # Worker.step_host: the same copies, pipelined with the force evaluations in stripes of cell layers
+                # Worker.step_host: the same copies, pipelined with the force evaluations in stripes of cell layers;
+                # SlabWorker.step_host (N > 1): the copies in pieces, download of step n next to the upload of step n+1
                 w.step_host(hp[0], hp[1])
-                n = w.numParticles
+                n = w.numOwn if world > 1 else w.numParticles
             else:
                 w.pos[w.cur][:n].copy_(hp[0][:n], non_blocking=True)
                 w.vel[w.cur][:n].copy_(hp[1][:n], non_blocking=True)

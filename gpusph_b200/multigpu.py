@@ -602,6 +602,55 @@ class SlabWorker:
             self.backend.pack_state(self.pos[self.cur], self.vel[self.cur], self.packed[self.cur], 0, self.numOwn)
             self.launches += 1
 
+    # ---- stepping a state that lives in HOST memory (bench.py's e2e leg on N > 1 GPUs) ----
+    def step_host(self, hpos: torch.Tensor, hvel: torch.Tensor, chunks: int = 8) -> None:
+        """One time step of the particles this rank owns with the state held by the HOST: hpos / hvel (pinned, sorted
+        order) hold state n of [0, numOwn) on entry and state n+1 once the copies have landed (host_fence()). The copies
+        run in `chunks` pieces on an upload and a download stream: the upload of piece c of step n+1 waits (event) only
+        for the download of piece c of step n, so the two PCIe directions work at the same time and the host never
+        blocks; the force evaluations wait for the whole upload (every owned particle can be a neighbour).
+        Halo copies are not the host's business: they arrive from the neighbours over NVLink as usual."""
+        if not (hpos.is_pinned() and hvel.is_pinned()):
+            raise ValueError("step_host needs pinned host buffers")
+        dev = self.device
+        if getattr(self, "_up", None) is None:
+            self._up, self._down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._down_ev, self._down_n = [], -1
+        main = torch.cuda.current_stream(dev)
+        n = self.numOwn
+        cur = self.cur
+        if n > 0:
+            b = [n * c // chunks for c in range(chunks + 1)]
+            self._up.wait_stream(main)                       # whatever still reads / writes the state on the compute stream
+            if self._down_n != n or len(self._down_ev) != chunks:
+                self._up.wait_stream(self._down)             # ranges moved (a rebuild): wait for every earlier download
+            with torch.cuda.stream(self._up):
+                for c in range(chunks):
+                    if self._down_n == n and len(self._down_ev) == chunks:
+                        self._up.wait_event(self._down_ev[c])
+                    self.pos[cur][b[c]:b[c + 1]].copy_(hpos[b[c]:b[c + 1]], non_blocking=True)
+                    self.vel[cur][b[c]:b[c + 1]].copy_(hvel[b[c]:b[c + 1]], non_blocking=True)
+            main.wait_stream(self._up)
+            self.state_modified()
+        self.step()
+        n, cur = self.numOwn, self.cur
+        b = [n * c // chunks for c in range(chunks + 1)]
+        self._down.wait_stream(main)
+        evs = []
+        with torch.cuda.stream(self._down):
+            for c in range(chunks):
+                hpos[b[c]:b[c + 1]].copy_(self.pos[cur][b[c]:b[c + 1]], non_blocking=True)
+                hvel[b[c]:b[c + 1]].copy_(self.vel[cur][b[c]:b[c + 1]], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._down)
+                evs.append(ev)
+        self._down_ev, self._down_n = evs, n
+
+    def host_fence(self) -> None:
+        """The compute stream waits for the copies of earlier step_host calls."""
+        if getattr(self, "_down", None) is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._down)
+
     def download_own(self) -> ParticleArrays:
         n = self.numOwn
         return ParticleArrays(self.pos[self.cur][:n].cpu().numpy(), self.vel[self.cur][:n].cpu().numpy(),

@@ -24,7 +24,7 @@ def make_problem():
     return params, parts
 
 
-def _rank_main(rank, world, port, steps, outdir):
+def _rank_main(rank, world, port, steps, outdir, host_state=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -32,9 +32,27 @@ def _rank_main(rank, world, port, steps, outdir):
     params, parts = make_problem()
     w = SlabWorker(params, parts, rank, rank=rank, world=world)
     dts = []
-    for _ in range(steps):
-        w.step()
+    if host_state:
+        # the state of the owned particles lives in pinned host buffers: every step uploads it and downloads the result
+        # (SlabWorker.step_host, what bench.py's e2e leg times on N > 1 GPUs); no host synchronisation in between
+        A = w.pos[0].shape[0]
+        hp, hv = torch.zeros((A, 4)).pin_memory(), torch.zeros((A, 4)).pin_memory()
+        w.step()                                   # the first rebuild decides who owns what
         dts.append(w.dt)
+        n = w.numOwn
+        hp[:n].copy_(w.pos[w.cur][:n]); hv[:n].copy_(w.vel[w.cur][:n])
+        torch.cuda.synchronize()
+        for _ in range(steps - 1):
+            w.step_host(hp, hv)
+        w.host_fence()
+        torch.cuda.synchronize()
+        n = w.numOwn
+        assert torch.equal(hp[:n], w.pos[w.cur][:n].cpu()) and torch.equal(hv[:n], w.vel[w.cur][:n].cpu())
+        dts = [w.dt] * steps
+    else:
+        for _ in range(steps):
+            w.step()
+            dts.append(w.dt)
     out = w.download_own()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), pos=out.pos, vel=out.vel, info=out.info, hash=out.hash,
              dts=np.array(dts))
@@ -46,7 +64,8 @@ def ids_of(info):
 
 
 @pytest.mark.timeout(600)
-def test_two_gpu_slab_run_matches_single_gpu_bitwise():
+@pytest.mark.parametrize("host_state", [False, True], ids=["resident", "host_state"])
+def test_two_gpu_slab_run_matches_single_gpu_bitwise(host_state):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from gpusph_b200.simulation import Worker
@@ -60,10 +79,13 @@ def test_two_gpu_slab_run_matches_single_gpu_bitwise():
     exp = ref.download()
     with tempfile.TemporaryDirectory() as d:
         port = 29500 + (os.getpid() % 2000)
-        mp.spawn(_rank_main, args=(2, port, steps, d), nprocs=2, join=True)
+        mp.spawn(_rank_main, args=(2, port, steps, d, host_state), nprocs=2, join=True)
         r = [np.load(os.path.join(d, f"rank{k}.npz")) for k in range(2)]
     assert np.array_equal(r[0]["dts"], r[1]["dts"])
-    assert np.array_equal(r[0]["dts"].astype(np.float32), np.array(ref_dts, dtype=np.float32))
+    if host_state:
+        assert np.float32(r[0]["dts"][-1]) == np.float32(ref_dts[-1])
+    else:
+        assert np.array_equal(r[0]["dts"].astype(np.float32), np.array(ref_dts, dtype=np.float32))
     ids = np.concatenate([ids_of(r[k]["info"]) for k in range(2)])
     assert np.array_equal(np.sort(ids), np.arange(parts.n))
     pos = np.concatenate([r[k]["pos"] for k in range(2)])

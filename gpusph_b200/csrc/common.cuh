@@ -145,8 +145,6 @@ struct b200sph_ctx {
 	const void *host_pos_last, *host_vel_last, *dev_pos_last, *dev_vel_last;
 	int host_pending;
 	cudaEvent_t *trace_ev; int trace_resident;      // B200SPH_HOST_TRACE diagnostics
-	// zero-copy downloads (B200_HOST_ZEROCOPY builds + B200SPH_HOST_ZEROCOPY=1): host mirrors the next fused launch writes to
-	void *zc_host_pos, *zc_host_vel; int host_zerocopy;
 };
 
 // ---- error plumbing ----
@@ -206,4 +204,3 @@ __device__ __forceinline__ int3 grid_pos(const DevParams &P, uint cellHash)
 int b200_packed_scratch(b200sph_ctx *ctx, int which, uint32_t n, PosVel **out);   // forces.cu
 void b200_hoststep_destroy(b200sph_ctx *ctx);
 int b200_euler_bodies(b200sph_ctx *ctx, const uint32_t *hash, const BodyData **out);   // api.cu
-int b200_zero_copy_supported(void);   // forces.cu: was the pair kernel compiled with the zero-copy epilogue?

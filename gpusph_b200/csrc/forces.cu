@@ -266,15 +266,6 @@ integrate_epilogue(const DevParams &P, const BodyOut &bo, const uint index, cons
 	bo.eul_new_vel[index] = v;
 	// the integrated state as the record the NEXT force evaluation gathers (no pack pre-pass between launches)
 	if (bo.eul_new_packed) st_posvel(bo.eul_new_packed + index, p, v);
-#if B200_HOST_ZEROCOPY
-	// B200_HOST_ZEROCOPY (experimental, off): the integrated state also goes straight to the caller's mapped host
-	// buffers - a warp writes 512 contiguous bytes per array over PCIe - so that b200sph_step_host needs no
-	// device-to-host copy (and no copy-engine hand-over) behind the corrector
-	if (bo.eul_host_pos) {
-		__stcs(bo.eul_host_pos + index, p);
-		__stcs(bo.eul_host_vel + index, v);
-	}
-#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -293,13 +284,6 @@ __device__ __forceinline__ float4 lds_f4(uint a)
 #ifndef B200_MIN_BLOCKS
 #define B200_MIN_BLOCKS 7
 #endif
-// B200_CELLTABLE=1: per-warp table of neighbour-cell bases (B200_CT_SLOTS distinct cells) instead of 27 bases per thread
-#ifndef B200_CELLTABLE
-#define B200_CELLTABLE 0
-#endif
-#ifndef B200_CT_SLOTS
-#define B200_CT_SLOTS 8
-#endif
 // (the detour through shared memory is what stops ptxas from re-deriving the value from the constant bank)
 struct Pinned { float v[24]; };
 
@@ -315,14 +299,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 	const uint fromParticle, const uint toParticle, const uint cflOffset)
 {
 	constexpr bool GEN = RHODIFF == RHODIFF_RUNTIME;
-#if B200_CELLTABLE
-	// per warp: the 27 neighbour-cell bases of each DISTINCT cell its 32 particles lie in (particles are sorted by cell:
-	// 2-4 cells per warp in the bulk) instead of 27 bases per thread: 3.5 KB per CTA instead of 13.8 KB, and the
-	// difference stays L1 for the neighbour gathers, which is what this kernel waits for
-	__shared__ uint s_cellbase[BLOCK_FORCES / 32][B200_CT_SLOTS][28];
-#else
 	__shared__ uint s_cellbase[27 * BLOCK_FORCES];
-#endif
 	__shared__ float4 s_celloff[27];
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x + fromParticle;
 	float cfl_term = 0.0f;
@@ -358,68 +335,6 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 	__syncthreads();
 #endif
 
-#if B200_CELLTABLE
-	{
-		const uint lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-		const bool in_range = index < toParticle;
-		ushort4 info = make_ushort4(0, 0, 0, 0);
-		float4 pos = make_float4(0.f, 0.f, 0.f, 0.f), vel = pos;
-		int type = -1;
-		if (in_range) { info = infoArray[index]; type = ptype_of(info); ld_posvel(pv + index, pos, vel); }
-		const bool active = in_range && (type == PT_FLUID || type == PT_BOUNDARY) && fabsf(pos.w) < __int_as_float(0x7f800000);
-		const uint cellHash = active ? (particleHash[index] & CELLTYPE_BITMASK) : 0xFFFFFFFFu;
-		// distinct cells of the warp: a lane opens a new one when its cell differs from the previous lane's
-		const uint prevHash = __shfl_up_sync(0xffffffffu, cellHash, 1);
-		const uint heads = __ballot_sync(0xffffffffu, active && (lane == 0 || cellHash != prevHash));
-		const uint rank = __popc(heads & (0xffffffffu >> (31u - lane))) - 1u;        // of my cell, for active lanes
-		const uint nslots = min((uint)__popc(heads), (uint)B200_CT_SLOTS);
-		for (uint sl = 0; sl < nslots; ++sl) {
-			const uint h0 = __shfl_sync(0xffffffffu, cellHash, __fns(heads, 0, sl + 1));
-			if (lane < 27) {
-				const int3 gp = grid_pos(P, h0);
-				const int sx = P.hstride[0], sy = P.hstride[1], sz = P.hstride[2];
-				const int Gx = P.gridSize[0], Gy = P.gridSize[1], Gz = P.gridSize[2];
-				const int cx = (int)lane % 3, cy = ((int)lane / 3) % 3, cz = (int)lane / 9;
-				const int dx = cx == 0 ? (gp.x == 0 ? (Gx - 1) * sx : -sx) : (cx == 2 ? (gp.x == Gx - 1 ? -(Gx - 1) * sx : sx) : 0);
-				const int dy = cy == 0 ? (gp.y == 0 ? (Gy - 1) * sy : -sy) : (cy == 2 ? (gp.y == Gy - 1 ? -(Gy - 1) * sy : sy) : 0);
-				const int dz = cz == 0 ? (gp.z == 0 ? (Gz - 1) * sz : -sz) : (cz == 2 ? (gp.z == Gz - 1 ? -(Gz - 1) * sz : sz) : 0);
-				s_cellbase[warp][sl][lane] = __ldg(cellStart + ((int)h0 + dx + dy + dz));
-			}
-		}
-		__syncwarp();
-		if (in_range) {
-			float4 acc;
-			bool have_acc = false;
-			if (active) {
-				have_acc = true;
-				const bool tabled = rank < (uint)B200_CT_SLOTS;
-				const uint a_base = smem_u32(&s_cellbase[warp][tabled ? rank : 0][0]);
-				auto lut = [=](const uint cell, uint &base, float &ox, float &oy, float &oz) {
-					if (tabled) base = lds_u32(a_base + cell * 4u);
-					else {
-						// more distinct cells in this warp than table slots (sparse regions: few neighbours): look it up
-						const int3 gp = grid_pos(P, cellHash);
-						const int cx = (int)cell % 3, cy = ((int)cell / 3) % 3, cz = (int)cell / 9;
-						const int dx = cx == 0 ? (gp.x == 0 ? (P.gridSize[0] - 1) * P.hstride[0] : -P.hstride[0]) : (cx == 2 ? (gp.x == P.gridSize[0] - 1 ? -(P.gridSize[0] - 1) * P.hstride[0] : P.hstride[0]) : 0);
-						const int dy = cy == 0 ? (gp.y == 0 ? (P.gridSize[1] - 1) * P.hstride[1] : -P.hstride[1]) : (cy == 2 ? (gp.y == P.gridSize[1] - 1 ? -(P.gridSize[1] - 1) * P.hstride[1] : P.hstride[1]) : 0);
-						const int dz = cz == 0 ? (gp.z == 0 ? (P.gridSize[2] - 1) * P.hstride[2] : -P.hstride[2]) : (cz == 2 ? (gp.z == P.gridSize[2] - 1 ? -(P.gridSize[2] - 1) * P.hstride[2] : P.hstride[2]) : 0);
-						base = __ldg(cellStart + ((int)cellHash + dx + dy + dz));
-					}
-					const float4 o = lds_f4(a_off + cell * 16u);
-					ox = o.x; oy = o.y; oz = o.z;
-				};
-				auto fetch = [&](const uint j, float4 &np, float4 &nv) { ld_posvel(pv + j, np, nv); };
-				auto eos = [&](const uint j, const float4 nv) {
-					return MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
-				};
-				cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE, B200_GATHER_AHEAD != 0>(P, k, index, info, type, pos,
-					vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, eos, forces,
-					GEN ? bo.xsph : NULL, &acc);
-			}
-			integrate_epilogue(P, bo, index, info, pos, vel, acc, have_acc, particleHash, forces);
-		}
-	}
-#else
 	if (index < toParticle) {
 		const ushort4 info = infoArray[index];
 		const int type = ptype_of(info);
@@ -450,8 +365,6 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 		}
 		integrate_epilogue(P, bo, index, info, pos, vel, acc, have_acc, particleHash, forces);
 	}
-
-#endif
 
 	// block max (maxBlockReduce, device_core.cu:40-59) with warp shuffles
 	if (cfl) {
@@ -549,7 +462,6 @@ extern "C" int b200sph_forces_bodies(b200sph_ctx *ctx, const void *pos, const vo
 }
 
 static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const b200sph_fused_euler_args *eul, uint32_t *num_cfl_blocks);
-int b200_zero_copy_supported(void) { return B200_HOST_ZEROCOPY; }
 
 extern "C" int b200sph_forces_ex(b200sph_ctx *ctx, const b200sph_forces_args *args, uint32_t *num_cfl_blocks)
 {
@@ -651,12 +563,6 @@ static int forces_impl(b200sph_ctx *ctx, const b200sph_forces_args *args, const 
 		bo.eul_new_packed = (PosVel *)eul->new_packed;
 		{ const int rc = b200_euler_bodies(ctx, hash, &bo.eul_bodies); if (rc) return rc; }
 	}
-#if B200_HOST_ZEROCOPY
-	bo.eul_host_pos = fuse ? (float4 *)ctx->zc_host_pos : NULL;
-	bo.eul_host_vel = fuse ? (float4 *)ctx->zc_host_vel : NULL;
-	if (ctx->zc_host_pos && !fuse) { b200_set_error("forces_euler: zero-copy mirror requested but the launch is not fused"); return B200SPH_EINVAL; }
-#endif
-	ctx->zc_host_pos = ctx->zc_host_vel = NULL;      // one launch only
 	// 32-bit list offsets unless the list has 2^31 entries or more
 	const bool wide = ((unsigned long long)d.neiblistsize + 1) * d.stride + num_particles >= 0x7fffffffull;
 	gather_kernel_t gks[2];

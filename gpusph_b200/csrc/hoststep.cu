@@ -33,7 +33,6 @@ static int host_streams(b200sph_ctx *ctx)
 		CUDA_TRY(cudaEventCreateWithFlags(&ctx->pred_ev[i], cudaEventDisableTiming));
 	}
 	{ const char *e = getenv("B200SPH_HOST_LANES"); ctx->host_lanes = e ? atoi(e) : 2; }
-	{ const char *e = getenv("B200SPH_HOST_ZEROCOPY"); ctx->host_zerocopy = (e && atoi(e) > 0 && b200_zero_copy_supported()) ? 1 : 0; }
 	if (ctx->host_lanes < 1) ctx->host_lanes = 1;
 	if (ctx->host_lanes > B200_MAX_LANES) ctx->host_lanes = B200_MAX_LANES;
 	for (int l = 1; l < B200_MAX_LANES; ++l) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
@@ -147,15 +146,6 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 	cudaStream_t Q = ctx->host_lanes > 1 ? ctx->lane_stream[1] : P;
 	struct Restore { b200sph_ctx *c; cudaStream_t s; ~Restore() { c->stream = s; } } restore = { ctx, P };
 
-	// experimental (B200_HOST_ZEROCOPY builds, B200SPH_HOST_ZEROCOPY=1): the corrector's epilogue writes state n+1 straight
-	// into the mapped host buffers, no download copies; only for fused launches and host pointers the device can address
-	bool zc = ctx->host_zerocopy && !xsph;
-	if (zc) {
-		cudaPointerAttributes pa, va;
-		zc = cudaPointerGetAttributes(&pa, a->host_pos) == cudaSuccess && cudaPointerGetAttributes(&va, a->host_vel) == cudaSuccess &&
-			pa.type == cudaMemoryTypeHost && va.type == cudaMemoryTypeHost && pa.devicePointer == a->host_pos && va.devicePointer == a->host_vel;
-		cudaGetLastError();
-	}
 	TRACE(TR_BASE, P);
 	ctx->trace_resident = a->resident;
 	if (Q != P) {                                     // Q starts after whatever precedes this call on P
@@ -227,23 +217,16 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		b200sph_fused_euler_args eu;
 		eu.old_pos = a->pos; eu.old_vel = a->vel; eu.new_pos = a->pos; eu.new_vel = a->vel;
 		eu.dt = 0.0f; eu.step = 2; eu.dt_from_device = 1; eu.new_packed = NULL;
-		if (zc) { ctx->zc_host_pos = a->host_pos; ctx->zc_host_vel = a->host_vel; }
 		int r = b200sph_forces_euler(ctx, &f, &eu, &nb);
-		ctx->zc_host_pos = ctx->zc_host_vel = NULL;
 		if (r) return r;
 		offQ += nb;
 		CUDA_TRY(cudaEventRecord(ctx->comp_ev[j], Q));
 		TRACE(TR_CORR + j, Q);
-		if (zc) {
-			// the kernel's own stores are the download: stripe j has "landed" when the launch completes
-			CUDA_TRY(cudaEventRecord(ctx->down_ev[j], Q));
-		} else {
-			CUDA_TRY(cudaStreamWaitEvent(D, ctx->comp_ev[j], 0));
-			CUDA_TRY(cudaMemcpyAsync((char *)a->host_pos + o16, (char *)a->pos + o16, (size_t)(e - s) * 16, cudaMemcpyDeviceToHost, D));
-			CUDA_TRY(cudaMemcpyAsync((char *)a->host_vel + o16, (char *)a->vel + o16, (size_t)(e - s) * 16, cudaMemcpyDeviceToHost, D));
-			CUDA_TRY(cudaEventRecord(ctx->down_ev[j], D));
-		}
-		TRACE(TR_DOWN + j, zc ? Q : D);
+		CUDA_TRY(cudaStreamWaitEvent(D, ctx->comp_ev[j], 0));
+		CUDA_TRY(cudaMemcpyAsync((char *)a->host_pos + o16, (char *)a->pos + o16, (size_t)(e - s) * 16, cudaMemcpyDeviceToHost, D));
+		CUDA_TRY(cudaMemcpyAsync((char *)a->host_vel + o16, (char *)a->vel + o16, (size_t)(e - s) * 16, cudaMemcpyDeviceToHost, D));
+		CUDA_TRY(cudaEventRecord(ctx->down_ev[j], D));
+		TRACE(TR_DOWN + j, D);
 		return B200SPH_OK;
 	};
 	for (uint32_t k = 0; k < ns; ++k) {
@@ -253,7 +236,7 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 	}
 	rc = corrector(ns - 1);
 	if (rc) return rc;
-	CUDA_TRY(cudaEventRecord(ctx->down_all_ev, zc ? Q : D));
+	CUDA_TRY(cudaEventRecord(ctx->down_all_ev, D));
 	// dt candidates of the two force evaluations, then t += dt, dt = min(candidates) once both are known
 	ctx->stream = P;
 	rc = b200sph_dtreduce_async(ctx, a->cfl, offP, 1);

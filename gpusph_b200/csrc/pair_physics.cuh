@@ -277,9 +277,6 @@ __device__ __forceinline__ void plane_forces(const DevParams &P, const int3 gp, 
 // particles (:4091), CFL term max(|a|, c^2/h) (dyndt_forces_shared_data::store :3436-3456); for particles of a
 // force-feedback body (FG_COMPUTE_FORCE) the acceleration is turned into a force (x mass) and, with its torque
 // about the body's centre of gravity, scattered to the body buffers (:4116-4141).
-#ifndef B200_HOST_ZEROCOPY
-#define B200_HOST_ZEROCOPY 0
-#endif
 struct BodyOut {
 	const BodyData *bodies;     // NULL: no body output requested
 	float4 *rb_forces, *rb_torques;
@@ -293,9 +290,6 @@ struct BodyOut {
 	float4 *eul_new_pos, *eul_new_vel;
 	PosVel *eul_new_packed;                // the same state as neighbour records for the next force evaluation (NULL: none)
 	const BodyData *eul_bodies;            // rigid motion of moving bodies (NULL: none)
-#if B200_HOST_ZEROCOPY
-	float4 *eul_host_pos, *eul_host_vel;   // mapped pinned HOST mirrors of eul_new_* (NULL: none), see forces.cu
-#endif
 };
 
 __device__ __forceinline__ float finalize_particle(const DevParams &P, const int type, const int fnum, const float sspeed,

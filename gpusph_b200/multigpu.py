@@ -603,48 +603,171 @@ class SlabWorker:
             self.launches += 1
 
     # ---- stepping a state that lives in HOST memory (bench.py's e2e leg on N > 1 GPUs) ----
+    def _inner_stripes(self, want: int = 6, min_particles: int = 150000):
+        """The inner stripe [0, edge_start) cut into ranges of whole cell layers (every neighbour of a particle of range k
+        lies in ranges k-1 .. k+1, in the edge stripe or in the halo). Cached per neighbour rebuild (one small readback)."""
+        key = (self.iterations // self.buildneibsfreq, self.numOwn, self.edge_start)
+        if getattr(self, "_istripes_key", None) == key:
+            return self._istripes_val
+        e0 = min(self.edge_start, self.numOwn)
+        cs2 = self.cellstart.view(-1, self.S)
+        big = torch.iinfo(torch.int32).max
+        first = torch.where(cs2 != -1, cs2, big).min(dim=1).values.cpu().numpy().astype(np.int64)
+        starts = sorted(set(int(x) for x in first if x != big and 0 < x < e0))
+        want = max(1, min(want, e0 // max(min_particles, 1)))
+        bounds = [0]
+        for k in range(1, want):
+            target = e0 * k // want
+            nxt = next((x for x in starts if x >= target), None)
+            if nxt is not None and nxt > bounds[-1]:
+                bounds.append(nxt)
+        bounds.append(e0)
+        self._istripes_key, self._istripes_val = key, [(a, b_) for a, b_ in zip(bounds[:-1], bounds[1:]) if b_ > a]
+        return self._istripes_val
+
     def step_host(self, hpos: torch.Tensor, hvel: torch.Tensor, chunks: int = 8) -> None:
         """One time step of the particles this rank owns with the state held by the HOST: hpos / hvel (pinned, sorted
-        order) hold state n of [0, numOwn) on entry and state n+1 once the copies have landed (host_fence()). The copies
-        run in `chunks` pieces on an upload and a download stream: the upload of piece c of step n+1 waits (event) only
-        for the download of piece c of step n, so the two PCIe directions work at the same time and the host never
-        blocks; the force evaluations wait for the whole upload (every owned particle can be a neighbour).
-        Halo copies are not the host's business: they arrive from the neighbours over NVLink as usual."""
+        order) hold state n of [0, numOwn) on entry and state n+1 once the copies have landed (host_fence()). Nothing is
+        synchronised; consecutive calls chain piece by piece through events. Halo copies are not the host's business:
+        they arrive from the neighbours over NVLink as usual. Results are bitwise those of step().
+
+        Between neighbour rebuilds the step is pipelined with its copies: the owned particles are cut into the edge
+        stripe and a few inner ranges of whole cell layers; the predictor's pair kernel of range k starts when range
+        k+1 has been uploaded, the corrector (integration fused, in place) of range k is followed at once by its download,
+        and the upload of a piece of step n+1 waits only for the download of the same piece of step n - both PCIe
+        directions and the SMs are busy at the same time. A step that starts with a rebuild needs the whole state
+        first: its copies run in `chunks` pieces around the ordinary step()."""
         if not (hpos.is_pinned() and hvel.is_pinned()):
             raise ValueError("step_host needs pinned host buffers")
         dev = self.device
         if getattr(self, "_up", None) is None:
             self._up, self._down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            self._down_ev, self._down_n = [], -1
+            self._down_ev, self._down_key = {}, None
+        rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
+        records = self.device_dt and self.packed is not None and self._edge_stream is not None
+        if rebuild or not records or self.numOwn == 0:
+            return self._step_host_plain(hpos, hvel, chunks)
+        be = self.backend
+        ctx = be.fw.ctx
+        main, es, up, down = torch.cuda.current_stream(dev), self._edge_stream, self._up, self._down
+        n, n_own = self.numParticles, self.numOwn
+        e0 = min(self.edge_start, n_own)
+        cur, oth = self.cur, 1 - self.cur
+        P = self.packed
+        inner = self._inner_stripes()
+        pieces = ([("E", e0, n_own)] if n_own > e0 else []) + [(k, a, b_) for k, (a, b_) in enumerate(inner)]
+        key = ("pipe", self.iterations // self.buildneibsfreq, n_own, e0, len(inner))
+        chained = self._down_key == key
+        # ---- uploads: edge stripe first (both ends of the inner range need it), then the inner ranges in order
+        up.wait_stream(main)
+        if not chained:
+            up.wait_stream(down)
+        up_ev = {}
+        with torch.cuda.stream(up):
+            for name, a, b_ in pieces:
+                if chained:
+                    up.wait_event(self._down_ev[name])
+                self.pos[cur][a:b_].copy_(hpos[a:b_], non_blocking=True)
+                self.vel[cur][a:b_].copy_(hvel[a:b_], non_blocking=True)
+                up_ev[name] = torch.cuda.Event()
+                up_ev[name].record(up)
+
+        def landed(name, a, b_):               # the compute stream sees the piece and its neighbour records
+            main.wait_event(up_ev[name])
+            be.pack_state(self.pos[cur], self.vel[cur], P[cur], a, b_)
+        # ---- predictor: pair kernel per inner range as soon as the NEXT range is there; the integration waits for dt
+        self._wait_halo(cur)                   # the halo update of state n (sent at the end of the previous step) has landed:
+        if n_own > e0:                         # nothing still reads the edge records this step re-makes from the upload
+            landed("E", e0, n_own)
+        if inner:
+            landed(0, *inner[0])
+        args = (self.pos[cur], self.vel[cur], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
+        off = 0
+        for k, (a, b_) in enumerate(inner):
+            if k + 1 < len(inner):
+                landed(k + 1, *inner[k + 1])
+            off += be.forces(*args, a, b_, off, packed=P[cur])
+        if n_own > e0:
+            es.wait_stream(main)
+            try:
+                ctx.use_stream(es)
+                off += be.forces(*args, e0, n_own, off, packed=P[cur])
+            finally:
+                ctx.use_stream(main)
+            main.wait_stream(es)
+        self._cfl_candidate(off, 1)
+        self._finish_dt()
+        be.euler_async(self.pos[cur], self.vel[cur], self.info, self.hash, self.forces_buf, self.pos[oth], self.vel[oth],
+                       n, n_own, 1, new_packed=P[oth])
+        self._pending_x[oth] = self._start_halo_update(oth)
+        predicted = torch.cuda.Event()
+        predicted.record(main)
+        # ---- corrector: integration fused, IN PLACE into the state-n buffers, every range followed by its download
+        args2 = (self.pos[oth], self.vel[oth], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
+        fused = (self.pos[cur], self.vel[cur], self.pos[cur], self.vel[cur], 2, P[cur])
+        down_ev = {}
+
+        def download(name, a, b_, after):
+            down.wait_event(after)
+            with torch.cuda.stream(down):
+                hpos[a:b_].copy_(self.pos[cur][a:b_], non_blocking=True)
+                hvel[a:b_].copy_(self.vel[cur][a:b_], non_blocking=True)
+                down_ev[name] = torch.cuda.Event()
+                down_ev[name].record(down)
+        off = 0
+        for k, (a, b_) in enumerate(inner):
+            off += be.forces(*args2, a, b_, off, packed=P[oth], fused=fused)
+            done = torch.cuda.Event()
+            done.record(main)
+            download(k, a, b_, done)
+        if n_own > e0:
+            es.wait_event(predicted)
+            with torch.cuda.stream(es):
+                self._wait_halo(oth)
+            try:
+                ctx.use_stream(es)
+                off += be.forces(*args2, e0, n_own, off, packed=P[oth], fused=fused)
+            finally:
+                ctx.use_stream(main)
+            with torch.cuda.stream(es):
+                self._pending_x[cur] = self._start_halo_update(cur)
+                done = torch.cuda.Event()
+                done.record(es)
+            download("E", e0, n_own, done)
+            main.wait_stream(es)
+        self._cfl_candidate(off, 2)
+        self.cfl_global.copy_(self.cfl_local)
+        self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True
+        self._stale = True
+        self.launches += 2 * (len(inner) + 1) + len(pieces) + 2
+        self.iterations += 1
+        self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
+        self._down_ev, self._down_key = down_ev, key
+
+    def _step_host_plain(self, hpos, hvel, chunks):
+        """step_host around the ordinary step(): the copies in pieces, the download of step n next to the upload of
+        step n+1 (the force evaluations wait for the whole upload)."""
+        dev = self.device
         main = torch.cuda.current_stream(dev)
         n = self.numOwn
         cur = self.cur
         if n > 0:
-            b = [n * c // chunks for c in range(chunks + 1)]
             self._up.wait_stream(main)                       # whatever still reads / writes the state on the compute stream
-            if self._down_n != n or len(self._down_ev) != chunks:
-                self._up.wait_stream(self._down)             # ranges moved (a rebuild): wait for every earlier download
+            self._up.wait_stream(self._down)                 # and every earlier download (the piece tables differ)
             with torch.cuda.stream(self._up):
-                for c in range(chunks):
-                    if self._down_n == n and len(self._down_ev) == chunks:
-                        self._up.wait_event(self._down_ev[c])
-                    self.pos[cur][b[c]:b[c + 1]].copy_(hpos[b[c]:b[c + 1]], non_blocking=True)
-                    self.vel[cur][b[c]:b[c + 1]].copy_(hvel[b[c]:b[c + 1]], non_blocking=True)
+                self.pos[cur][:n].copy_(hpos[:n], non_blocking=True)
+                self.vel[cur][:n].copy_(hvel[:n], non_blocking=True)
             main.wait_stream(self._up)
             self.state_modified()
         self.step()
         n, cur = self.numOwn, self.cur
         b = [n * c // chunks for c in range(chunks + 1)]
         self._down.wait_stream(main)
-        evs = []
         with torch.cuda.stream(self._down):
             for c in range(chunks):
                 hpos[b[c]:b[c + 1]].copy_(self.pos[cur][b[c]:b[c + 1]], non_blocking=True)
                 hvel[b[c]:b[c + 1]].copy_(self.vel[cur][b[c]:b[c + 1]], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self._down)
-                evs.append(ev)
-        self._down_ev, self._down_n = evs, n
+        self._down_ev, self._down_key = {}, None
 
     def host_fence(self) -> None:
         """The compute stream waits for the copies of earlier step_host calls."""

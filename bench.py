@@ -47,7 +47,7 @@ FLOP_PER_PAIR = 80
 # as config.neibs_per_particle by every run of this file; the list is bit-identical to the reference's, see
 # tests/test_golden.py, and the reference does not print its own numInteractions counter). The reference arm multiplies
 # its particle-updates/s by this constant so that it does not have to load anything of ours.
-NEIBS_PER_PARTICLE = {"dambreak84k": 36.45, "dambreak2m": 49.68, "dambreak8m": 58.54, "dambreak16m": 61.0}
+NEIBS_PER_PARTICLE = {"dambreak84k": 36.45, "dambreak2m": 49.68, "dambreak8m": 58.54, "dambreak16m": 62.68}
 
 
 def make_problem(name, world=1, scaling="strong"):

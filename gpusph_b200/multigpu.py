@@ -69,21 +69,23 @@ def slab_partition(params: capi.Params, hashes: np.ndarray, world: int, weights:
 
 def compact_device_map(params: capi.Params, slab: tuple[int, int], rank: int, world: int) -> np.ndarray:
     """Per-cell type bits (already shifted to bits 30-31), reference createCompactDeviceMap
-    (src/GPUWorker.cc:1560-1634). Periodicity along the split axis is not supported."""
+    (src/GPUWorker.cc:1560-1634). With periodicity along the split axis the first and the last slab are neighbours: the
+    layer below the first one is the last layer of the grid and vice versa."""
     c3 = params.coord[2]
-    if params.periodic & (1 << c3):
-        raise capi.B200Unsupported("periodicity along the slab axis is not implemented for multi-GPU")
+    periodic = bool(params.periodic & (1 << c3))
     G3 = int(params.grid_size[c3])
     S = int(params.grid_size[params.coord[0]]) * int(params.grid_size[params.coord[1]])
     xs, xe = slab
+    if periodic and world > 1 and G3 < 2 * world:
+        raise ValueError("too few cell layers for a periodic split")
     t = np.full(G3, CELLTYPE_OUTER, dtype=np.uint32)
     t[xs:xe] = CELLTYPE_INNER
-    if rank > 0:
+    if rank > 0 or (periodic and world > 1):
         t[xs] = CELLTYPE_INNER_EDGE
-        t[xs - 1] = CELLTYPE_OUTER_EDGE
-    if rank < world - 1:
+        t[(xs - 1) % G3] = CELLTYPE_OUTER_EDGE
+    if rank < world - 1 or (periodic and world > 1):
         t[xe - 1] = CELLTYPE_INNER_EDGE
-        t[xe] = CELLTYPE_OUTER_EDGE
+        t[xe % G3] = CELLTYPE_OUTER_EDGE
     return np.repeat(t << 30, S).astype(np.uint32)
 
 
@@ -193,8 +195,15 @@ class SlabWorker:
         self.S = S
         xs, xe = self.slab
         layer = (particles.hash.astype(np.int64) & CELLMASK) // S
-        lo, hi = xs - (1 if rank > 0 else 0), xe + (1 if rank < world - 1 else 0)
-        sel = np.flatnonzero((layer >= lo) & (layer < hi))          # own cells + halo layers
+        G3 = int(params.grid_size[c3])
+        self.periodic_split = bool(params.periodic & (1 << c3)) and world > 1
+        keep = np.zeros(G3, dtype=bool)                              # own cell layers + one halo layer per neighbour
+        keep[xs:xe] = True
+        if rank > 0 or self.periodic_split:
+            keep[(xs - 1) % G3] = True
+        if rank < world - 1 or self.periodic_split:
+            keep[xe % G3] = True
+        sel = np.flatnonzero(keep[layer])
         n = sel.shape[0]
         self.allocated = int(n * alloc_factor) + 1024
         p = params.copy()
@@ -289,10 +298,31 @@ class SlabWorker:
 
     # ------------------------------------------------------------------ communication helpers
     def _left(self):
+        if self.periodic_split:
+            return (self.rank - 1) % self.world
         return self.rank - 1 if self.rank > 0 else None
 
     def _right(self):
+        if self.periodic_split:
+            return (self.rank + 1) % self.world
         return self.rank + 1 if self.rank < self.world - 1 else None
+
+    def _halo_pairs(self, t, edge_left=None, edge_right=None, halo_left=None, halo_right=None):
+        """(sends, recvs) moving the edge layers of array `t` (row = particle) into the neighbours' halo ranges. Sends
+        are posted right neighbour first, receives left neighbour first: when both neighbours are the SAME rank (two
+        slabs of a periodic split) messages between two ranks match in posting order, and my left halo is that rank's
+        right edge."""
+        el, er = edge_left or self.edge_left, edge_right or self.edge_right
+        hl, hr = halo_left or self.halo_left, halo_right or self.halo_right
+        sends, recvs = [], []
+        if self._right() is not None:
+            sends.append((t[er[0]:er[0] + er[1]], self._right()))
+        if self._left() is not None:
+            sends.append((t[el[0]:el[0] + el[1]], self._left()))
+            recvs.append((t[hl[0]:hl[0] + hl[1]], self._left()))
+        if self._right() is not None:
+            recvs.append((t[hr[0]:hr[0] + hr[1]], self._right()))
+        return sends, recvs
 
     def _exchange(self, sends, recvs):
         """sends/recvs: lists of (tensor, peer). One batched NCCL group (reference: transferBursts)."""
@@ -315,10 +345,12 @@ class SlabWorker:
         sr = torch.tensor([n_to_right], dtype=torch.int64, device=dev)
         rl = torch.zeros(1, dtype=torch.int64, device=dev)
         rr = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self._right() is not None:
+            sends.append((sr, self._right()))
         if self._left() is not None:
             sends.append((sl, self._left())); recvs.append((rl, self._left()))
         if self._right() is not None:
-            sends.append((sr, self._right())); recvs.append((rr, self._right()))
+            recvs.append((rr, self._right()))
         self._exchange(sends, recvs)
         out["from_left"] = int(rl.item()) if self._left() is not None else 0
         out["from_right"] = int(rr.item()) if self._right() is not None else 0
@@ -379,14 +411,8 @@ class SlabWorker:
         self.halo_right = (n_own + nl_, nr_)
         sends, recvs = [], []
         for buf in (self.pos[cur], self.vel[cur], self.info, self.hash):
-            if self._left() is not None:
-                a, c = self.edge_left
-                sends.append((buf[a:a + c], self._left()))
-                recvs.append((buf[self.halo_left[0]:self.halo_left[0] + nl_], self._left()))
-            if self._right() is not None:
-                a, c = self.edge_right
-                sends.append((buf[a:a + c], self._right()))
-                recvs.append((buf[self.halo_right[0]:self.halo_right[0] + nr_], self._right()))
+            s_, r_ = self._halo_pairs(buf)
+            sends += s_; recvs += r_
         self._exchange(sends, recvs)
         n = n_own + nl_ + nr_
         # received hashes carry the sender's INNER_EDGE bits: they are OUTER_EDGE here
@@ -427,12 +453,8 @@ class SlabWorker:
         if ops is None:
             sends, recvs = [], []
             for t in self._halo_tensors(which):
-                if self._left() is not None:
-                    sends.append((t[self.edge_left[0]:self.edge_left[0] + self.edge_left[1]], self._left()))
-                    recvs.append((t[self.halo_left[0]:self.halo_left[0] + self.halo_left[1]], self._left()))
-                if self._right() is not None:
-                    sends.append((t[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
-                    recvs.append((t[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
+                s_, r_ = self._halo_pairs(t)
+                sends += s_; recvs += r_
             ops = [dist.P2POp(dist.isend, t.view(torch.uint8), peer, self.group) for t, peer in sends if t.numel()]
             ops += [dist.P2POp(dist.irecv, t.view(torch.uint8), peer, self.group) for t, peer in recvs if t.numel()]
             self._xops[which] = ops
@@ -587,12 +609,8 @@ class SlabWorker:
         """Host-dt path with the CUDA engines: the halo update carries the pos / vel arrays themselves."""
         sends, recvs = [], []
         for t in (self.pos[which], self.vel[which]):
-            if self._left() is not None:
-                sends.append((t[self.edge_left[0]:self.edge_left[0] + self.edge_left[1]], self._left()))
-                recvs.append((t[self.halo_left[0]:self.halo_left[0] + self.halo_left[1]], self._left()))
-            if self._right() is not None:
-                sends.append((t[self.edge_right[0]:self.edge_right[0] + self.edge_right[1]], self._right()))
-                recvs.append((t[self.halo_right[0]:self.halo_right[0] + self.halo_right[1]], self._right()))
+            s_, r_ = self._halo_pairs(t)
+            sends += s_; recvs += r_
         return self._exchange_start(sends, recvs)
 
     def state_modified(self) -> None:
@@ -645,8 +663,26 @@ class SlabWorker:
             self._down_ev, self._down_key = {}, None
         rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
         records = self.device_dt and self.packed is not None and self._edge_stream is not None
-        if rebuild or not records or self.numOwn == 0:
+        if not records or self.numOwn == 0:
             return self._step_host_plain(hpos, hvel, chunks)
+        resident = False
+        if rebuild:
+            # the sort needs the whole state: upload it (behind every earlier download), rebuild, then run the same
+            # pipelined step on the resident, re-sorted state (only its downloads are left to overlap)
+            main0 = torch.cuda.current_stream(dev)
+            n0, cur0 = self.numOwn, self.cur
+            self._up.wait_stream(main0)
+            self._up.wait_stream(self._down)
+            with torch.cuda.stream(self._up):
+                self.pos[cur0][:n0].copy_(hpos[:n0], non_blocking=True)
+                self.vel[cur0][:n0].copy_(hvel[:n0], non_blocking=True)
+            main0.wait_stream(self._up)
+            self.state_modified()
+            self.build_neibs()
+            self._down_key = None
+            resident = True
+            if self.numOwn == 0:
+                return self._step_host_plain(hpos, hvel, chunks)
         be = self.backend
         ctx = be.fw.ctx
         main, es, up, down = torch.cuda.current_stream(dev), self._edge_stream, self._up, self._down
@@ -659,20 +695,26 @@ class SlabWorker:
         key = ("pipe", self.iterations // self.buildneibsfreq, n_own, e0, len(inner))
         chained = self._down_key == key
         # ---- uploads: edge stripe first (both ends of the inner range need it), then the inner ranges in order
-        up.wait_stream(main)
-        if not chained:
-            up.wait_stream(down)
         up_ev = {}
-        with torch.cuda.stream(up):
-            for name, a, b_ in pieces:
-                if chained:
-                    up.wait_event(self._down_ev[name])
-                self.pos[cur][a:b_].copy_(hpos[a:b_], non_blocking=True)
-                self.vel[cur][a:b_].copy_(hvel[a:b_], non_blocking=True)
-                up_ev[name] = torch.cuda.Event()
-                up_ev[name].record(up)
+        if not resident:
+            up.wait_stream(main)
+            if not chained:
+                up.wait_stream(down)
+            with torch.cuda.stream(up):
+                for name, a, b_ in pieces:
+                    if chained:
+                        up.wait_event(self._down_ev[name])
+                    self.pos[cur][a:b_].copy_(hpos[a:b_], non_blocking=True)
+                    self.vel[cur][a:b_].copy_(hvel[a:b_], non_blocking=True)
+                    up_ev[name] = torch.cuda.Event()
+                    up_ev[name].record(up)
+        else:
+            # earlier downloads read the buffers the corrector is about to integrate in place
+            main.wait_stream(down)
 
         def landed(name, a, b_):               # the compute stream sees the piece and its neighbour records
+            if resident:
+                return                         # the rebuild left state and records of every particle on the device
             main.wait_event(up_ev[name])
             be.pack_state(self.pos[cur], self.vel[cur], P[cur], a, b_)
         # ---- predictor: pair kernel per inner range as soon as the NEXT range is there; the integration waits for dt

@@ -20,20 +20,25 @@ from gpusph_b200.multigpu import compact_device_map, slab_partition  # noqa: E40
 from gpusph_b200.problems import dambreak_problem, lattice_problem  # noqa: E402
 
 
-def make_problem():
-    params, parts = lattice_problem(14, ny=8, nz=8, jitter=0.2, densitydiffusion=capi.RHODIFF_COLAGROSSI)
+def make_problem(periodic=False):
+    if periodic:
+        # periodic along x, the slab axis of the default yzx linearisation: the first and the last slab are neighbours.
+        # The domain must be a whole number of lattice spacings long for the lattice to close on itself.
+        params, parts = lattice_problem(16, ny=8, nz=8, jitter=0.2, densitydiffusion=capi.RHODIFF_COLAGROSSI, periodic=capi.PERIODIC_X)
+    else:
+        params, parts = lattice_problem(14, ny=8, nz=8, jitter=0.2, densitydiffusion=capi.RHODIFF_COLAGROSSI)
     # a strong flow along the split axis so that particles cross the slab face within a few steps
     parts.vel[:, 0] += 6.0
     return params, parts
 
 
-def _rank_main(rank, world, port, steps, outdir, device_dt=False):
+def _rank_main(rank, world, port, steps, outdir, device_dt=False, periodic=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     from gpusph_b200.multigpu import SlabWorker
     from oracle_backend import OracleBackend, OracleDeviceDtBackend
-    params, parts = make_problem()
+    params, parts = make_problem(periodic)
     w = SlabWorker(params, parts, None, rank=rank, world=world, backend=OracleDeviceDtBackend if device_dt else OracleBackend)
     assert w.device_dt == device_dt
     own0 = None
@@ -67,9 +72,40 @@ def test_partition_and_device_map():
     assert (t[xs + 1:xe - 1] == 0).all() and (t[:xs - 1] == 3).all() and (t[xe + 1:] == 3).all()
     with pytest.raises(ValueError):
         slab_partition(params, parts.hash, G3)        # fewer than 2 layers per device
+    # periodic along the slab axis: the layer "below" the first slab is the last layer of the grid
     pp, _ = lattice_problem(6, periodic=1 << params.coord[2])
-    with pytest.raises(capi.B200Unsupported):
-        compact_device_map(pp, (0, 2), 0, 2)
+    Gp = int(pp.grid_size[pp.coord[2]])
+    Sp = int(pp.grid_size[pp.coord[0]]) * int(pp.grid_size[pp.coord[1]])
+    tp = (compact_device_map(pp, (0, Gp // 2), 0, 2) >> 30).reshape(Gp, Sp)
+    assert (tp[0] == 1).all() and (tp[Gp // 2 - 1] == 1).all() and (tp[Gp - 1] == 2).all() and (tp[Gp // 2] == 2).all()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 3])
+def test_periodic_slab_axis_matches_single_domain_bitwise(world):
+    """Periodicity ALONG the slab axis (the reference's device map handles it, src/GPUWorker.cc:1560-1634): the first and
+    the last slab exchange halos across the periodic face; with two slabs both neighbours of a rank are the same rank."""
+    import oracle_binding as ob
+    steps = 12
+    params, parts = make_problem(periodic=True)
+    ref = ob.OracleWorker(params, parts)
+    for _ in range(steps):
+        ref.step()
+    exp = ref.download()
+    with tempfile.TemporaryDirectory() as d:
+        port = 31500 + (os.getpid() % 2000) + world
+        mp.spawn(_rank_main, args=(world, port, steps, d, True, True), nprocs=world, join=True)
+        r = [np.load(os.path.join(d, f"rank{k}.npz")) for k in range(world)]
+    ids = np.concatenate([ids_of(r[k]["info"]) for k in range(world)])
+    assert np.array_equal(np.sort(ids), np.arange(parts.n))
+    assert any(int(r[k]["own0"]) != r[k]["pos"].shape[0] for k in range(world)), "particles should change owner"
+    pos = np.concatenate([r[k]["pos"] for k in range(world)])
+    vel = np.concatenate([r[k]["vel"] for k in range(world)])
+    hashv = np.concatenate([r[k]["hash"] for k in range(world)]) & 0x3FFFFFFF
+    o, oe = np.argsort(ids), np.argsort(ids_of(exp.info))
+    assert np.array_equal(hashv[o], exp.hash[oe])
+    assert np.array_equal(pos[o].view(np.uint32), exp.pos[oe].view(np.uint32))
+    assert np.array_equal(vel[o].view(np.uint32), exp.vel[oe].view(np.uint32))
 
 
 @pytest.mark.timeout(600)

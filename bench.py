@@ -276,6 +276,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the engines have no CPU fallback")
     torch.cuda.set_device(local)
+    # one process per GPU: keep the process (and the pinned host buffers it allocates) on the GPU's own socket
+    from gpusph_b200.hostmem import bind_host_near_gpu
+    host_affinity = bind_host_near_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gpusph_b200.simulation import Worker
@@ -472,6 +475,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "particles": n_global,
                        "neibs_per_particle": w.last_neibs_info.num_interactions / max(w.numOwn if world > 1 else w.numParticles, 1),
+                       "host_affinity": host_affinity or "unbound",
                        "buildneibsfreq": 10, "density_diffusion": "ferrari" if "dambreak" in args.workload else "none",
                        "viscosity": "laminar (Morris)" if "poiseuille" in args.workload else "artificial",
                        "l2": f"inputs larger than L2 (working set {working_set / 1e6:.0f} MB vs 126 MB)" if working_set > L2_BYTES

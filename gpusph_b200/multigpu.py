@@ -267,6 +267,17 @@ class SlabWorker:
         if isinstance(self.backend, CudaBackend) and os.environ.get("B200SPH_SLAB_EDGE_STREAM", "1") != "0":
             self._edge_stream = torch.cuda.Stream(self.device, priority=-1)
 
+    def _mark(self, label: str, stream=None) -> None:
+        """Diagnostics (tools/diag_slab_*.py): with self._trace a list, record a timed event on `stream` (default: the
+        current one) together with the host clock at enqueue time."""
+        trace = getattr(self, "_trace", None)
+        if trace is None:
+            return
+        import time
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+        trace.append((self.iterations, label, ev, time.perf_counter()))
+
     def _finish_dt(self):
         """Complete the step whose dt candidates are still being all-reduced: dt = f(global CFL maxima), t += dt."""
         if self._pending_dt is None:
@@ -364,6 +375,7 @@ class SlabWorker:
         # halo updates still in flight land first; with neighbour records the halo particles only live as records
         # between rebuilds: bring them back into pos / vel, where the hash update below looks for particles that
         # crossed the slab face (that is how ownership changes, src/Integrator.cc:216-221)
+        self._mark("rebuild: begin")
         self._wait_halo(0)
         self._wait_halo(1)
         self._xops = {}
@@ -378,6 +390,7 @@ class SlabWorker:
                    self.info, self.hash, self.partindex, n, self.new_num)
         self.cur = cur = oth
         oth = 1 - cur
+        self._mark("rebuild: hash+sort+reorder")
         # one packed readback: segment starts, active count and the particle ranges of the two edge layers
         # (contiguous: the slab axis is the slowest hash digit, so a cell layer is one run of cells)
         xs, xe = self.slab
@@ -403,8 +416,10 @@ class SlabWorker:
         # first inner-edge particle: [0, edge_start) is the inner stripe, [edge_start, n_own) the edge stripe
         self.edge_start = int(seg[1]) if seg[1] != 0xFFFFFFFF else n_own
         # APPEND_EXTERNAL: fresh halo copies from the owners (pos, vel, info, hash)
+        self._mark("rebuild: readback")
         cnt = self._exchange_counts(self.edge_left[1], self.edge_right[1])
         nl_, nr_ = cnt["from_left"], cnt["from_right"]
+        self._mark("rebuild: counts exchanged")
         if n_own + nl_ + nr_ > self.allocated:
             raise MemoryError(f"rank {self.rank}: {n_own + nl_ + nr_} particles exceed the allocation {self.allocated}")
         self.halo_left = (n_own, nl_)
@@ -425,11 +440,13 @@ class SlabWorker:
         be.reorder(self.cellstart, self.cellend, self.segments, self.pos[oth], self.vel[oth], self.pos[cur], self.vel[cur],
                    self.info, self.hash, self.partindex, n, self.new_num)
         self.cur = oth
+        self._mark("rebuild: halo appended + cell ranges")
         # BUILDNEIBS for the particles this rank owns (their neighbours include the halo)
         self.last_neibs_info = be.build_neibs(self.pos[self.cur], self.info, self.hash, self.cellstart, self.cellend,
                                               self.neibslist, n, n_own)
         if records:
             be.pack_state(self.pos[self.cur], self.vel[self.cur], self.packed[self.cur], 0, n)
+        self._mark("rebuild: list built")
         self.launches += 9
 
     # ------------------------------------------------------------------ time stepping
@@ -561,14 +578,19 @@ class SlabWorker:
             # the first integration needs it: the all-reduce (one per step, both maxima) overlaps with the predictor's
             # pair kernels, which is why the predictor integrates in a separate (streaming) launch and the corrector,
             # whose dt is known by then, in the pair kernel's epilogue.
+            self._mark("step: begin")
             self._forces(cur, 1)
+            self._mark("predictor forces")
             self._finish_dt()
             be.euler_async(*eargs, 1, new_packed=self.packed[oth])
+            self._mark("dt + predictor euler")
             self._pending_x[oth] = self._start_halo_update(oth)
             self._forces(oth, 2, fused=(cur, 2))         # state n+1 lands IN PLACE in the buffers of state n
+            self._mark("corrector forces+euler")
             self.cfl_global.copy_(self.cfl_local)
             self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True
             self._stale = True
+            self._mark("step: end")
             self.launches += 1
             oth = cur
         elif self.device_dt:
@@ -660,76 +682,99 @@ class SlabWorker:
         dev = self.device
         if getattr(self, "_up", None) is None:
             self._up, self._down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._upE, self._downE = torch.cuda.Stream(dev), torch.cuda.Stream(dev)   # the edge stripe's own copy lanes
             self._down_ev, self._down_key = {}, None
         rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
         records = self.device_dt and self.packed is not None and self._edge_stream is not None
         if not records or self.numOwn == 0:
             return self._step_host_plain(hpos, hvel, chunks)
+        mark = self._mark
         resident = False
         if rebuild:
             # the sort needs the whole state: upload it (behind every earlier download), rebuild, then run the same
             # pipelined step on the resident, re-sorted state (only its downloads are left to overlap)
             main0 = torch.cuda.current_stream(dev)
             n0, cur0 = self.numOwn, self.cur
+            mark("rebuild: begin", main0)
             self._up.wait_stream(main0)
             self._up.wait_stream(self._down)
+            self._up.wait_stream(self._downE)
             with torch.cuda.stream(self._up):
                 self.pos[cur0][:n0].copy_(hpos[:n0], non_blocking=True)
                 self.vel[cur0][:n0].copy_(hvel[:n0], non_blocking=True)
             main0.wait_stream(self._up)
+            mark("rebuild: uploaded", main0)
             self.state_modified()
             self.build_neibs()
+            mark("rebuild: done", main0)
             self._down_key = None
             resident = True
             if self.numOwn == 0:
                 return self._step_host_plain(hpos, hvel, chunks)
         be = self.backend
         ctx = be.fw.ctx
-        main, es, up, down = torch.cuda.current_stream(dev), self._edge_stream, self._up, self._down
+        main, es = torch.cuda.current_stream(dev), self._edge_stream
         n, n_own = self.numParticles, self.numOwn
         e0 = min(self.edge_start, n_own)
         cur, oth = self.cur, 1 - self.cur
         P = self.packed
         inner = self._inner_stripes()
-        pieces = ([("E", e0, n_own)] if n_own > e0 else []) + [(k, a, b_) for k, (a, b_) in enumerate(inner)]
-        key = ("pipe", self.iterations // self.buildneibsfreq, n_own, e0, len(inner))
+        K = len(inner)
+        ranges = {k: ab for k, ab in enumerate(inner)}
+        if n_own > e0:
+            ranges["E"] = (e0, n_own)
+        lane_up = lambda name: self._upE if name == "E" else self._up
+        lane_down = lambda name: self._downE if name == "E" else self._down
+        key = ("pipe", self.iterations // self.buildneibsfreq, n_own, e0, K)
         chained = self._down_key == key
-        # ---- uploads: edge stripe first (both ends of the inner range need it), then the inner ranges in order
+        mark("step: begin", main)
+        # ---- uploads: the inner ranges in order on one lane, the edge stripe on its own. Chained to the previous step
+        # piece by piece: the upload of a piece waits only for the download of the same piece (which followed its
+        # corrector), so the copies of step n+1 run under the corrector of step n.
         up_ev = {}
         if not resident:
-            up.wait_stream(main)
-            if not chained:
-                up.wait_stream(down)
-            with torch.cuda.stream(up):
-                for name, a, b_ in pieces:
-                    if chained:
-                        up.wait_event(self._down_ev[name])
+            for name, (a, b_) in ranges.items():
+                lu = lane_up(name)
+                if chained:
+                    lu.wait_event(self._down_ev[name])
+                else:
+                    lu.wait_stream(main)
+                    lu.wait_stream(self._down)
+                    lu.wait_stream(self._downE)
+                with torch.cuda.stream(lu):
                     self.pos[cur][a:b_].copy_(hpos[a:b_], non_blocking=True)
                     self.vel[cur][a:b_].copy_(hvel[a:b_], non_blocking=True)
                     up_ev[name] = torch.cuda.Event()
-                    up_ev[name].record(up)
+                    up_ev[name].record(lu)
+                    mark(f"up {name}", lu)
         else:
             # earlier downloads read the buffers the corrector is about to integrate in place
-            main.wait_stream(down)
+            main.wait_stream(self._down)
+            main.wait_stream(self._downE)
+        have = set()
 
-        def landed(name, a, b_):               # the compute stream sees the piece and its neighbour records
-            if resident:
-                return                         # the rebuild left state and records of every particle on the device
-            main.wait_event(up_ev[name])
-            be.pack_state(self.pos[cur], self.vel[cur], P[cur], a, b_)
-        # ---- predictor: pair kernel per inner range as soon as the NEXT range is there; the integration waits for dt
+        def need(*names):                      # the compute stream sees these pieces and their neighbour records
+            for name in names:
+                if resident or name in have or name not in ranges:
+                    continue                   # (a rebuild left state and records of every particle on the device)
+                have.add(name)
+                main.wait_event(up_ev[name])
+                be.pack_state(self.pos[cur], self.vel[cur], P[cur], *ranges[name])
+        # ---- predictor: the pair kernel of an inner range runs as soon as the range and its two neighbours are there;
+        # the ranges next to the edge stripe (first and last) go last. The integration waits for dt.
         self._wait_halo(cur)                   # the halo update of state n (sent at the end of the previous step) has landed:
-        if n_own > e0:                         # nothing still reads the edge records this step re-makes from the upload
-            landed("E", e0, n_own)
-        if inner:
-            landed(0, *inner[0])
+        #                                        nothing still reads the edge records this step re-makes from the upload
         args = (self.pos[cur], self.vel[cur], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
         off = 0
-        for k, (a, b_) in enumerate(inner):
-            if k + 1 < len(inner):
-                landed(k + 1, *inner[k + 1])
-            off += be.forces(*args, a, b_, off, packed=P[cur])
+        order = list(range(1, K - 1)) + ([0] if K >= 1 else []) + ([K - 1] if K >= 2 else [])
+        for k in order:
+            need(k - 1, k, k + 1)
+            if k == 0 or k == K - 1:
+                need("E")
+            off += be.forces(*args, *ranges[k], off, packed=P[cur])
+            mark(f"pred {k}", main)
         if n_own > e0:
+            need("E", 0, K - 1)
             es.wait_stream(main)
             try:
                 ctx.use_stream(es)
@@ -744,24 +789,29 @@ class SlabWorker:
         self._pending_x[oth] = self._start_halo_update(oth)
         predicted = torch.cuda.Event()
         predicted.record(main)
+        mark("predicted", main)
         # ---- corrector: integration fused, IN PLACE into the state-n buffers, every range followed by its download
         args2 = (self.pos[oth], self.vel[oth], self.info, self.hash, self.cellstart, self.neibslist, self.forces_buf, self.cfl, n)
         fused = (self.pos[cur], self.vel[cur], self.pos[cur], self.vel[cur], 2, P[cur])
         down_ev = {}
 
-        def download(name, a, b_, after):
-            down.wait_event(after)
-            with torch.cuda.stream(down):
+        def download(name, after):
+            a, b_ = ranges[name]
+            ld = lane_down(name)
+            ld.wait_event(after)
+            with torch.cuda.stream(ld):
                 hpos[a:b_].copy_(self.pos[cur][a:b_], non_blocking=True)
                 hvel[a:b_].copy_(self.vel[cur][a:b_], non_blocking=True)
                 down_ev[name] = torch.cuda.Event()
-                down_ev[name].record(down)
+                down_ev[name].record(ld)
+                mark(f"down {name}", ld)
         off = 0
-        for k, (a, b_) in enumerate(inner):
-            off += be.forces(*args2, a, b_, off, packed=P[oth], fused=fused)
+        for k in range(K):
+            off += be.forces(*args2, *ranges[k], off, packed=P[oth], fused=fused)
             done = torch.cuda.Event()
             done.record(main)
-            download(k, a, b_, done)
+            mark(f"corr {k}", main)
+            download(k, done)
         if n_own > e0:
             es.wait_event(predicted)
             with torch.cuda.stream(es):
@@ -775,13 +825,15 @@ class SlabWorker:
                 self._pending_x[cur] = self._start_halo_update(cur)
                 done = torch.cuda.Event()
                 done.record(es)
-            download("E", e0, n_own, done)
+                mark("corr E", es)
+            download("E", done)
             main.wait_stream(es)
         self._cfl_candidate(off, 2)
         self.cfl_global.copy_(self.cfl_local)
         self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True
         self._stale = True
-        self.launches += 2 * (len(inner) + 1) + len(pieces) + 2
+        mark("step: end", main)
+        self.launches += 2 * (K + 1) + len(ranges) + 2
         self.iterations += 1
         self.total_interactions += 2 * int(self.last_neibs_info.num_interactions)
         self._down_ev, self._down_key = down_ev, key
@@ -796,6 +848,7 @@ class SlabWorker:
         if n > 0:
             self._up.wait_stream(main)                       # whatever still reads / writes the state on the compute stream
             self._up.wait_stream(self._down)                 # and every earlier download (the piece tables differ)
+            self._up.wait_stream(self._downE)
             with torch.cuda.stream(self._up):
                 self.pos[cur][:n].copy_(hpos[:n], non_blocking=True)
                 self.vel[cur][:n].copy_(hvel[:n], non_blocking=True)
@@ -815,6 +868,7 @@ class SlabWorker:
         """The compute stream waits for the copies of earlier step_host calls."""
         if getattr(self, "_down", None) is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._down)
+            torch.cuda.current_stream(self.device).wait_stream(self._downE)
 
     def download_own(self) -> ParticleArrays:
         n = self.numOwn

@@ -142,6 +142,7 @@ struct b200sph_ctx {
 	cudaStream_t lane_stream[B200_MAX_LANES]; int host_lanes;        // extra compute lanes ([0] unused: the context's stream)
 	cudaEvent_t fork_ev[2], join_ev[2 * B200_MAX_LANES];
 	uint32_t host_bounds[B200SPH_MAX_STRIPES + 1]; uint32_t host_nstripes;
+	uint32_t host_ring_next;      // periodic COORD3: the stripe the next b200sph_step_host starts its ring at (hoststep.cu)
 	const void *host_pos_last, *host_vel_last, *dev_pos_last, *dev_vel_last;
 	int host_pending;
 	cudaEvent_t *trace_ev; int trace_resident;      // B200SPH_HOST_TRACE diagnostics

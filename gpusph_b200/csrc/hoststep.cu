@@ -8,6 +8,11 @@
 // whole cell layers on three streams, and consecutive calls are chained stripe by stripe (the upload of stripe s of
 // step n+1 only waits for the download of stripe s of step n), so PCIe runs in both directions while the pair kernel
 // computes. Results are bitwise those of the resident path: same kernels, same arguments, same order per particle.
+//
+// Periodicity along COORD3 (the stripes' axis) closes the stripes into a RING: stripe 0 and stripe ns-1 are neighbours.
+// A call then starts the ring at stripe r: uploads r-1, r, r+1, ..., r-2; predictors r, ..., r-1; correctors (and
+// downloads) r+1, ..., r-2 behind the predictor wave, then r-1 and r, which need the last predictor. The next call
+// starts at r+2, so its upload order (r+1, r+2, ...) is this call's download order and the chain stays stripe by stripe.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -62,22 +67,31 @@ void b200_hoststep_destroy(b200sph_ctx *ctx)
 // the same host buffers from the same device buffers with a stripe table covering n particles, stripe s only waits
 // for that download (which itself followed the last device-side use of the stripe); otherwise the upload stream
 // waits for everything enqueued so far on the compute and download streams.
+// `first` != 0 (ring order first, first+1, ..., first-1): chained only on an identical stripe table, stripe by stripe.
 static int enqueue_uploads(b200sph_ctx *ctx, const void *host_pos, const void *host_vel, void *pos, void *vel,
-	const uint32_t *bounds, uint32_t ns)
+	const uint32_t *bounds, uint32_t ns, uint32_t first = 0)
 {
-	const bool chained = ctx->host_pending && ctx->host_pos_last == host_pos && ctx->host_vel_last == host_vel &&
+	bool chained = ctx->host_pending && ctx->host_pos_last == host_pos && ctx->host_vel_last == host_vel &&
 		ctx->dev_pos_last == pos && ctx->dev_vel_last == vel && ctx->host_nstripes > 0 &&
 		ctx->host_bounds[ctx->host_nstripes] == bounds[ns];
+	if (first != 0) {
+		chained = chained && ctx->host_nstripes == ns;
+		for (uint32_t k = 0; chained && k <= ns; ++k) chained = ctx->host_bounds[k] == bounds[k];
+	}
 	if (!chained) {
 		CUDA_TRY(cudaEventRecord(ctx->fence_ev, ctx->stream));
 		CUDA_TRY(cudaStreamWaitEvent(ctx->up_stream, ctx->fence_ev, 0));
 		if (ctx->host_pending) CUDA_TRY(cudaStreamWaitEvent(ctx->up_stream, ctx->down_all_ev, 0));
 	}
 	uint32_t waited = 0;   // stripes [0, waited) of the previous call's table have been waited for
-	for (uint32_t k = 0; k < ns; ++k) {
+	for (uint32_t i = 0; i < ns; ++i) {
+		const uint32_t k = (first + i) % ns;
 		const uint32_t a = bounds[k], b = bounds[k + 1];
-		// the previous call's downloads into [a, b): its stripes are ordered, and so is the upload stream
-		if (chained)
+		// the previous call's downloads into [a, b): the upload stream is ordered, so with ascending stripes every
+		// download event is waited for once, before the first upload that touches its range
+		if (chained && first != 0)
+			CUDA_TRY(cudaStreamWaitEvent(ctx->up_stream, ctx->down_ev[k], 0));
+		else if (chained)
 			for (; waited < ctx->host_nstripes && ctx->host_bounds[waited] < b; ++waited)
 				CUDA_TRY(cudaStreamWaitEvent(ctx->up_stream, ctx->down_ev[waited], 0));
 		const size_t off = (size_t)a * 16, bytes = (size_t)(b - a) * 16;
@@ -135,6 +149,10 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 	rc = host_streams(ctx);
 	if (rc) return rc;
 	const uint32_t *B = a->stripe_bounds;
+	// periodic along the stripes' axis: a ring of stripes (2 stripes are each other's only neighbours either way)
+	const bool ring = (ctx->hp.periodic & (1u << ctx->hp.coord[2])) != 0 && ns >= 3;
+	const uint32_t r0 = ring ? ctx->host_ring_next % ns : 0;                 // where this call's ring starts
+	auto ring_pos = [&](uint32_t k) { return (k + ns - r0) % ns; };           // place of stripe k in the predictor order
 	// Two compute lanes: P (the context's stream) runs the predictor of stripe k — forces(n), euler step 1 (dt/2) -> n* —
 	// and Q the corrector of stripe k-1 — forces(n*), euler step 2 IN PLACE into the state-n buffers, download — as
 	// soon as n* exists for stripes k-2..k. The corrector of a stripe therefore starts long before the predictor of the
@@ -153,7 +171,7 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		CUDA_TRY(cudaStreamWaitEvent(Q, ctx->fork_ev[0], 0));
 	}
 	if (!a->resident) {
-		rc = enqueue_uploads(ctx, a->host_pos, a->host_vel, a->pos, a->vel, B, ns);
+		rc = enqueue_uploads(ctx, a->host_pos, a->host_vel, a->pos, a->vel, B, ns, ring ? (r0 + ns - 1) % ns : 0);
 		if (rc) return rc;
 	}
 
@@ -172,6 +190,14 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		return r;
 	};
 	if (a->resident) { rc = pack_upto(ns); if (rc) return rc; }
+	bool have[B200SPH_MAX_STRIPES] = {};              // ring: stripes whose upload P has waited for and whose records exist
+	auto need_stripe = [&](uint32_t k) -> int {
+		if (a->resident || have[k]) return B200SPH_OK;
+		have[k] = true;
+		CUDA_TRY(cudaStreamWaitEvent(P, ctx->up_ev[k], 0));
+		ctx->stream = P;
+		return b200sph_pack_state(ctx, a->pos, a->vel, pv_n, B[k], B[k + 1]);
+	};
 
 	b200sph_forces_args f;
 	memset(&f, 0, sizeof(f));
@@ -186,8 +212,12 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		const uint32_t s = B[k], e = B[k + 1];
 		const size_t o16 = (size_t)s * 16;
 		ctx->stream = P;
-		if (!a->resident) CUDA_TRY(cudaStreamWaitEvent(P, ctx->up_ev[k + 1 < ns ? k + 1 : ns - 1], 0));
-		{ const int r = pack_upto(k + 2); if (r) return r; }
+		if (ring) {
+			for (uint32_t d = 0; d < 3; ++d) { const int rn = need_stripe((k + ns - 1 + d) % ns); if (rn) return rn; }
+		} else {
+			if (!a->resident) CUDA_TRY(cudaStreamWaitEvent(P, ctx->up_ev[k + 1 < ns ? k + 1 : ns - 1], 0));
+			const int rp = pack_upto(k + 2); if (rp) return rp;
+		}
 		if (xsph) CUDA_TRY(cudaMemsetAsync((char *)a->xsph + o16, 0, (size_t)(e - s) * 16, P));
 		f.pos = a->pos; f.vel = a->vel; f.step = 1; f.packed = pv_n;
 		f.from_particle = s; f.to_particle = e; f.cfl_offset = offP;
@@ -209,7 +239,12 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		const uint32_t s = B[j], e = B[j + 1];
 		const size_t o16 = (size_t)s * 16;
 		ctx->stream = Q;
-		if (Q != P) CUDA_TRY(cudaStreamWaitEvent(Q, ctx->pred_ev[j + 1 < ns ? j + 1 : ns - 1], 0));
+		uint32_t last = j + 1 < ns ? j + 1 : ns - 1;     // the predictor that completes n* of stripes j-1..j+1
+		if (ring) {
+			last = j;
+			for (uint32_t d = 0; d < 3; d += 2) { const uint32_t k = (j + ns - 1 + d) % ns; if (ring_pos(k) > ring_pos(last)) last = k; }
+		}
+		if (Q != P) CUDA_TRY(cudaStreamWaitEvent(Q, ctx->pred_ev[last], 0));
 		if (xsph) CUDA_TRY(cudaMemsetAsync((char *)a->xsph + o16, 0, (size_t)(e - s) * 16, Q));
 		f.pos = a->pos_star; f.vel = a->vel_star; f.step = 2; f.packed = pv_star;
 		f.from_particle = s; f.to_particle = e; f.cfl_offset = cflQ + offQ;
@@ -229,13 +264,26 @@ extern "C" int b200sph_step_host(b200sph_ctx *ctx, const b200sph_host_step_args 
 		TRACE(TR_DOWN + j, D);
 		return B200SPH_OK;
 	};
-	for (uint32_t k = 0; k < ns; ++k) {
-		rc = predictor(k);
+	if (ring) {
+		for (uint32_t i = 0; i < ns; ++i) {
+			rc = predictor((r0 + i) % ns);
+			if (rc) return rc;
+			if (i >= 2) { rc = corrector((r0 + i - 1) % ns); if (rc) return rc; }
+		}
+		rc = corrector((r0 + ns - 1) % ns);           // the two stripes next to where the ring was cut
 		if (rc) return rc;
-		if (k >= 1) { rc = corrector(k - 1); if (rc) return rc; }
+		rc = corrector(r0);
+		if (rc) return rc;
+		ctx->host_ring_next = (r0 + 2) % ns;
+	} else {
+		for (uint32_t k = 0; k < ns; ++k) {
+			rc = predictor(k);
+			if (rc) return rc;
+			if (k >= 1) { rc = corrector(k - 1); if (rc) return rc; }
+		}
+		rc = corrector(ns - 1);
+		if (rc) return rc;
 	}
-	rc = corrector(ns - 1);
-	if (rc) return rc;
 	CUDA_TRY(cudaEventRecord(ctx->down_all_ev, D));
 	// dt candidates of the two force evaluations, then t += dt, dt = min(candidates) once both are known
 	ctx->stream = P;

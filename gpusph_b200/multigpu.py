@@ -25,6 +25,8 @@ tests plug in a CPU backend to run the same decomposition/exchange logic at worl
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -643,9 +645,12 @@ class SlabWorker:
             self.launches += 1
 
     # ---- stepping a state that lives in HOST memory (bench.py's e2e leg on N > 1 GPUs) ----
-    def _inner_stripes(self, want: int = 6, min_particles: int = 150000):
+    def _inner_stripes(self, max_pieces: int = 24):
         """The inner stripe [0, edge_start) cut into ranges of whole cell layers (every neighbour of a particle of range k
-        lies in ranges k-1 .. k+1, in the edge stripe or in the halo). Cached per neighbour rebuild (one small readback)."""
+        lies in ranges k-1 .. k+1, in the edge stripe or in the halo). Cached per neighbour rebuild (one small readback).
+        A range holds about B200SPH_SLAB_HOST_PIECE particles (default 350 000, ~11 MB per copy direction): what the
+        pipeline cannot overlap is one range's download + upload + pair kernels, so ranges are kept small, but large
+        enough for a copy to run at the link's rate and for the pair kernel to fill the GPU (at most `max_pieces`)."""
         key = (self.iterations // self.buildneibsfreq, self.numOwn, self.edge_start)
         if getattr(self, "_istripes_key", None) == key:
             return self._istripes_val
@@ -654,7 +659,8 @@ class SlabWorker:
         big = torch.iinfo(torch.int32).max
         first = torch.where(cs2 != -1, cs2, big).min(dim=1).values.cpu().numpy().astype(np.int64)
         starts = sorted(set(int(x) for x in first if x != big and 0 < x < e0))
-        want = max(1, min(want, e0 // max(min_particles, 1)))
+        piece = max(1, int(os.environ.get("B200SPH_SLAB_HOST_PIECE", "350000")))
+        want = max(1, min(max_pieces, e0 // piece))
         bounds = [0]
         for k in range(1, want):
             target = e0 * k // want

@@ -377,8 +377,8 @@ class Worker:
         if not (hpos.is_pinned() and hvel.is_pinned()):
             raise ValueError("step_host needs pinned host buffers")
         rebuild = self.iterations % self.buildneibsfreq == 0 or self.last_neibs_info is None
-        wraps = bool(self.params.periodic & (1 << self.params.coord[2]))     # first and last cell layer are neighbours
-        if not self.device_dt or self.filters or self.particleRangeEnd != n or wraps:
+        # (periodicity along COORD3 makes the first and the last stripe neighbours: the library runs the stripes as a ring)
+        if not self.device_dt or self.filters or self.particleRangeEnd != n:
             # configurations the pipelined entry point does not serve: plain upload / step / download
             self.host_fence()
             self.pos[self.cur][:n].copy_(hpos[:n], non_blocking=True)

@@ -316,6 +316,34 @@ def test_pipelined_host_stepping_equals_resident_stepping_bitwise(name):
     assert a.dt == b.dt and a.t == pytest.approx(b.t, rel=1e-15)
 
 
+@pytest.mark.parametrize("stripes", [2, 3, 4, 7])
+def test_chained_host_stepping_on_a_ring_of_stripes(stripes):
+    """Periodic along COORD3 (the stripes' axis): stripe 0 and the last stripe are neighbours, b200sph_step_host runs the
+    stripes as a ring whose starting point moves by two stripes per call. 23 chained steps, no host synchronisation."""
+    from gpusph_b200.problems import lattice_problem
+    params, parts = lattice_problem(40, ny=10, nz=10, jitter=0.25, periodic=capi.PERIODIC_X,
+                                    densitydiffusion=capi.RHODIFF_COLAGROSSI)
+    assert params.coord[2] == 0, "x is the slowest hash digit in the default linearisation"
+    parts.vel[:, 0] += 4.0                               # flow across the periodic face
+    a = Worker(params, parts, 0)
+    b = Worker(params, parts, 0)
+    a.host_stripes, a.host_stripe_min = stripes, 300
+    A = a.pos[0].shape[0]
+    hp, hv = torch.zeros((A, 4)).pin_memory(), torch.zeros((A, 4)).pin_memory()
+    n = a.numParticles
+    hp[:n].copy_(a.pos[a.cur][:n]); hv[:n].copy_(a.vel[a.cur][:n])
+    for it in range(23):
+        a.step_host(hp, hv)
+    for it in range(23):
+        b.step()
+    a.host_sync()
+    assert len(a._stripes()) == stripes
+    exp_p, exp_v = b.pos[b.cur][:n].cpu(), b.vel[b.cur][:n].cpu()
+    assert torch.equal(hp[:n].view(torch.int32), exp_p.view(torch.int32))
+    assert torch.equal(hv[:n].view(torch.int32), exp_v.view(torch.int32))
+    assert a.dt == b.dt
+
+
 @pytest.mark.parametrize("stripes", [1, 3, 7])
 def test_chained_host_stepping_without_host_synchronisation(stripes):
     """b200sph_step_host calls chain on each other through per-stripe events only: 23 steps (three neighbour rebuilds)

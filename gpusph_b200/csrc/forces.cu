@@ -28,10 +28,12 @@
 // (SURVEY.md section 8b "Threading")
 static std::mutex g_kernel_cache_lock;
 
-// list rows kept in flight by the gather kernel: measured on B200 at 2 M particles (dambreak2m / lattice2m):
-// 1 row 0.585 / 0.769 ms, 2 rows 0.535 / 0.805 ms, 4 rows 0.651 / 0.808 ms
+// list rows kept in flight by the gather kernel. Round 1 (two 128-bit gathers per neighbour, no record look-ahead),
+// dambreak2m / lattice2m: 1 row 0.585 / 0.769 ms, 2 rows 0.535 / 0.805 ms, 4 rows 0.651 / 0.808 ms. Round 2 (one
+// 256-bit gather, record look-ahead, 8 CTAs per SM), dambreak2m: 1 row 0.471 ms, 2 rows 0.480 ms, 3 rows 0.70 ms
+// (spills): one row - a register is worth more than the second row in flight.
 #ifndef GATHER_PF
-#define GATHER_PF 2
+#define GATHER_PF 1
 #endif
 // B200_GATHER_AHEAD=1: the neighbour record of the next list entry is requested before the current one is evaluated
 #ifndef B200_GATHER_AHEAD
@@ -191,7 +193,9 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
 		if ((r2 < k.R2) && (fabsf(np.w) < __int_as_float(0x7f800000)))
-			pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, eos(j, nv), NFLUID, acc, xs);
+			pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w,
+				make_float4(c.vel.x - nv.x, c.vel.y - nv.y, c.vel.z - nv.z, RatioSpace<RHODIFF, LAMINAR, MULTIFLUID>::value ? nv.w + 1.0f : nv.w),
+				eos(j, make_float4(0.f, 0.f, 0.f, RatioSpace<RHODIFF, LAMINAR, MULTIFLUID>::value ? nv.w + 1.0f : nv.w)), NFLUID, acc, xs);
 		if (!more) break;
 		np = np2; nv = nv2; j = j2;
 		rx = pcx - np.x; ry = pcy - np.y; rz = pcz - np.z;
@@ -207,7 +211,7 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 		const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
 		// skip inactive neighbours and pairs beyond the kernel support (forces_kernel.def:3987-3999)
 		if (!(r2 < k.R2) || !(fabsf(np.w) < __int_as_float(0x7f800000))) continue;
-		pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, nv, eos(j, nv), NFLUID, acc, xs);
+		pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, np.w, make_float4(c.vel.x - nv.x, c.vel.y - nv.y, c.vel.z - nv.z, nv.w), eos(j, nv), NFLUID, acc, xs);
 	}
 	}
 }
@@ -222,6 +226,7 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 	Central c;
 	c.pos = pos; c.vel = vel;
 	c.p_precalc = e.x; c.sspeed = e.y; c.rho = e.z;
+	c.ratio = vel.w + 1.0f;
 	c.fnum = MULTIFLUID ? __float_as_int(e.w) : 0;
 	// the Molteni-Colagrossi switch compares raw pressures (forces_kernel.def:1925-1928)
 	c.press = (RHODIFF == B200SPH_RHODIFF_COLAGROSSI || RHODIFF == RHODIFF_RUNTIME) ? eos_pressure(P, vel.w, c.fnum) : 0.0f;
@@ -241,6 +246,9 @@ particle_forces(const DevParams &P, const PairConsts &k, const uint index, const
 		c.momentum = (info.x & B200SPH_FG_COMPUTE_FORCE) != 0;
 		walk_section<true, RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, PF, WIDE, AHEAD>(P, k, c, index, lut, L, fetch, eos, acc, xs);
 	}
+	// ratio-space variants: the density-diffusion sum of the particle, scaled once (pair_physics.cuh)
+	if (RatioSpace<RHODIFF, LAMINAR, MULTIFLUID>::value && RHODIFF != B200SPH_RHODIFF_NONE)
+		acc.w = fmaf(k.diff / c.ratio, xs.x, acc.w);
 	const float cfl_term = finalize_particle(P, type, c.fnum, c.sspeed, info, pos, vel, c.rho, cellHash, bo, acc);
 	forces[index] = acc;
 	if (acc_out) *acc_out = acc;
@@ -281,17 +289,24 @@ __device__ __forceinline__ float4 lds_f4(uint a)
 #ifndef B200_HOIST
 #define B200_HOIST 1
 #endif
+#ifndef B200_PIN_CELLBASE
+#define B200_PIN_CELLBASE 1
+#endif
 #ifndef B200_MIN_BLOCKS
-#define B200_MIN_BLOCKS 7
+#define B200_MIN_BLOCKS 8
 #endif
 // (the detour through shared memory is what stops ptxas from re-deriving the value from the constant bank)
 struct Pinned { float v[24]; };
 
-// 8 CTAs (32 warps) per SM for the lean variants: 64 registers (8 bytes of spill) measured 2.7 % faster than 7 CTAs at
-// 72 registers, 9 CTAs at 56 registers 15 % slower (dambreak2m; the kernel is latency-bound: 1.3 eligible warps per
-// cycle, profiles/r01_forces_gather_final_ncu.txt). The variants with more live state keep 7.
+// CTAs per SM of the lean variants. The loop waits on its gather (one record in flight per warp; long-scoreboard stalls
+// 2.5-4.4 per issued instruction, profiles/r02_forces_gather_final_ncu.txt), so warps per SM count for more than
+// instructions per pair: trimming the loop from 114 to 96 instructions (ratio-space physics, pinned shared-memory
+// address) at 7 CTAs / 72 registers bought 1.5 %; the same loop at 8 CTAs / 64 registers 8 % (dambreak2m, forces launch:
+// 6 CTAs 0.560 ms, 7 0.507, 8 0.471, 9 0.478 with the constants left in the constant bank (0.74 pinned: spills in the
+// loop), 10 0.528). The variants with more live state keep 7 (Colagrossi + artificial viscosity would spill inside the loop).
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID, bool WIDE>
-__global__ void __launch_bounds__(BLOCK_FORCES, (LAMINAR || MULTIFLUID || WIDE || RHODIFF == RHODIFF_RUNTIME) ? 7 : B200_MIN_BLOCKS)
+__global__ void __launch_bounds__(BLOCK_FORCES, (LAMINAR || MULTIFLUID || WIDE || RHODIFF == RHODIFF_RUNTIME ||
+	(RHODIFF == B200SPH_RHODIFF_COLAGROSSI && ARTVISC)) ? 7 : B200_MIN_BLOCKS)
 forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restrict__ pvArray,
 	const ushort4 *__restrict__ infoArray, const uint *__restrict__ particleHash,
 	const uint *__restrict__ cellStart, const ushort *__restrict__ neibsList,
@@ -304,10 +319,13 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x + fromParticle;
 	float cfl_term = 0.0f;
 	if (threadIdx.x < 27) s_celloff[threadIdx.x] = cell_offset(P, threadIdx.x);
-	PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID>(P);
+	constexpr bool FAST = RatioSpace<RHODIFF, LAMINAR, MULTIFLUID>::value;
+	PairConsts k = make_pair_consts<RHODIFF, MULTIFLUID, LAMINAR>(P);
 	EosConsts E;
 	E.gamma = P.gammacoeff[0]; E.sspow = P.sspowercoeff[0]; E.b = P.bcoeff[0]; E.ss = P.sscoeff[0]; E.rho0 = P.rho0[0];
+	if (FAST) { E.b = P.bcoeff[0] / (P.rho0[0] * P.rho0[0]); E.rho0 = P.bcoeff[0]; }     // eos_ratio_from_density
 	uint a_off = smem_u32(s_celloff);
+	uint a_cellbase = smem_u32(s_cellbase);
 	const PosVel *pv = pvArray;       // pinned below: the record base is used by every gather
 	ListGeom L;
 	L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos;
@@ -320,6 +338,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 		v[15] = __uint_as_float(a_off); v[16] = k.h; v[17] = __uint_as_float(L.stride);
 		v[18] = __uint_as_float((uint)(uintptr_t)neibsList); v[19] = __uint_as_float((uint)((uintptr_t)neibsList >> 32));
 		v[20] = __uint_as_float((uint)(uintptr_t)pvArray); v[21] = __uint_as_float((uint)((uintptr_t)pvArray >> 32));
+		v[22] = __uint_as_float(smem_u32(s_cellbase));
 	}
 	__syncthreads();
 	{
@@ -330,6 +349,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 		a_off = __float_as_uint(ld(15)); k.h = ld(16); L.stride = __float_as_uint(ld(17));
 		L.list = (const ushort *)((uintptr_t)__float_as_uint(ld(18)) | ((uintptr_t)__float_as_uint(ld(19)) << 32));
 		pv = (const PosVel *)((uintptr_t)__float_as_uint(ld(20)) | ((uintptr_t)__float_as_uint(ld(21)) << 32));
+		a_cellbase = __float_as_uint(ld(22));
 	}
 #else
 	__syncthreads();
@@ -348,7 +368,11 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 			const uint cellHash = particleHash[index] & CELLTYPE_BITMASK;
 			load_cell_starts(P, (int)cellHash, cellStart, my_base, BLOCK_FORCES);
 			// 32-bit shared-memory addresses computed once (the generic-pointer form is re-derived per use)
+#if B200_PIN_CELLBASE
+			const uint a_base = a_cellbase + 4u * threadIdx.x;
+#else
 			const uint a_base = smem_u32(my_base);
+#endif
 			auto lut = [=](const uint cell, uint &base, float &ox, float &oy, float &oz) {
 				base = lds_u32(a_base + cell * (BLOCK_FORCES * 4u));
 				const float4 o = lds_f4(a_off + cell * 16u);
@@ -357,12 +381,15 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 			// one 256-bit gather per neighbour: its {pos, mass, vel, rho~} record; EOS terms from rho~ on the fly
 			auto fetch = [&](const uint j, float4 &np, float4 &nv) { ld_posvel(pv + j, np, nv); };
 			auto eos = [&](const uint j, const float4 nv) {
+				if (FAST) return eos_ratio_from_density(E, nv.w, B200_GATHER_AHEAD != 0);
 				return MULTIFLUID ? eos_from_density(P, nv.w, fluid_num_of(__ldg(infoArray + j))) : eos_from_density(E, nv.w);
 			};
 			cfl_term = particle_forces<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID, GATHER_PF, WIDE, B200_GATHER_AHEAD != 0>(P, k, index, info, type, pos,
 				vel, eos_from_density(P, vel.w, MULTIFLUID ? fluid_num_of(info) : 0), cellHash, bo, lut, L, fetch, eos, forces,
 				GEN ? bo.xsph : NULL, &acc);
 		}
+		// (the lean variants do not keep rho~ of the particle across the pair loop: one more register for the loop)
+		if (FAST && bo.eul_step && have_acc) vel.w = __ldg(&pv[index].vel.w);
 		integrate_epilogue(P, bo, index, info, pos, vel, acc, have_acc, particleHash, forces);
 	}
 

@@ -39,6 +39,7 @@ __device__ __forceinline__ float visc_avg_dyn(const DevParams &P, float v, float
 }
 
 
+#define RHODIFF_RUNTIME_VALUE (-1)      // = RHODIFF_RUNTIME, defined with its explanation below
 struct PairConsts {
 	float inv_h, fc, R2;       // 1/h, Wendland gradient coefficient, squared influence radius
 	float h_alpha, eps;        // artificial viscosity: h*alpha, eps
@@ -48,16 +49,29 @@ struct PairConsts {
 	float h;
 };
 
-template<int RHODIFF, bool MULTIFLUID>
+// The lean single-fluid variants (one fluid, no laminar viscosity, physics fixed at compile time) work with density
+// RATIOS rho/rho0 = 1 + rho~ instead of densities: rho0 folds into the constants (h_alpha -> h alpha / rho0,
+// grav_scale -> 1/c0^2, the EOS prefactor -> B/rho0^2), and the factor diff / (rho_i/rho0) every density-diffusion
+// term of a particle shares is applied once per particle, to the sum, instead of once per pair. Same algebra as the
+// reference's expressions (cited below), fewer instructions in a loop that is bound by instruction issue.
+#ifndef B200_RATIO_SPACE
+#define B200_RATIO_SPACE 1
+#endif
+template<int RHODIFF, bool LAMINAR, bool MULTIFLUID>
+struct RatioSpace { static constexpr bool value = B200_RATIO_SPACE && RHODIFF != RHODIFF_RUNTIME_VALUE && !LAMINAR && !MULTIFLUID; };
+
+template<int RHODIFF, bool MULTIFLUID, bool LAMINAR = true>
 __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P)
 {
+	constexpr bool FAST = RatioSpace<RHODIFF, LAMINAR, MULTIFLUID>::value;
 	PairConsts k;
 	k.h = P.slength; k.inv_h = 1.0f / P.slength; k.fc = P.fcoeff_wendland;
 	k.R2 = P.influenceradius * P.influenceradius;
 	k.h_alpha = P.slength * P.artvisccoeff; k.eps = P.epsartvisc;
+	if (FAST) k.h_alpha /= P.rho0[0];
 	k.g0 = P.gravity[0]; k.g1 = P.gravity[1]; k.g2 = P.gravity[2];
 	k.diff = RHODIFF == B200SPH_RHODIFF_COLAGROSSI && !MULTIFLUID ? P.densityDiffCoeff * P.sscoeff[0] : P.densityDiffCoeff;
-	k.grav_scale = P.rho0[0] / P.sqC0[0];
+	k.grav_scale = FAST ? 1.0f / P.sqC0[0] : P.rho0[0] / P.sqC0[0];
 	return k;
 }
 
@@ -103,6 +117,21 @@ __device__ __forceinline__ float4 eos_from_density(const EosConsts &E, const flo
 	e.w = E.b * (pw - 1.0f);        // single fluid: the raw pressure P() rides in the slot the fluid number takes otherwise
 	return e;
 }
+// ratio-space flavour (RatioSpace variants): e.z = rho/rho0, and the constants arrive folded: E.b = B/rho0^2,
+// E.rho0 = B (the slot of the density scale, which this flavour does not need)
+// (is_ratio: the caller already added the 1)
+__device__ __forceinline__ float4 eos_ratio_from_density(const EosConsts &E, const float rho_tilde, const bool is_ratio = false)
+{
+	const float ratio = is_ratio ? rho_tilde : rho_tilde + 1.0f;
+	const float lg = lg2_approx(ratio);
+	const float pw1 = ex2_approx(E.gamma * lg) - 1.0f;
+	float4 e;
+	e.x = E.b * pw1 * rcp_approx(ratio * ratio);
+	e.y = E.ss * ex2_approx(E.sspow * lg);
+	e.z = ratio;
+	e.w = E.rho0 * pw1;             // raw pressure (Molteni-Colagrossi switch; dead code elsewhere)
+	return e;
+}
 __device__ __forceinline__ float4 eos_from_density(const DevParams &P, const float rho_tilde, const int f)
 {
 	EosConsts E;
@@ -116,6 +145,7 @@ __device__ __forceinline__ float4 eos_from_density(const DevParams &P, const flo
 struct Central {
 	float4 pos, vel;
 	float rho, p_precalc, sspeed;
+	float ratio;      // rho/rho0 (RatioSpace variants)
 	float press;      // raw pressure P(rho~), Molteni-Colagrossi switch only
 	int fnum;
 	bool momentum;    // accumulate the momentum equation (false for DYN boundary particles without force feedback)
@@ -139,50 +169,63 @@ __device__ __forceinline__ float average_op(const uint op, const float a, const 
 }
 
 // One pair interaction. (rx,ry,rz) = relPos, r2 its squared length (already known to be inside the support),
-// np/nv = neighbour position|mass and velocity|rho~, ne = neighbour {P/rho^2, sound speed, density, fluid#}.
+// nmass = neighbour mass, rv = {relative velocity v_i - v_j, neighbour rho~} (the caller subtracts: the pair loop frees the
+// registers of the neighbour record as early as it can), ne = neighbour {P/rho^2, sound speed, density, fluid#}.
 // nfluid: the neighbour is a fluid particle (density diffusion applies), else a DYN boundary particle
 // (forces_kernel.def:1594-1606, 3717-3726). xs accumulates the XSPH mean velocity (general variant only).
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
 __device__ __forceinline__ void
 pair_interaction_x(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
-	const float r2, const float nmass, const float4 nv, const float4 ne, const bool nfluid, float4 &acc, float3 &xs)
+	const float r2, const float nmass, const float4 rv, const float4 ne, const bool nfluid, float4 &acc, float3 &xs)
 {
 	constexpr bool GEN = RHODIFF == RHODIFF_RUNTIME;
+	// FAST: ne.z and `rho` are density ratios, xs.x collects the density-diffusion sum still to be scaled by diff/ratio_i
+	constexpr bool FAST = RatioSpace<RHODIFF, LAMINAR, MULTIFLUID>::value;
 	const int rhodiff = GEN ? (int)P.densitydiffusiontype : RHODIFF;
 	const bool artvisc = GEN ? P.turbmodel == B200SPH_TURB_ARTIFICIAL : ARTVISC;
 	const bool laminar = GEN ? !P.inviscid : LAMINAR;
 	const int nfnum = MULTIFLUID ? __float_as_int(ne.w) : 0;
 	const float r = r2 * rsqrt_approx(r2 + 1e-30f);
 	// common_neib_data :1099-1130
-	const float rvx = c.vel.x - nv.x, rvy = c.vel.y - nv.y, rvz = c.vel.z - nv.z;
+	const float rvx = rv.x, rvy = rv.y, rvz = rv.z;
 	const float vel_dot_pos = fmaf(rvz, rz, fmaf(rvy, ry, rvx * rx));
 	const float qm2 = fmaf(r, k.inv_h, -2.0f);                       // F<WENDLAND>, sph_core.cu:168-174
 	const float f = qm2 * qm2 * qm2 * k.fc;
 	const float mf = nmass * f;
 	const float np_precalc = ne.x, nsspeed = ne.y, nrho = ne.z;
-	const float rho = c.rho;
+	const float rho = FAST ? c.ratio : c.rho;
 
 	// --- continuity: mass_continuity_div_vel_term :2140-2150 ---
 	float DrDt = mf * vel_dot_pos;
 	if (nfluid) {
 		if (rhodiff == B200SPH_RHODIFF_FERRARI) {                   // :1614-1636
 			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
+			if (FAST) {
+				// (rho - rho_j + corr) / rho = ((a - b) - g.r / c0^2) / a with a, b the density ratios; diff / a: caller
+				const float s = fmaxf(c.sspeed, nsspeed) * fmaf(-gdot, k.grav_scale, rho - nrho) * r;
+				xs.x = fmaf(mf, (r > 1e-4f * k.h) ? s : 0.0f, xs.x);
+			} else {
 			const float grav_corr = -gdot * (MULTIFLUID ? P.rho0[c.fnum] / P.sqC0[c.fnum] : k.grav_scale);
 			// ferraricor . relPos = max(c) (rho - rho_j + corr)/rho / r * r^2   (zero for r <= 1e-4 h)
 			const float s = (r > 1e-4f * k.h) ? fmaxf(c.sspeed, nsspeed) * (rho - nrho + grav_corr) * rcp_approx(rho) * r : 0.0f;
 			DrDt = fmaf(k.diff * mf, s, DrDt);
+			}
 		} else if (rhodiff == B200SPH_RHODIFF_COLAGROSSI) {         // :1916-1951
 			if (!MULTIFLUID || c.fnum == nfnum) {
 				// P() of both particles as the reference compares them (:1925-1928), not rebuilt from P/rho^2: the test is
 				// a discontinuous switch, a borderline pair must fall on the reference's side
-				const float Pi = c.press, Pj = MULTIFLUID ? eos_pressure(P, nv.w, nfnum) : ne.w;
+				const float Pi = c.press, Pj = MULTIFLUID ? eos_pressure(P, rv.w, nfnum) : ne.w;
 				const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
+				if (FAST) {
+					// (rho_j / rho - 1) = (b - a) / a; diff / a: caller
+					if (!(fabsf(Pi - Pj) < fabsf(gdot * c.rho))) xs.x = fmaf(rho - nrho, mf, xs.x);
+				} else
 				if (!(fabsf(Pi - Pj) < fabsf(gdot * rho)))
 					DrDt -= k.diff * (MULTIFLUID ? P.sscoeff[c.fnum] : 1.0f) * (nrho * rcp_approx(rho) - 1.0f) * mf;
 			}
 		} else if (GEN && rhodiff == B200SPH_RHODIFF_BREZZI) {      // :1765-1782
 			const float dt = P.dev_state ? (P.cmd_step == 1 ? P.dev_state->dt / 2 : P.dev_state->dt) : P.cmd_dt;
-			const float Pi = eos_pressure(P, c.vel.w, c.fnum), Pj = eos_pressure(P, nv.w, nfnum);
+			const float Pi = eos_pressure(P, c.vel.w, c.fnum), Pj = eos_pressure(P, rv.w, nfnum);
 			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
 			DrDt += k.diff * ((2.0f / (rho + nrho)) * (Pi - Pj) - gdot) * nmass / nrho * f * dt * 2.0f * rho;
 		}
@@ -242,10 +285,10 @@ pair_interaction_x(const DevParams &P, const PairConsts &k, const Central &c, co
 template<int RHODIFF, bool ARTVISC, bool LAMINAR, bool MULTIFLUID>
 __device__ __forceinline__ void
 pair_interaction(const DevParams &P, const PairConsts &k, const Central &c, const float rx, const float ry, const float rz,
-	const float r2, const float nmass, const float4 nv, const float4 ne, const bool nfluid, float4 &acc)
+	const float r2, const float nmass, const float4 rv, const float4 ne, const bool nfluid, float4 &acc)
 {
 	float3 xs = make_float3(0.f, 0.f, 0.f);
-	pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, nmass, nv, ne, nfluid, acc, xs);
+	pair_interaction_x<RHODIFF, ARTVISC, LAMINAR, MULTIFLUID>(P, k, c, rx, ry, rz, r2, nmass, rv, ne, nfluid, acc, xs);
 }
 
 // Lennard-Jones repulsion and wall friction of the geometric planes on a fluid particle: GeometryForce / PlaneForce /

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SPH_LIB: alternative build of the same library (kernel tuning experiments, tools/build_variants.sh)
 LIB_PATH = os.environ.get("B200SPH_LIB") or os.path.join(_HERE, "libb200sph.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+NEIBLIST_BLOCK = 2097152          # B200SPH_NEIBLIST_BLOCK: particles per block of the neighbour-list layout (include/b200sph.h)
 MAX_FLUIDS = 4
 MAX_PLANES = 8
 
@@ -79,6 +80,8 @@ class Params(C.Structure):
         ("epsxsph", C.c_float), ("monaghan_visc_coeff", C.c_float),
         ("visc2coeff", C.c_float * MAX_FLUIDS),
         ("r0", C.c_float), ("dcoeff", C.c_float), ("p1coeff", C.c_float), ("p2coeff", C.c_float), ("partsurf", C.c_float),
+        # ABI version 4
+        ("neiblist_block", C.c_uint32),
     ]
 
     def copy(self) -> "Params":

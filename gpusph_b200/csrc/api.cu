@@ -42,6 +42,9 @@ extern "C" int b200sph_validate(const b200sph_params *p)
 	const uint64_t ncells = (uint64_t)p->grid_size[0] * p->grid_size[1] * p->grid_size[2];
 	if (ncells > (0xFFFFFFFFu >> 2)) { b200_set_error("too many cells (MAX_CELLS, src/multi_gpu_defines.h:56)"); return B200SPH_EINVAL; }
 	if (p->neiblistsize < 4 || p->neibboundpos >= p->neiblistsize) { b200_set_error("bad neiblistsize/neibboundpos"); return B200SPH_EINVAL; }
+	if (p->neiblist_block && (p->neiblist_block < 32 || (p->neiblist_block & (p->neiblist_block - 1)))) {
+		b200_set_error("neiblist_block %u: a power of two >= 32 (or 0 for the default) expected", p->neiblist_block); return B200SPH_EINVAL;
+	}
 	if (p->num_fluids < 1 || p->num_fluids > B200SPH_MAX_FLUIDS) { b200_set_error("num_fluids out of range"); return B200SPH_EINVAL; }
 	if (p->kerneltype != B200SPH_KERNEL_WENDLAND) { b200_set_error("unsupported SPH kernel %u: only WENDLAND is implemented", p->kerneltype); return B200SPH_EUNSUP; }
 	if (p->sph_formulation != B200SPH_SPH_F1) { b200_set_error("unsupported SPH formulation %u: only SPH_F1 is implemented", p->sph_formulation); return B200SPH_EUNSUP; }
@@ -82,6 +85,7 @@ static void fill_devparams(const b200sph_params *p, DevParams *d)
 	d->hstride[p->coord[1]] = (int)p->grid_size[p->coord[0]];
 	d->hstride[p->coord[2]] = (int)(p->grid_size[p->coord[0]] * p->grid_size[p->coord[1]]);
 	d->neiblistsize = p->neiblistsize; d->neibboundpos = p->neibboundpos; d->stride = p->neiblist_stride;
+	d->listblock = p->neiblist_block ? p->neiblist_block : (uint32_t)B200SPH_NEIBLIST_BLOCK;
 	d->nlSqInflRad = p->nl_sq_influence_radius;
 	d->kerneltype = p->kerneltype; d->densitydiffusiontype = p->densitydiffusiontype; d->boundarytype = p->boundarytype;
 	d->inviscid = (p->rheologytype == B200SPH_RHEOLOGY_INVISCID);

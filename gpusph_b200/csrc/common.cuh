@@ -19,6 +19,14 @@ typedef unsigned short ushort;
 #define CELLNUM_SHIFT 11
 #define CELLNUM_ENCODED (1U << CELLNUM_SHIFT)
 #define NEIBINDEX_MASK (CELLNUM_ENCODED - 1)
+// blocked neighbour-list layout (include/b200sph.h, B200SPH_NEIBLIST_BLOCK): element offset of row 0 of particle `index`
+// and the distance between its rows. `block` = particles per block, a power of two.
+__device__ __forceinline__ size_t list_column(const uint index, const uint stride, const uint rows, const uint block, uint &row_step)
+{
+	const uint b0 = index & ~(block - 1u);
+	row_step = min(block, stride - b0);
+	return (size_t)b0 * rows + (index - b0);
+}
 
 #define PT_FLUID 0
 #define PT_BOUNDARY 1
@@ -42,6 +50,7 @@ struct DevParams {
 	int hstride[3];         // linear-hash stride of one cell step along x, y, z (derived from coord + gridSize)
 	uint periodic;
 	uint neiblistsize, neibboundpos, stride;
+	uint listblock;         // particles per block of the neighbour-list layout
 	float nlSqInflRad;
 	uint kerneltype, densitydiffusiontype, boundarytype;
 	uint inviscid, turbmodel, compvisc, viscavgop, is_const_visc;

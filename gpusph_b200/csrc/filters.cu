@@ -21,14 +21,15 @@ for_each_neib(const DevParams &P, const uint index, const float4 pos, const uint
 	const ushort *__restrict__ neibsList, const float4 *__restrict__ posArray, const bool with_boundary, Body body)
 {
 	const int3 gp = grid_pos(P, cellHash);
-	const size_t stride = P.stride;
+	uint row_step;
+	const ushort *const column = neibsList + list_column(index, P.stride, P.neiblistsize, P.listblock, row_step);
 	for (int section = 0; section < (with_boundary ? 2 : 1); ++section) {
 		long long row = section == 0 ? 0 : (long long)P.neibboundpos;
 		const long long step = section == 0 ? 1 : -1;
 		uint base = 0;
 		float pcx = 0.f, pcy = 0.f, pcz = 0.f;
 		for (; row >= 0 && row < (long long)P.neiblistsize; row += step) {
-			uint nd = ldl(neibsList + (size_t)row * stride + index);
+			uint nd = ldl(column + (size_t)row * row_step);
 			if (nd == NEIBS_END) break;
 			if (nd >= CELLNUM_ENCODED) {
 				const int cell = (int)(nd >> CELLNUM_SHIFT) - 1;

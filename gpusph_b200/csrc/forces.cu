@@ -131,7 +131,7 @@ __device__ __forceinline__ float4 cell_offset(const DevParams &P, const int c)
 // lut(cell, base, ox, oy, oz) returns the first particle of neighbour cell `cell` and its offset times the cell size. PF list rows are read ahead of use; the read-ahead offset is clamped to the list.
 // WIDE: 64-bit list offsets (lists of 2^31 entries or more), else 32-bit (one VIADDMNMX per row).
 // Accumulation order = list order, as in the reference (neibs_iteration.cuh:56-200).
-struct ListGeom { const ushort *list; uint stride, rows, boundpos; };      // neighbour list + its shape (DevParams copies)
+struct ListGeom { const ushort *list; uint stride, rows, boundpos, block; };      // neighbour list + its shape (DevParams copies)
 template<bool WIDE> struct ListOff { typedef uint type; typedef int stype; };
 template<> struct ListOff<true> { typedef unsigned long long type; typedef long long stype; };
 
@@ -143,10 +143,15 @@ walk_section(const DevParams &P, const PairConsts &k, const Central &c, const ui
 	typedef typename ListOff<WIDE>::type off_t;
 	typedef typename ListOff<WIDE>::stype soff_t;
 	const ushort *__restrict__ neibsList = L.list;
-	const off_t stride = (off_t)L.stride;
+	// the particle's column in the blocked list layout (include/b200sph.h): first row, distance between rows
+	uint row_step;
+	const off_t lo = (off_t)list_column(index, L.stride, L.rows, L.block, row_step);
+	const off_t stride = (off_t)row_step;
 	// element offset of the next row to read ahead: the fluid section grows up from row 0, the boundary section
-	// down from neibboundpos; the last (first) row of the list is re-read instead of running off the buffer
-	const off_t lo = index, hi = lo + (off_t)(L.rows - 1) * stride;
+	// down from neibboundpos; the last (first) row of the column is re-read instead of running off it (the read-ahead
+	// must not depend on the entry just read: predicating it on "not the end marker" chains the list loads and
+	// was measured 4 % slower)
+	const off_t hi = lo + (off_t)(L.rows - 1) * stride;
 	off_t off = NFLUID ? lo : lo + (off_t)L.boundpos * stride;
 	auto advance = [&](off_t o) -> off_t {
 		return NFLUID ? min(o + stride, hi) : (off_t)max((soff_t)(o - stride), (soff_t)lo);
@@ -328,7 +333,7 @@ forces_gather_kernel(const __grid_constant__ DevParams P, const PosVel *__restri
 	uint a_cellbase = smem_u32(s_cellbase);
 	const PosVel *pv = pvArray;       // pinned below: the record base is used by every gather
 	ListGeom L;
-	L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos;
+	L.list = neibsList; L.stride = P.stride; L.rows = P.neiblistsize; L.boundpos = P.neibboundpos; L.block = P.listblock;
 #if B200_HOIST
 	__shared__ Pinned s_pin;
 	if (threadIdx.x == 0) {

@@ -369,7 +369,8 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 {
 	const uint index = blockIdx.x * blockDim.x + threadIdx.x;
 	uint nf = 0, nb = 0, nv = 0;
-	const size_t stride = P.stride;
+	uint row_step;
+	ushort *const column = neibsList + list_column(index, P.stride, P.neiblistsize, P.listblock, row_step);   // rows of THIS particle
 	// the search radius is used once per candidate: passing it through a shuffle pins it in a register (ptxas would
 	// otherwise re-load it from the constant bank inside the candidate loop)
 	const float R2_pinned = __shfl_sync(0xffffffffu, P.nlSqInflRad, 0);
@@ -423,7 +424,7 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 					if (nt == PT_FLUID) ++nf; else if (nt == PT_BOUNDARY) ++nb; else ++nv;
 					if (!too_many_neibs(P, nf, nb, nv, nt)) {                             // :626-634
 						const uint enc = encode_cell ? ((cell + 1) << CELLNUM_SHIFT) : 0u;
-						st_list(neibsList + offset * stride + index, (ushort)((j - bucketStart) + enc));
+						st_list(column + offset * row_step, (ushort)((j - bucketStart) + enc));
 						encode_cell = false;
 					}
 				};
@@ -485,9 +486,9 @@ build_neibs_kernel(const __grid_constant__ DevParams P, const float4 *__restrict
 		// end markers / overflow, :1108-1137
 		bool overflow = too_many_neibs(P, nf, nb, nv, PT_FLUID);
 		const uint marker = overflow ? P.neibboundpos : nf;
-		neibsList[marker * stride + index] = NEIBS_END;
+		column[marker * row_step] = NEIBS_END;
 		overflow |= too_many_neibs(P, nf, nb, nv, PT_BOUNDARY);
-		if (!overflow) neibsList[neib_list_offset(P, nb, PT_BOUNDARY) * stride + index] = NEIBS_END;
+		if (!overflow) column[neib_list_offset(P, nb, PT_BOUNDARY) * row_step] = NEIBS_END;
 		if (overflow) {
 			const int myid = (int)id_of(info);
 			atomicCAS(&counters->hasTooManyNeibs, -1, myid);

@@ -72,6 +72,8 @@ __device__ __forceinline__ PairConsts make_pair_consts(const DevParams &P)
 	k.g0 = P.gravity[0]; k.g1 = P.gravity[1]; k.g2 = P.gravity[2];
 	k.diff = RHODIFF == B200SPH_RHODIFF_COLAGROSSI && !MULTIFLUID ? P.densityDiffCoeff * P.sscoeff[0] : P.densityDiffCoeff;
 	k.grav_scale = FAST ? 1.0f / P.sqC0[0] : P.rho0[0] / P.sqC0[0];
+	// Ferrari, ratio space: gravity only enters as g.r / c0^2
+	if (FAST && RHODIFF == B200SPH_RHODIFF_FERRARI) { k.g0 *= k.grav_scale; k.g1 *= k.grav_scale; k.g2 *= k.grav_scale; }
 	return k;
 }
 
@@ -202,7 +204,8 @@ pair_interaction_x(const DevParams &P, const PairConsts &k, const Central &c, co
 			const float gdot = fmaf(k.g2, rz, fmaf(k.g1, ry, k.g0 * rx));
 			if (FAST) {
 				// (rho - rho_j + corr) / rho = ((a - b) - g.r / c0^2) / a with a, b the density ratios; diff / a: caller
-				const float s = fmaxf(c.sspeed, nsspeed) * fmaf(-gdot, k.grav_scale, rho - nrho) * r;
+				// (k.g* arrive divided by c0^2 in this variant)
+				const float s = fmaxf(c.sspeed, nsspeed) * ((rho - nrho) - gdot) * r;
 				xs.x = fmaf(mf, (r > 1e-4f * k.h) ? s : 0.0f, xs.x);
 			} else {
 			const float grav_corr = -gdot * (MULTIFLUID ? P.rho0[c.fnum] / P.sqC0[c.fnum] : k.grav_scale);

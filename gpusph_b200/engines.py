@@ -429,3 +429,29 @@ class SimFramework:
     @property
     def params(self) -> capi.Params:
         return self.ctx.params
+
+
+def neibs_list_rows(nl: torch.Tensor, block: int = 0) -> torch.Tensor:
+    """The neighbour list buffer ([neiblistsize, allocated] int16, filled by NeibsEngine.buildNeibsList in the blocked
+    layout of include/b200sph.h) re-arranged into the reference's interleaved layout: out[k, i] = entry k of particle i
+    (src/cuda/neibs_iteration.cuh:60-75). For inspection and tests; the engines only ever use the blocked layout.
+    block = Params.neiblist_block of the context that made the list (0: the default)."""
+    rows, A = nl.shape
+    B = block or capi.NEIBLIST_BLOCK
+    nb, rem = A // B, A % B
+    flat = nl.reshape(-1)
+    full = flat[:nb * B * rows].view(nb, rows, B).permute(1, 0, 2).reshape(rows, nb * B)
+    if rem:
+        return torch.cat([full, flat[nb * B * rows:].view(rows, rem)], dim=1)
+    return full
+
+
+def neibs_list_blocked(rows_layout: torch.Tensor, block: int = 0) -> torch.Tensor:
+    """Inverse of neibs_list_rows: a list in the reference's layout ([neiblistsize, allocated]) as the engines expect it."""
+    rows, A = rows_layout.shape
+    B = block or capi.NEIBLIST_BLOCK
+    nb, rem = A // B, A % B
+    full = rows_layout[:, :nb * B].reshape(rows, nb, B).permute(1, 0, 2).reshape(-1)
+    if rem:
+        full = torch.cat([full, rows_layout[:, nb * B:].reshape(-1)])
+    return full.view(rows, A)

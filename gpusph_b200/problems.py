@@ -10,6 +10,8 @@ from __future__ import annotations
 import dataclasses
 import math
 
+import os
+
 import numpy as np
 
 from . import capi
@@ -71,6 +73,8 @@ def make_params(*, origin, size, deltap, allocated_particles: int,
     p.periodic = periodic
     p.neiblistsize = neiblistsize
     p.neibboundpos = neiblistsize - 1                            # non-SA: ProblemCore.h:346-353
+    # (diagnostics: B200SPH_TEST_ALLOC_SCALE spreads the rows of the neighbour list further apart at a fixed particle count)
+    allocated_particles = int(allocated_particles * float(os.environ.get("B200SPH_TEST_ALLOC_SCALE", "1")))
     p.neiblist_stride = allocated_particles
     p.nl_sq_influence_radius = np.float32(nl_influence * nl_influence)
     p.kerneltype = capi.KERNEL_WENDLAND

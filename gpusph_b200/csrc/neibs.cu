@@ -102,7 +102,8 @@ extern "C" int b200sph_fix_hash(b200sph_ctx *ctx, uint32_t *hash, uint32_t *part
 // sort — reference thrust::sort_by_key with ptype_hash_compare, src/cuda/buildneibs.cu:358-415.
 // The comparator is a TOTAL order: (hash incl. high bits, particle type, id). We pack it into one
 // 64-bit radix key  [ hash : 32 | ptype : 2 | id : 30 ]  and run CUB's onesweep radix sort on
-// (key, partIndex) pairs, only over the key bits that can be non-zero. If some id needs more than
+// (key, partIndex) pairs over all 64 key bits (trimming the range to the live bits would save one of
+// eight passes, ~0.07 ms per rebuild at 8 M particles: not done). If some id needs more than
 // 30 bits the packed key cannot hold it; then two stable passes (by id, then by hash|ptype) give
 // the same order. The result is the unique sorted permutation, hence bit-identical to the
 // reference's merge sort.

@@ -164,6 +164,37 @@ def test_reorder_and_cell_ranges_bit_exact(pipe):
     assert np.array_equal(host(pipe.g["svel"]).view(np.uint32), pipe.o["svel"].view(np.uint32))
 
 
+def test_reorder_gathers_extra_buffers():
+    """b200sph_reorder's `extras`: every further per-particle buffer the caller wants re-ordered with POS / VEL (the
+    reference's reorderDataAndFindCellStart sorts all the buffers it is handed, src/cuda/buildneibs.cu:220-330; the C++
+    adapter passes the optional ones this way) - 4-, 8- and 16-byte elements, against the sorted particle index."""
+    p = Pipeline("dambreak")
+    g, n, fw = p.g, p.n, p.fw
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    tke = torch.randn(n, generator=gen).to(DEV)                       # float
+    vertpos = torch.randn((n, 2), generator=gen).to(DEV)              # float2
+    eulervel = torch.randn((n, 4), generator=gen).to(DEV)             # float4
+    uns = BufferList({BUFFER_POS: g["pos_unsorted"], BUFFER_VEL: g["vel"], BUFFER_INFO: g["info"], BUFFER_HASH: g["hash"],
+                      BUFFER_PARTINDEX: g["pidx"], "BUFFER_TKE": tke, "BUFFER_VERTPOS": vertpos, "BUFFER_EULERVEL": eulervel})
+    srt = BufferList(uns)
+    out = {k: torch.zeros_like(v) for k, v in (("BUFFER_TKE", tke), ("BUFFER_VERTPOS", vertpos), ("BUFFER_EULERVEL", eulervel))}
+    srt.update({BUFFER_POS: torch.zeros_like(g["pos"]), BUFFER_VEL: torch.zeros_like(g["vel"]),
+                BUFFER_CELLSTART: torch.full_like(g["cs"], -1), BUFFER_CELLEND: torch.full_like(g["ce"], -1), **out})
+    newn = torch.zeros(1, dtype=torch.int32, device=DEV)
+    fw.neibsEngine.reorderDataAndFindCellStart(None, srt, uns, n, newn, extra_keys=tuple(out))
+    torch.cuda.synchronize()
+    idx = g["pidx"].long()
+    assert torch.equal(srt[BUFFER_POS], g["spos"]) and torch.equal(srt[BUFFER_CELLSTART], g["cs"])
+    assert torch.equal(out["BUFFER_TKE"], tke[idx])
+    assert torch.equal(out["BUFFER_VERTPOS"], vertpos[idx])
+    assert torch.equal(out["BUFFER_EULERVEL"], eulervel[idx])
+    # an element size the gather has no kernel for is refused, not skipped
+    bad = torch.zeros((n, 3), device=DEV)
+    uns["BUFFER_BAD"], srt["BUFFER_BAD"] = bad, torch.zeros_like(bad)
+    with pytest.raises(ValueError):
+        fw.neibsEngine.reorderDataAndFindCellStart(None, srt, uns, n, newn, extra_keys=("BUFFER_BAD",))
+
+
 def test_neighbour_list_bit_exact(pipe):
     got = host(neibs_list_rows(pipe.g["nl"]), np.uint16)       # blocked layout -> the reference's (and the oracle's)
     assert np.array_equal(got, pipe.o["nl"])

@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", action="store_true", help="replay the time step as a CUDA graph between neighbour rebuilds")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: plain upload / step / download instead of Worker.step_host")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the checksum comparison with a single-GPU run of the warm-up steps")
     ap.add_argument("--quick", action="store_true", help="kernel tuning sweeps: skip the e2e leg and the CPU baseline")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: split the same problem over N slabs (default, BASELINE configs[3]) or widen the tank N times")
@@ -299,6 +300,42 @@ def main():
 
     for _ in range(args.warmup):
         w.step()
+    # N > 1: is the state after the warm-up steps, particle for particle and bit for bit, the state ONE GPU computes in the
+    # same steps? (tests/test_multigpu_gpu.py asserts this on small problems where several GPUs are available to the
+    # test run; this is the same evidence on the benchmark's own problem.) Order-independent checksums of the owned
+    # particles are summed over the ranks and compared with rank 0 stepping the whole problem by itself. Nothing of it is
+    # inside a timed region; a failure of the check itself is reported, never fatal.
+    parity_check = None
+    if world > 1 and not args.no_parity_check:
+        from gpusph_b200.multigpu import state_checksum
+        mine = torch.zeros(2, dtype=torch.int64, device="cuda")
+        try:
+            torch.cuda.synchronize()
+            no = w.numOwn
+            cs, cn = state_checksum(w.info[:no], w.hash[:no], w.pos[w.cur][:no], w.vel[w.cur][:no])
+            mine[0], mine[1] = cs, cn
+        except Exception as e:                                  # noqa: BLE001
+            mine[1] = -1
+            print(f"[bench] rank {rank}: parity checksum failed: {e!r}", file=sys.stderr)
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)              # every rank, whatever happened above
+        if rank == 0:
+            w1 = None
+            try:
+                w1 = Worker(params, parts, local)
+                for _ in range(args.warmup):
+                    w1.step()
+                torch.cuda.synchronize()
+                n1 = w1.numParticles
+                rs, rn = state_checksum(w1.info[:n1], w1.hash[:n1], w1.pos[w1.cur][:n1], w1.vel[w1.cur][:n1])
+                parity_check = {"against": f"one GPU stepping the whole problem for the same {args.warmup} warm-up steps (rank 0)",
+                                "what": "order-independent checksum over (id, cell, pos bits, vel bits) of every particle, summed over the ranks",
+                                "bitwise_equal": bool(rs == int(mine[0].item()) and rn == int(mine[1].item())),
+                                "particles": rn, "particles_on_ranks": int(mine[1].item())}
+            except Exception as e:                              # noqa: BLE001
+                parity_check = {"error": repr(e)[:300]}
+            finally:
+                del w1
+                torch.cuda.empty_cache()
     # working set: pos/vel x2 states + forces + list > L2 for every benchmark workload; say which
     working_set = n_global * (4 * 16 + 16 + 12) + w.last_neibs_info.num_interactions * 2
     barrier()
@@ -474,7 +511,8 @@ def main():
             "higher_is_better": True, "scaling": "weak" if world == 1 else args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "particles": n_global,
-                       "neibs_per_particle": w.last_neibs_info.num_interactions / max(w.numOwn if world > 1 else w.numParticles, 1),
+                       # list entries per particle over the WHOLE problem (all ranks): interactions = 2 x entries x steps
+                       "neibs_per_particle": interactions / (2.0 * args.steps * max(n_global, 1)),
                        "host_affinity": host_affinity or "unbound",
                        "buildneibsfreq": 10, "density_diffusion": "ferrari" if "dambreak" in args.workload else "none",
                        "viscosity": "laminar (Morris)" if "poiseuille" in args.workload else "artificial",
@@ -486,6 +524,8 @@ def main():
             "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if parity_check is not None:
+            line["parity_check"] = parity_check
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

@@ -91,6 +91,27 @@ def compact_device_map(params: capi.Params, slab: tuple[int, int], rank: int, wo
     return np.repeat(t << 30, S).astype(np.uint32)
 
 
+def state_checksum(info: torch.Tensor, hashv: torch.Tensor, pos: torch.Tensor, vel: torch.Tensor) -> tuple[int, int]:
+    """Order-independent 57-bit checksum of a set of particles: sum over particles of a 32-bit mix of (id, cell, the bit
+    patterns of pos and vel). The checksums of disjoint sets add up to the checksum of their union, so N ranks can
+    all-reduce(SUM) theirs and compare with a single-domain run particle for particle without gathering the state
+    (bench.py does that after the warm-up steps of a multi-GPU run). Returns (checksum, particle count). Integer
+    arithmetic stays below 2^63: every product is (< 2^32) x (< 2^27)."""
+    n = int(pos.shape[0])
+    if n == 0:
+        return 0, 0
+    i16 = info.to(torch.int64) & 0xFFFF
+    ids = i16[:, 2] | (i16[:, 3] << 16)
+    cell = hashv.to(torch.int64) & CELLMASK
+    p = pos.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    v = vel.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    h = (ids * 0x45D9F3B + 0x27D4EB2F) & 0xFFFFFFFF
+    for word in (cell, p[:, 0], p[:, 1], p[:, 2], p[:, 3], v[:, 0], v[:, 1], v[:, 2], v[:, 3]):
+        h = (((h ^ word) * 0x45D9F3B) & 0xFFFFFFFF)
+        h = h ^ (h >> 15)
+    return int(h.sum().item()), n
+
+
 class CudaBackend:
     """Numerical work through the C ABI (gpusph_b200.engines)."""
 

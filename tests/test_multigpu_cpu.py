@@ -142,3 +142,32 @@ def test_two_rank_gloo_run_matches_single_domain_bitwise(device_dt):
     assert np.array_equal(hashv[o], exp.hash[oe])
     assert np.array_equal(pos[o].view(np.uint32), exp.pos[oe].view(np.uint32))
     assert np.array_equal(vel[o].view(np.uint32), exp.vel[oe].view(np.uint32))
+
+
+def test_state_checksum_is_additive_order_independent_and_sensitive():
+    """multigpu.state_checksum (what bench.py all-reduces after the warm-up of a multi-GPU run to compare with a
+    single-GPU run of the same steps)."""
+    import torch
+    from gpusph_b200.multigpu import state_checksum
+    params, parts = make_problem()
+    n = parts.n
+    info = torch.from_numpy(parts.info.view(np.int16).copy())
+    hashv = torch.from_numpy(parts.hash.view(np.int32).copy())
+    pos, vel = torch.from_numpy(parts.pos.copy()), torch.from_numpy(parts.vel.copy())
+    whole, cnt = state_checksum(info, hashv, pos, vel)
+    assert cnt == n and 0 < whole < (1 << 57)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1))
+    assert state_checksum(info[perm], hashv[perm], pos[perm], vel[perm])[0] == whole
+    cut = n // 3
+    a = state_checksum(info[:cut], hashv[:cut], pos[:cut], vel[:cut])
+    b = state_checksum(info[cut:], hashv[cut:], pos[cut:], vel[cut:])
+    assert a[0] + b[0] == whole and a[1] + b[1] == n
+    # the multi-GPU cell-type bits in the hash do not count, everything else does, down to one bit of one float
+    tagged = hashv | torch.tensor(-(1 << 31), dtype=torch.int32)
+    assert state_checksum(info, tagged, pos, vel)[0] == whole
+    v2 = vel.clone()
+    v2.view(torch.int32)[n // 2, 1] ^= 1
+    assert state_checksum(info, hashv, pos, v2)[0] != whole
+    h2 = hashv.clone(); h2[5] += 1
+    assert state_checksum(info, h2, pos, vel)[0] != whole
+    assert state_checksum(info[:0], hashv[:0], pos[:0], vel[:0]) == (0, 0)

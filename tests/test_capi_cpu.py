@@ -128,6 +128,9 @@ def test_neighbour_list_layout_helpers_follow_the_documented_formula():
                 b0 = i // blk * blk
                 w = min(blk, A - b0)
                 assert flat[b0 * rows + k * w + (i - b0)] == x[k, i]
+    # the Python constant is the header's
+    hdr = open(os.path.join(ROOT, "include", "b200sph.h")).read()
+    assert int(re.search(r"#define\s+B200SPH_NEIBLIST_BLOCK\s+(\d+)", hdr).group(1)) == capi.NEIBLIST_BLOCK
     # up to one block of particles the layout IS the reference's interleaved one
     x = torch.arange(rows * 500, dtype=torch.int32).view(rows, 500)
     assert torch.equal(neibs_list_blocked(x), x)

@@ -21,6 +21,12 @@ from gpusph_b200.problems import dambreak_problem, lattice_problem  # noqa: E402
 
 
 def make_problem(periodic=False):
+    if periodic == "xzy":
+        # the linearisation bench.py uses on N > 1 GPUs (and the reference's `linearization=xzy` build): y is the slowest
+        # hash digit, hence the slab axis
+        params, parts = lattice_problem(8, ny=14, nz=8, jitter=0.2, densitydiffusion=capi.RHODIFF_COLAGROSSI, coord=(0, 2, 1))
+        parts.vel[:, 1] += 6.0
+        return params, parts
     if periodic:
         # periodic along x, the slab axis of the default yzx linearisation: the first and the last slab are neighbours.
         # The domain must be a whole number of lattice spacings long for the lattice to close on itself.
@@ -95,6 +101,34 @@ def test_periodic_slab_axis_matches_single_domain_bitwise(world):
     with tempfile.TemporaryDirectory() as d:
         port = 31500 + (os.getpid() % 2000) + world
         mp.spawn(_rank_main, args=(world, port, steps, d, True, True), nprocs=world, join=True)
+        r = [np.load(os.path.join(d, f"rank{k}.npz")) for k in range(world)]
+    ids = np.concatenate([ids_of(r[k]["info"]) for k in range(world)])
+    assert np.array_equal(np.sort(ids), np.arange(parts.n))
+    assert any(int(r[k]["own0"]) != r[k]["pos"].shape[0] for k in range(world)), "particles should change owner"
+    pos = np.concatenate([r[k]["pos"] for k in range(world)])
+    vel = np.concatenate([r[k]["vel"] for k in range(world)])
+    hashv = np.concatenate([r[k]["hash"] for k in range(world)]) & 0x3FFFFFFF
+    o, oe = np.argsort(ids), np.argsort(ids_of(exp.info))
+    assert np.array_equal(hashv[o], exp.hash[oe])
+    assert np.array_equal(pos[o].view(np.uint32), exp.pos[oe].view(np.uint32))
+    assert np.array_equal(vel[o].view(np.uint32), exp.vel[oe].view(np.uint32))
+
+
+@pytest.mark.timeout(600)
+def test_xzy_linearisation_slabs_along_y_match_single_domain_bitwise():
+    """bench.py --gpus N and the reference's own multi-GPU DamBreak3D split along Y; with the xzy cell linearisation y is
+    the slowest hash digit. Same bitwise comparison as above on that linearisation, 3 ranks."""
+    import oracle_binding as ob
+    steps, world = 12, 3
+    params, parts = make_problem("xzy")
+    assert list(params.coord) == [0, 2, 1]
+    ref = ob.OracleWorker(params, parts)
+    for _ in range(steps):
+        ref.step()
+    exp = ref.download()
+    with tempfile.TemporaryDirectory() as d:
+        port = 27500 + (os.getpid() % 2000)
+        mp.spawn(_rank_main, args=(world, port, steps, d, True, "xzy"), nprocs=world, join=True)
         r = [np.load(os.path.join(d, f"rank{k}.npz")) for k in range(world)]
     ids = np.concatenate([ids_of(r[k]["info"]) for k in range(world)])
     assert np.array_equal(np.sort(ids), np.arange(parts.n))

@@ -400,6 +400,35 @@ def test_time_stepping_tracks_oracle(name):
     assert np.abs(got.vel[og, 3] - exp.vel[oe, 3]).max() < (2e-5 if name == "dambreak" else 1e-6)
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: not yet run on a GPU box. The xzy "
+                   "linearisation itself has run on 2 / 4 / 8 GPUs (bench.py --gpus N; same list totals as yzx on one GPU, "
+                   "profiles/r02_scaling.json) and in the CPU multi-rank test; this is the single-GPU comparison with the oracle")
+def test_xzy_linearisation_tracks_oracle():
+    """The cell linearisation bench.py uses on N > 1 GPUs (xzy: y slowest) on ONE GPU against the oracle: list bit-exact,
+    12 steps within the drift bounds of test_time_stepping_tracks_oracle."""
+    params, parts = dambreak_problem(0.03, densitydiffusion=capi.RHODIFF_FERRARI, density_diff_coeff=0.1, coord=(0, 2, 1))
+    assert list(params.coord) == [0, 2, 1]
+    w = Worker(params, parts, 0, clobber=True)
+    ref = ob.OracleWorker(params, parts)
+    w.build_neibs(); ref.build_neibs()
+    n = w.numParticles
+    assert np.array_equal(host(w.hash[:n], np.uint32), ref.download().hash)
+    assert np.array_equal(host(neibs_list_rows(w.neibslist), np.uint16)[:, :n], ref.neibslist[:, :n])
+    for _ in range(12):
+        dt = w.dt
+        w.step()
+        ref.step(dt=dt)
+    got, exp = w.download(), ref.download()
+    gp, ep = global_positions(params, got.pos, got.hash), global_positions(params, exp.pos, exp.hash)
+    ids_g = (got.info[:, 3].astype(np.int64) << 16) | got.info[:, 2]
+    ids_e = (exp.info[:, 3].astype(np.int64) << 16) | exp.info[:, 2]
+    og, oe = np.argsort(ids_g), np.argsort(ids_e)
+    assert np.array_equal(ids_g[og], ids_e[oe])
+    assert np.abs(gp[og] - ep[oe]).max() < 1e-5 * float(params.deltap)
+    assert np.abs(got.vel[og, :3] - exp.vel[oe, :3]).max() < 1e-4 * np.abs(exp.vel[:, :3]).max()
+    assert np.abs(got.vel[og, 3] - exp.vel[oe, 3]).max() < 2e-5
+
+
 @pytest.mark.timeout(900)
 def test_list_layout_independence_at_benchmark_size():
     """DamBreak3D at the north-star size (--deltap 0.0026: 7.87 M particles, BASELINE configs' headline): the default list layout (blocks

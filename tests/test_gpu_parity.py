@@ -400,9 +400,6 @@ def test_time_stepping_tracks_oracle(name):
     assert np.abs(got.vel[og, 3] - exp.vel[oe, 3]).max() < (2e-5 if name == "dambreak" else 1e-6)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: not yet run on a GPU box. The xzy "
-                   "linearisation itself has run on 2 / 4 / 8 GPUs (bench.py --gpus N; same list totals as yzx on one GPU, "
-                   "profiles/r02_scaling.json) and in the CPU multi-rank test; this is the single-GPU comparison with the oracle")
 def test_xzy_linearisation_tracks_oracle():
     """The cell linearisation bench.py uses on N > 1 GPUs (xzy: y slowest) on ONE GPU against the oracle: list bit-exact,
     12 steps within the drift bounds of test_time_stepping_tracks_oracle."""

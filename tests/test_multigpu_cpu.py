@@ -55,8 +55,12 @@ def _rank_main(rank, world, port, steps, outdir, device_dt=False, periodic=False
         if own0 is None:
             own0 = w.numOwn
     out = w.download_own()
+    # the piece table of the host-resident step (SlabWorker.step_host): pieces of ~40 particles for this small system
+    os.environ["B200SPH_SLAB_HOST_PIECE"] = "40"
+    pieces = np.array(w._inner_stripes(), dtype=np.int64).reshape(-1, 2)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), pos=out.pos, vel=out.vel, info=out.info, hash=out.hash,
-             dts=np.array(dts), own0=own0, slab=np.array(w.slab), inter=w.total_interactions)
+             dts=np.array(dts), own0=own0, slab=np.array(w.slab), inter=w.total_interactions,
+             pieces=pieces, edge_start=w.edge_start, S=w.S)
     dist.destroy_process_group()
 
 
@@ -169,6 +173,16 @@ def test_two_rank_gloo_run_matches_single_domain_bitwise(device_dt):
     assert int(r[0]["own0"]) != r[0]["pos"].shape[0], "test problem should move particles across the slab face"
     # interactions counted once
     assert int(r[0]["inter"]) + int(r[1]["inter"]) > 0
+    # the pieces of the host-resident step: they tile the inner stripe [0, edge_start), and every boundary is the first
+    # particle of a cell layer (so that the neighbours of a piece lie in the adjacent pieces, the edge stripe or the halo)
+    for k in range(2):
+        pc, e0 = r[k]["pieces"], int(r[k]["edge_start"])
+        e0 = min(e0, r[k]["pos"].shape[0])
+        assert pc.shape[0] >= 2 and pc[0, 0] == 0 and pc[-1, 1] == e0
+        assert np.array_equal(pc[1:, 0], pc[:-1, 1]) and (pc[:, 1] > pc[:, 0]).all()
+        layer = (r[k]["hash"].astype(np.int64) & 0x3FFFFFFF) // int(r[k]["S"])
+        for b in pc[1:, 0]:
+            assert layer[b] != layer[b - 1], "a piece must start with a cell layer"
     pos = np.concatenate([r[k]["pos"] for k in range(2)])
     vel = np.concatenate([r[k]["vel"] for k in range(2)])
     hashv = np.concatenate([r[k]["hash"] for k in range(2)]) & 0x3FFFFFFF
